@@ -1,0 +1,189 @@
+// C-ABI glue: version / status / device check, covariance entry points and the host-buffer
+// convenience layer (lfm_*_host) with its scratch-caching handle.
+#include <cstdlib>
+#include <cstring>
+#include "lfm_common.cuh"
+
+int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X, const double* Y, int G,
+                         const double* theta, double* out, int64_t ld);
+
+extern "C" int lfm_abi_version(void) { return LFM_ABI_VERSION; }
+
+extern "C" const char* lfm_status_string(int status) {
+  switch (status) {
+    case LFM_OK: return "ok";
+    case LFM_ERR_INVALID: return "invalid argument";
+    case LFM_ERR_CUDA: return "CUDA runtime error";
+    case LFM_ERR_UNSUPPORTED: return "unsupported size";
+    case LFM_ERR_WORKSPACE: return "workspace too small";
+    case LFM_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int lfm_device_check(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return LFM_ERR_NO_DEVICE; }
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return LFM_ERR_NO_DEVICE; }
+  return p.major == 10 ? LFM_OK : LFM_ERR_NO_DEVICE;
+}
+
+extern "C" int lfm_cross_covariance(lfm_stream_t stream, int64_t N, int64_t M, const double* X, const double* Y,
+                                    int G, const double* theta, double* out, int64_t ld_out) {
+  if (N < 0 || M < 0 || G <= 0 || !theta) return LFM_ERR_INVALID;
+  if (N == 0 || M == 0) return LFM_OK;  // empty block: nothing to write
+  if (!X || !Y || !out || ld_out < M) return LFM_ERR_INVALID;
+  return lfm_launch_cross_cov((cudaStream_t)stream, N, M, X, Y, G, theta, out, ld_out);
+}
+
+extern "C" int lfm_gram(lfm_stream_t stream, int64_t N, const double* X, int G, const double* theta, double* out,
+                        int64_t ld_out) {
+  return lfm_cross_covariance(stream, N, N, X, X, G, theta, out, ld_out);
+}
+
+// ---- host-buffer layer --------------------------------------------------------------------------
+struct lfm_handle {
+  cudaStream_t stream;
+  void* ws; size_t ws_bytes;       // device scratch (grown on demand)
+  double* dbuf; size_t dbuf_bytes;  // device staging for inputs / outputs
+  double* hpin; size_t hpin_bytes;  // pinned host staging
+  int* dinfo;
+};
+
+static int ensure(void** p, size_t* have, size_t need, bool pinned_host) {
+  if (*have >= need) return LFM_OK;
+  if (*p) { if (pinned_host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
+  cudaError_t e = pinned_host ? cudaMallocHost(p, need) : cudaMalloc(p, need);
+  if (e != cudaSuccess) { cudaGetLastError(); return LFM_ERR_CUDA; }
+  *have = need;
+  return LFM_OK;
+}
+
+extern "C" int lfm_handle_create(lfm_handle** out) {
+  if (!out) return LFM_ERR_INVALID;
+  LFM_TRY(lfm_device_check());
+  lfm_handle* h = (lfm_handle*)calloc(1, sizeof(lfm_handle));
+  if (!h) return LFM_ERR_INVALID;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { free(h); return LFM_ERR_CUDA; }
+  if (cudaMalloc((void**)&h->dinfo, 4096 * sizeof(int)) != cudaSuccess) { cudaStreamDestroy(h->stream); free(h); return LFM_ERR_CUDA; }
+  *out = h;
+  return LFM_OK;
+}
+
+extern "C" int lfm_handle_destroy(lfm_handle* h) {
+  if (!h) return LFM_OK;
+  cudaStreamSynchronize(h->stream);
+  if (h->ws) cudaFree(h->ws);
+  if (h->dbuf) cudaFree(h->dbuf);
+  if (h->hpin) cudaFreeHost(h->hpin);
+  if (h->dinfo) cudaFree(h->dinfo);
+  cudaStreamDestroy(h->stream);
+  free(h);
+  return LFM_OK;
+}
+
+static size_t r2(size_t n) { return (n + 1) & ~(size_t)1; }
+
+extern "C" int lfm_nlml_grad_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
+                                  const double* theta, double jitter, int unconstrained, double* out, int* info) {
+  if (!h || N <= 0 || G <= 0 || !X || !y || !theta || !out) return LFM_ERR_INVALID;
+  const size_t P = 3 * (size_t)G + 2;
+  const size_t nin = r2(3 * (size_t)N) + r2((size_t)N) + r2(P);
+  const size_t nout = r2(1 + P);
+  LFM_TRY(ensure(&h->ws, &h->ws_bytes, lfm_nlml_workspace_bytes(N, G), false));
+  LFM_TRY(ensure((void**)&h->dbuf, &h->dbuf_bytes, (nin + nout) * 8, false));
+  LFM_TRY(ensure((void**)&h->hpin, &h->hpin_bytes, (nin + nout) * 8, true));
+  double* hp = h->hpin;
+  memcpy(hp, X, 3 * (size_t)N * 8);
+  memcpy(hp + r2(3 * (size_t)N), y, (size_t)N * 8);
+  memcpy(hp + r2(3 * (size_t)N) + r2((size_t)N), theta, P * 8);
+  LFM_CUDA_OK(cudaMemcpyAsync(h->dbuf, hp, nin * 8, cudaMemcpyHostToDevice, h->stream));
+  double* dX = h->dbuf;
+  double* dy = dX + r2(3 * (size_t)N);
+  double* dth = dy + r2((size_t)N);
+  double* dout = h->dbuf + nin;
+  int st = unconstrained ? lfm_nlml_grad_unc(h->stream, N, G, dX, dy, dth, jitter, h->ws, h->ws_bytes, dout, h->dinfo)
+                         : lfm_nlml_grad(h->stream, N, G, dX, dy, dth, jitter, h->ws, h->ws_bytes, dout, h->dinfo);
+  if (st != LFM_OK) return st;
+  LFM_CUDA_OK(cudaMemcpyAsync(hp + nin, dout, (1 + P) * 8, cudaMemcpyDeviceToHost, h->stream));
+  int hinfo = 0;
+  LFM_CUDA_OK(cudaMemcpyAsync(&hinfo, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  LFM_CUDA_OK(cudaStreamSynchronize(h->stream));
+  memcpy(out, hp + nin, (1 + P) * 8);
+  if (info) *info = hinfo;
+  return LFM_OK;
+}
+
+extern "C" int lfm_latent_posterior_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
+                                         const double* variances, const double* theta, double jitter,
+                                         int64_t Tstar, const double* Xstar, double* out_mean, double* out_var,
+                                         int* info) {
+  if (!h || N <= 0 || G <= 0 || Tstar <= 0 || !X || !y || !variances || !theta || !Xstar || !out_mean || !out_var)
+    return LFM_ERR_INVALID;
+  const size_t P = 3 * (size_t)G + 2;
+  const size_t oX = 0, oy = oX + r2(3 * (size_t)N), ov = oy + r2((size_t)N), oth = ov + r2((size_t)N),
+               oXs = oth + r2(P), nin = oXs + r2(3 * (size_t)Tstar);
+  const size_t nout = 2 * r2((size_t)Tstar);
+  LFM_TRY(ensure(&h->ws, &h->ws_bytes, lfm_latent_posterior_workspace_bytes(N, G, Tstar), false));
+  LFM_TRY(ensure((void**)&h->dbuf, &h->dbuf_bytes, (nin + nout) * 8, false));
+  LFM_TRY(ensure((void**)&h->hpin, &h->hpin_bytes, (nin + nout) * 8, true));
+  double* hp = h->hpin;
+  memcpy(hp + oX, X, 3 * (size_t)N * 8);
+  memcpy(hp + oy, y, (size_t)N * 8);
+  memcpy(hp + ov, variances, (size_t)N * 8);
+  memcpy(hp + oth, theta, P * 8);
+  memcpy(hp + oXs, Xstar, 3 * (size_t)Tstar * 8);
+  LFM_CUDA_OK(cudaMemcpyAsync(h->dbuf, hp, nin * 8, cudaMemcpyHostToDevice, h->stream));
+  double* d = h->dbuf;
+  double* dmean = d + nin;
+  double* dvar = dmean + r2((size_t)Tstar);
+  LFM_TRY(lfm_latent_posterior(h->stream, N, G, d + oX, d + oy, d + ov, d + oth, jitter, Tstar, d + oXs, h->ws,
+                               h->ws_bytes, dmean, dvar, h->dinfo));
+  LFM_CUDA_OK(cudaMemcpyAsync(hp + nin, dmean, nout * 8, cudaMemcpyDeviceToHost, h->stream));
+  int hinfo = 0;
+  LFM_CUDA_OK(cudaMemcpyAsync(&hinfo, h->dinfo, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  LFM_CUDA_OK(cudaStreamSynchronize(h->stream));
+  memcpy(out_mean, hp + nin, (size_t)Tstar * 8);
+  memcpy(out_var, hp + nin + r2((size_t)Tstar), (size_t)Tstar * 8);
+  if (info) *info = hinfo;
+  return LFM_OK;
+}
+
+extern "C" int lfm_batched_fit_host(lfm_handle* h, int64_t B, int64_t N, int G, const double* X, const double* y,
+                                    const double* theta0, double jitter, double lr, double b1, double b2,
+                                    double eps, int steps, int fix_params, int steps_per_epoch, double* out_theta,
+                                    double* out_hist, int* info) {
+  if (!h || B <= 0 || N <= 0 || G <= 0 || steps < 0 || !X || !y || !theta0 || !out_theta) return LFM_ERR_INVALID;
+  const size_t P = 3 * (size_t)G + 2;
+  const size_t oX = 0, oy = oX + r2(3 * (size_t)N), oth = oy + r2((size_t)N), nin = oth + r2((size_t)B * P);
+  const size_t ou = nin, oadam = ou + r2((size_t)B * P), ohist = oadam + r2(2 * (size_t)B * P),
+               ntot = ohist + r2((size_t)B * (size_t)(steps > 0 ? steps : 1));
+  LFM_TRY(ensure((void**)&h->dbuf, &h->dbuf_bytes, ntot * 8, false));
+  LFM_TRY(ensure((void**)&h->hpin, &h->hpin_bytes, ntot * 8, true));
+  int* dinfo = nullptr;
+  if (B > 4096) { LFM_CUDA_OK(cudaMalloc((void**)&dinfo, (size_t)B * sizeof(int))); } else dinfo = h->dinfo;
+  double* hp = h->hpin;
+  memcpy(hp + oX, X, 3 * (size_t)N * 8);
+  memcpy(hp + oy, y, (size_t)N * 8);
+  memcpy(hp + oth, theta0, (size_t)B * P * 8);
+  LFM_CUDA_OK(cudaMemcpyAsync(h->dbuf, hp, nin * 8, cudaMemcpyHostToDevice, h->stream));
+  double* d = h->dbuf;
+  int st = lfm_unconstrain(h->stream, B, G, d + oth, d + ou);
+  if (st == LFM_OK)
+    st = lfm_batched_fit(h->stream, B, N, G, d + oX, d + oy, d + ou, d + oadam, jitter, lr, b1, b2, eps, 0, steps,
+                         steps, fix_params, steps_per_epoch, d + ohist, steps, d + oth, dinfo);
+  // d + oth (the start points, dead after lfm_unconstrain) receives the constrained result
+  if (st == LFM_OK) {
+    cudaMemcpyAsync(hp + ou, d + oth, (size_t)B * P * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (steps > 0 && out_hist) cudaMemcpyAsync(hp + ohist, d + ohist, (size_t)B * steps * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (info) cudaMemcpyAsync(info, dinfo, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) st = LFM_ERR_CUDA;
+  }
+  if (st == LFM_OK) {
+    memcpy(out_theta, hp + ou, (size_t)B * P * 8);
+    if (steps > 0 && out_hist) memcpy(out_hist, hp + ohist, (size_t)B * steps * 8);
+  }
+  if (B > 4096) cudaFree(dinfo);
+  return st;
+}

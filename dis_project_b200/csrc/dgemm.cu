@@ -1,0 +1,185 @@
+// FP64 tensor-core GEMM for sm_100a: C = alpha * op(A) op(B) + beta * C (row-major).
+//
+// tcgen05.mma has no f64 kind, so the Blackwell FP64 tensor path is the warp-level
+// mma.sync.aligned.m8n8k4.f64 (SASS DMMA.8x8x4; ptxas lowers the m16n8k{4,8,16} f64 shapes to the
+// same instruction on sm_100a).  128 x 128 x 16 CTA tile, 8 warps of 64 x 32, 4-stage cp.async
+// (LDGSTS) pipeline into padded shared memory so that every fragment read is bank-conflict free
+// in both operand orientations.  Per-tile k-ranges (kmode) let the same kernel serve every
+// triangular Level-3 shape of the blocked Cholesky / inverse (SYRK, TRMM, LAUUM, TRSM via
+// inverted diagonal blocks) without multiplying structural zeros at tile granularity.
+#include "lfm_common.cuh"
+
+#define BM 128
+#define BN 128
+#define BK 16
+#define STAGES 4
+#define LDK (BK + 4)    // [row][k] layout, 20 doubles per row
+#define LDM (BM + 4)    // [k][row] layout, 132 doubles per row
+#define STAGE_DOUBLES (BM * LDK)  // 2560 doubles = 20480 B >= 16*132 = 2112
+#define GEMM_SMEM_BYTES (2 * STAGES * STAGE_DOUBLES * 8)
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// Load one operand tile (128 "rows" x 16 k) into a stage.
+//  TRANS == 0: operand stored [row][k] in global (k contiguous)  -> smem [row][LDK]
+//  TRANS == 1: operand stored [k][row] in global (row contiguous) -> smem [k][LDM]
+template <int TRANS>
+__device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t row0,
+                                          int64_t k0, int tid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int id = tid + 256 * i;
+    if (TRANS == 0) {
+      const int r = id >> 3, kc = id & 7;
+      cp_async16(s + r * LDK + kc * 2, g + (row0 + r) * ld + k0 + kc * 2);
+    } else {
+      const int kr = id >> 6, mc = id & 63;
+      cp_async16(s + kr * LDM + mc * 2, g + (k0 + kr) * ld + row0 + mc * 2);
+    }
+  }
+}
+
+template <int TA, int TBN>  // TA: op(A)=A^T ; TBN = 1 when B is stored N x K ("NT"), 0 when stored K x N
+__global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
+  extern __shared__ __align__(16) double smem[];
+  double* sA = smem;
+  double* sB = smem + STAGES * STAGE_DOUBLES;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  int tm, tn;
+  if (g.lower_only) {
+    // blockIdx.x enumerates lower-triangle tiles, largest rows first (they carry the longest k-ranges)
+    const int64_t total = (int64_t)gridDim.x;
+    const int64_t t = total - 1 - (int64_t)blockIdx.x;
+    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    while ((i + 1) * (i + 2) / 2 <= t) ++i;
+    while (i * (i + 1) / 2 > t) --i;
+    tm = (int)i;
+    tn = (int)(t - i * (i + 1) / 2);
+  } else {
+    tm = blockIdx.x / tiles_n;
+    tn = blockIdx.x % tiles_n;
+  }
+  const int64_t row0 = (int64_t)tm * BM, col0 = (int64_t)tn * BN;
+  int64_t kb = 0, ke = g.K;
+  switch (g.kmode) {
+    case LFM_K_LE_ROW: ke = min(g.K, row0 + BM); break;
+    case LFM_K_GE_COL: kb = col0; break;
+    case LFM_K_GE_ROW: kb = row0; break;
+    case LFM_K_GE_ROWCOL: kb = max(row0, col0); break;
+    default: break;
+  }
+  const int nk = (int)((ke - kb) / BK);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+  const int wm = (warp >> 2) * 64;
+  const int wn = (warp & 3) * 32;
+  const int fr = lane >> 2, fc = lane & 3;
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nk) {
+      load_tile<TA>(sA + s * STAGE_DOUBLES, g.A, g.lda, row0, kb + (int64_t)s * BK, tid);
+      load_tile<TBN ? 0 : 1>(sB + s * STAGE_DOUBLES, g.B, g.ldb, col0, kb + (int64_t)s * BK, tid);
+    }
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    {
+      const int nx = kt + STAGES - 1;
+      if (nx < nk) {
+        const int slot = nx % STAGES;
+        load_tile<TA>(sA + slot * STAGE_DOUBLES, g.A, g.lda, row0, kb + (int64_t)nx * BK, tid);
+        load_tile<TBN ? 0 : 1>(sB + slot * STAGE_DOUBLES, g.B, g.ldb, col0, kb + (int64_t)nx * BK, tid);
+      }
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % STAGES) * STAGE_DOUBLES;
+    const double* b_s = sB + (kt % STAGES) * STAGE_DOUBLES;
+#pragma unroll
+    for (int k4 = 0; k4 < BK; k4 += 4) {
+      double af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (TA == 0) af[i] = a_s[(wm + i * 8 + fr) * LDK + k4 + fc];
+        else af[i] = a_s[(k4 + fc) * LDM + wm + i * 8 + fr];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (TBN) bf[j] = b_s[(wn + j * 8 + fr) * LDK + k4 + fc];
+        else bf[j] = b_s[(k4 + fc) * LDM + wn + j * 8 + fr];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue: thread holds C[row = 8i + lane/4][col = 8j + 2*(lane%4) + {0,1}]
+  const double alpha = g.alpha, beta = g.beta;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = row0 + wm + i * 8 + fr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = col0 + wn + j * 8 + fc * 2;
+      double2* p = reinterpret_cast<double2*>(g.C + r * g.ldc + c);
+      double2 o;
+      o.x = alpha * acc[i][j][0];
+      o.y = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        const double2 old = *p;
+        o.x += beta * old.x;
+        o.y += beta * old.y;
+      }
+      *p = o;
+    }
+  }
+}
+
+template <int TA, int TBN>
+static int launch(cudaStream_t st, const LfmGemm& g) {
+  static bool configured = false;
+  if (!configured) {
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  const int64_t tm = g.M / BM, tn = g.N / BN;
+  int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  if (tiles <= 0) return LFM_OK;
+  if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
+  lfm_dgemm_kernel<TA, TBN><<<(unsigned)tiles, 256, GEMM_SMEM_BYTES, st>>>(g, (int)tn);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
+
+int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
+  if (g.M % BM || g.N % BN || g.K % BK) return LFM_ERR_INVALID;
+  if (g.lower_only && g.M != g.N) return LFM_ERR_INVALID;
+  if (g.transA == 0 && g.transB == 1) return launch<0, 1>(st, g);
+  if (g.transA == 0 && g.transB == 0) return launch<0, 0>(st, g);
+  if (g.transA == 1 && g.transB == 0) return launch<1, 0>(st, g);
+  return launch<1, 1>(st, g);
+}

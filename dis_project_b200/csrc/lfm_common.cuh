@@ -1,0 +1,77 @@
+// Shared declarations for the LFM sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lfm_b200.h"
+
+#define LFM_SQRT_PI 1.7724538509055160273
+#define LFM_TWO_OVER_SQRT_PI 1.1283791670955125739
+#define LFM_LOG_2PI 1.8378770664093454836
+
+#define LFM_CUDA_OK(expr)                          \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return LFM_ERR_CUDA;    \
+  } while (0)
+
+#define LFM_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != LFM_OK) return _s; \
+  } while (0)
+
+// Dense block size: every dense matrix is padded to a multiple of LFM_NB rows/cols.
+#define LFM_NB 128
+
+static inline int64_t lfm_round_up(int64_t n, int64_t m) { return (n + m - 1) / m * m; }
+
+// theta layout (device, constrained): [d(G), s(G), b(G), l, sigma]
+struct LfmTheta {
+  const double* d;
+  const double* s;
+  const double* b;
+  const double* l;      // pointer to scalar
+  const double* sigma;  // pointer to scalar
+};
+
+static inline LfmTheta lfm_theta_view(const double* theta, int G) {
+  LfmTheta t;
+  t.d = theta;
+  t.s = theta + G;
+  t.b = theta + 2 * G;
+  t.l = theta + 3 * G;
+  t.sigma = theta + 3 * G + 1;
+  return t;
+}
+
+// ---- dense primitives (dgemm.cu / chol.cu) -------------------------------------------------
+// C[M x N] = alpha * op(A) op(B) + beta * C, row-major, M,N multiples of 128, K multiple of 16.
+// kmode restricts the k-range per output tile (triangular operands):
+enum LfmKMode {
+  LFM_K_FULL = 0,
+  LFM_K_LE_ROW = 1,   // k <  row_tile_end          (A lower-triangular, op(A) = A)
+  LFM_K_GE_COL = 2,   // k >= col_tile_start        (B lower-triangular, op(B) = B, NN)
+  LFM_K_GE_ROW = 3,   // k >= row_tile_start        (op(A) = A^T with A lower-triangular)
+  LFM_K_GE_ROWCOL = 4 // k >= max(row, col) start   (A^T A with A lower-triangular)
+};
+struct LfmGemm {
+  int transA, transB;  // op(A) = A (M x K row-major) or A^T (A stored K x M row-major); same for B (op(B) is K x N;
+                       // transB=1 means B stored N x K row-major, i.e. the "NT" form)
+  int64_t M, N, K;
+  const double* A; int64_t lda;
+  const double* B; int64_t ldb;
+  double* C; int64_t ldc;
+  double alpha, beta;
+  int lower_only;      // skip output tiles strictly above the diagonal (requires square tiling of C)
+  int kmode;
+};
+int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
+
+// In-place lower Cholesky of A (n x n, ld, n multiple of 128); writes inverse diagonal blocks
+// (and, through the recursion, nothing else) into W's diagonal blocks.  info (device int) receives
+// 0 or the 1-based failing pivot.
+int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info);
+// W = L^-1 (lower) given L and the inverse diagonal blocks already in W's diagonal.
+int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw);
+// S(lower) = W^T W, out of place.
+int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds);

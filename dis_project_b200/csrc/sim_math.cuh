@@ -1,0 +1,150 @@
+// Single-input-motif (SIM) covariance arithmetic, fp64, device side.
+//
+// Restates src/model.py:197-369 of the reference (k_xx :197-235, k_xf :237-282, k_ff :284-312,
+// h :315-365, gamma :367-369) in a factored form: everything that depends on one point only is
+// computed once per point (LfmPoint), the per-pair work is 2 exp + 4 erf for a k_xx entry.
+#pragma once
+#include "lfm_common.cuh"
+
+// Per-point derived quantities for a gene-expression row (t, gene j):
+struct LfmPoint {
+  double t;     // time
+  double d;     // D_j
+  double s;     // S_j
+  double gam;   // gamma_j = D_j l / 2                         (model.py:367-369)
+  double eg2;   // exp(gamma_j^2)
+  double erfg;  // erf(gamma_j)
+  double e;     // exp(-D_j t)
+  double q;     // erf(t/l - gamma_j) + erf(gamma_j)           ("second_erf_terms", model.py:355-357)
+  double g3;    // 2/sqrt(pi) exp(-(t/l - gamma_j)^2)           (gradient only)
+  double g4;    // 2/sqrt(pi) exp(-gamma_j^2)                   (gradient only)
+  int gene;     // resolved gene index
+  int flag;     // 1 gene expression, 0 latent force
+};
+
+// jnp integer indexing semantics for the gene column (model.py:223-224): negative wraps, then clamp.
+__device__ __forceinline__ int lfm_resolve_gene(double gcol, int G) {
+  int g = (int)gcol;
+  if (g < 0) g += G;
+  g = g < 0 ? 0 : g;
+  g = g >= G ? G - 1 : g;
+  return g;
+}
+
+__device__ __forceinline__ LfmPoint lfm_make_point(const double* __restrict__ row3, int G,
+                                                   const double* __restrict__ d,
+                                                   const double* __restrict__ s, double l, bool grad) {
+  LfmPoint p;
+  p.t = row3[0];
+  p.gene = lfm_resolve_gene(row3[1], G);
+  p.flag = ((int)row3[2]) != 0;
+  p.d = d[p.gene];
+  p.s = s[p.gene];
+  p.gam = p.d * l * 0.5;
+  p.eg2 = exp(p.gam * p.gam);
+  p.erfg = erf(p.gam);
+  p.e = exp(-p.d * p.t);
+  const double x3 = p.t / l - p.gam;
+  p.q = erf(x3) + p.erfg;
+  if (grad) {
+    p.g3 = LFM_TWO_OVER_SQRT_PI * exp(-x3 * x3);
+    p.g4 = LFM_TWO_OVER_SQRT_PI * exp(-p.gam * p.gam);
+  } else {
+    p.g3 = 0.0;
+    p.g4 = 0.0;
+  }
+  return p;
+}
+
+// H(a,b,u,v) = h(j=a, k=b, t1=u, t2=v) of model.py:315-365, with "b" the gene whose gamma enters.
+// pa is the point (u, gene a), pb the point (v, gene b).
+//   H = E0 (A1 R1 - A2 R2),  E0 = exp(gam_b^2)/(d_a+d_b), A1 = exp(-d_b (v-u)),
+//   R1 = erf((v-u)/l - gam_b) + erf(u/l + gam_b), A2 = exp(-(d_b v + d_a u)) = e_a e_b, R2 = q_b.
+template <bool GRAD>
+__device__ __forceinline__ void lfm_h(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
+                                      double& H, double& dH_da, double& dH_db, double& dH_dl) {
+  const double delta = pb.t - pa.t;
+  const double inv = 1.0 / (pa.d + pb.d);
+  const double E0 = pb.eg2 * inv;
+  const double A1 = exp(-pb.d * delta);
+  const double x1 = delta * inv_l - pb.gam;
+  const double x2 = pa.t * inv_l + pb.gam;
+  const double R1 = erf(x1) + erf(x2);
+  const double A2 = pa.e * pb.e;
+  const double R2 = pb.q;
+  const double A1R1 = A1 * R1;
+  const double A2R2 = A2 * R2;
+  H = E0 * (A1R1 - A2R2);
+  if (GRAD) {
+    const double g1 = LFM_TWO_OVER_SQRT_PI * exp(-x1 * x1);
+    const double g2 = LFM_TWO_OVER_SQRT_PI * exp(-x2 * x2);
+    const double g3 = pb.g3, g4 = pb.g4;
+    const double hl = 0.5 * l;
+    const double hd = 0.5 * pb.d;
+    const double il2 = inv_l * inv_l;
+    dH_da = -H * inv + E0 * pa.t * A2R2;
+    dH_db = H * (pb.gam * l - inv) +
+            E0 * (-delta * A1R1 + A1 * hl * (g2 - g1) + pb.t * A2R2 - A2 * hl * (g4 - g3));
+    dH_dl = H * pb.gam * pb.d + E0 * (A1 * (g1 * (-delta * il2 - hd) + g2 * (-pa.t * il2 + hd)) -
+                                      A2 * (g3 * (-pb.t * il2 - hd) + g4 * hd));
+  }
+}
+
+// k_xx between gene point pi = (t, j) and gene point pj = (t', k)  (model.py:197-235):
+//   S_j S_k (sqrt(pi) l / 2) [ h(k, j, t', t) + h(j, k, t, t') ]
+__device__ __forceinline__ double lfm_kxx(const LfmPoint& pi, const LfmPoint& pj, double l, double inv_l) {
+  double H1, H2, u0, u1, u2;
+  lfm_h<false>(pj, pi, l, inv_l, H1, u0, u1, u2);  // h(k, j, t', t): a = col gene, b = row gene
+  lfm_h<false>(pi, pj, l, inv_l, H2, u0, u1, u2);  // h(j, k, t, t'): a = row gene, b = col gene
+  return pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l) * (H1 + H2);
+}
+
+// k_xx and the partials of it with respect to D of the ROW gene, D of the COLUMN gene and l.
+// (dk/dS_row = k / S_row, dk/dS_col = k / S_col are formed by the caller.)
+__device__ __forceinline__ void lfm_kxx_grad(const LfmPoint& pi, const LfmPoint& pj, double l, double inv_l,
+                                             double& k, double& dk_drow, double& dk_dcol, double& dk_dl) {
+  double H1, dH1_da, dH1_db, dH1_dl, H2, dH2_da, dH2_db, dH2_dl;
+  lfm_h<true>(pj, pi, l, inv_l, H1, dH1_da, dH1_db, dH1_dl);
+  lfm_h<true>(pi, pj, l, inv_l, H2, dH2_da, dH2_db, dH2_dl);
+  const double mult = pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l);
+  k = mult * (H1 + H2);
+  dk_drow = mult * (dH1_db + dH2_da);
+  dk_dcol = mult * (dH1_da + dH2_db);
+  dk_dl = mult * (dH1_dl + dH2_dl) + k * inv_l;
+}
+
+// k_xf between gene point pg = (t_gene, j) and a latent time (model.py:237-282).
+__device__ __forceinline__ double lfm_kxf(const LfmPoint& pg, double t_latent, double l, double inv_l) {
+  const double t_dist = pg.t - t_latent;
+  return (0.5 * l * LFM_SQRT_PI * pg.s) * pg.eg2 * exp(-pg.d * t_dist) *
+         (erf(t_dist * inv_l - pg.gam) + erf(t_latent * inv_l + pg.gam));
+}
+
+// k_ff, latent RBF with the reference's 2*l denominator (model.py:304-312).
+__device__ __forceinline__ double lfm_kff(double t, double tp, double l) {
+  const double dt = t - tp;
+  return exp(-(dt * dt) / (2.0 * l));
+}
+
+// ExactLFM.kernel (model.py:152-195).  Only the branch the 0/1 switches select is evaluated;
+// identical to the reference's blend whenever the discarded branches are finite.
+__device__ __forceinline__ double lfm_kernel(const LfmPoint& pi, const LfmPoint& pj, double l, double inv_l) {
+  if (pi.flag & pj.flag) return lfm_kxx(pi, pj, l, inv_l);
+  if (pi.flag) return lfm_kxf(pi, pj.t, l, inv_l);
+  if (pj.flag) return lfm_kxf(pj, pi.t, l, inv_l);
+  return lfm_kff(pi.t, pj.t, l);
+}
+
+// ---- bijectors (tfp Softplus / Sigmoid(0.5, 3.5); model.py:66,79,86,93,111) -----------------
+#define LFM_L_LOW 0.5
+#define LFM_L_HIGH 3.5
+__device__ __forceinline__ double lfm_softplus(double x) { return fmax(x, 0.0) + log1p(exp(-fabs(x))); }
+__device__ __forceinline__ double lfm_softplus_inv(double y) { return y + log(-expm1(-y)); }
+__device__ __forceinline__ double lfm_sigmoid(double x) { return 0.5 * (1.0 + tanh(0.5 * x)); }
+__device__ __forceinline__ double lfm_l_forward(double x) {
+  return LFM_L_LOW + (LFM_L_HIGH - LFM_L_LOW) * lfm_sigmoid(x);
+}
+__device__ __forceinline__ double lfm_l_inverse(double y) {
+  const double u = (y - LFM_L_LOW) / (LFM_L_HIGH - LFM_L_LOW);
+  return log(u) - log1p(-u);
+}

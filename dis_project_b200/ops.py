@@ -1,0 +1,251 @@
+"""Device-level operators: torch CUDA tensors in, torch CUDA tensors out, CUDA kernels through the
+C-ABI in between.  torch is plumbing only (device memory, streams); no torch op is on the compute
+path.  All calls are stream-ordered on torch's current stream and do not synchronise.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t) -> torch.Tensor:
+    """Accept numpy / torch input, return a contiguous fp64 CUDA tensor."""
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=F64)
+    if t.dtype != F64:
+        t = t.to(F64)
+    if not t.is_cuda:
+        _lib.require_device()
+        t = t.cuda()
+    return t.contiguous()
+
+
+def _rows3(X: torch.Tensor, name: str) -> torch.Tensor:
+    X = _dev(X)
+    if X.ndim != 2 or X.shape[1] != 3:
+        raise ValueError(f"{name} must have shape (n, 3) = [time, gene_index, flag] (dataset.py:391), got {tuple(X.shape)}")
+    return X
+
+
+def _theta(theta: torch.Tensor, G: int) -> torch.Tensor:
+    theta = _dev(theta).reshape(-1)
+    if theta.numel() != 3 * G + 2:
+        raise ValueError(f"theta must hold 3G+2={3 * G + 2} values [d,s,b,l,sigma], got {theta.numel()}")
+    return theta
+
+
+_WS: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device: torch.device, tag: str) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WS.pop(key, None)
+        buf = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _WS.clear()
+
+
+# ------------------------------------------------------------------------------------------------
+def cross_covariance(X, Y, theta, G: int) -> torch.Tensor:
+    """ExactLFM.cross_covariance(kernel, x, y) (reference src/model.py:372-394)."""
+    X, Y = _rows3(X, "x"), _rows3(Y, "y")
+    theta = _theta(theta, G)
+    N, M = X.shape[0], Y.shape[0]
+    out = torch.empty((N, M), dtype=F64, device=X.device)
+    if N == 0 or M == 0:
+        return out
+    _lib.check(_lib.lib().lfm_cross_covariance(_stream(), N, M, X.data_ptr(), Y.data_ptr(), G, theta.data_ptr(),
+                                               out.data_ptr(), M), "lfm_cross_covariance")
+    return out
+
+
+def gram(X, theta, G: int) -> torch.Tensor:
+    """ExactLFM.gram(kernel, x) as a dense array (reference src/model.py:396-414)."""
+    return cross_covariance(X, X, theta, G)
+
+
+def mean_function(X, theta, G: int) -> torch.Tensor:
+    """ExactLFM.mean_function(x) (reference src/model.py:124-149); shape (N, 1)."""
+    X = _rows3(X, "x")
+    theta = _theta(theta, G)
+    N = X.shape[0]
+    if N % G:
+        raise ValueError(f"mean_function: {N} rows is not divisible by num_genes={G} (model.py:145-149)")
+    out = torch.empty((N, 1), dtype=F64, device=X.device)
+    _lib.check(_lib.lib().lfm_mean_function(_stream(), N, X.data_ptr(), G, theta.data_ptr(), out.data_ptr()),
+               "lfm_mean_function")
+    return out
+
+
+def constrain(theta_unc, G: int) -> torch.Tensor:
+    u = _dev(theta_unc)
+    P = 3 * G + 2
+    B = u.numel() // P
+    out = torch.empty_like(u)
+    _lib.check(_lib.lib().lfm_constrain(_stream(), B, G, u.data_ptr(), out.data_ptr()), "lfm_constrain")
+    return out
+
+
+def unconstrain(theta, G: int) -> torch.Tensor:
+    t = _dev(theta)
+    P = 3 * G + 2
+    B = t.numel() // P
+    out = torch.empty_like(t)
+    _lib.check(_lib.lib().lfm_unconstrain(_stream(), B, G, t.data_ptr(), out.data_ptr()), "lfm_unconstrain")
+    return out
+
+
+def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int):
+    X = _rows3(X, "x")
+    y = _dev(y).reshape(-1)
+    theta = _theta(theta, G)
+    N = X.shape[0]
+    if y.numel() != N:
+        raise ValueError(f"y has {y.numel()} values for {N} input rows")
+    if N % G:
+        raise ValueError(f"{N} rows is not divisible by num_genes={G} (model.py:145-149)")
+    l = _lib.lib()
+    nbytes = l.lfm_nlml_workspace_bytes(N, G)
+    ws = _workspace(nbytes, X.device, "nlml")
+    out = torch.empty(nout, dtype=F64, device=X.device)
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    _lib.check(getattr(l, fn_name)(_stream(), N, G, X.data_ptr(), y.data_ptr(), theta.data_ptr(), float(jitter),
+                                   ws.data_ptr(), ws.numel(), out.data_ptr(), info.data_ptr()), fn_name)
+    return out, info
+
+
+def nlml(X, y, theta, jitter: float, G: int):
+    """CustomConjMLL(negative=True) value (reference src/objectives.py:21-78).  Returns (val[1], info[1])."""
+    return _nlml_call("lfm_nlml", X, y, theta, jitter, G, 1)
+
+
+def nlml_grad(X, y, theta, jitter: float, G: int):
+    """NLML and d NLML / d theta in constrained coordinates.  Returns (out[1+P], info[1])."""
+    return _nlml_call("lfm_nlml_grad", X, y, theta, jitter, G, 3 * G + 3)
+
+
+def nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
+    """jax.value_and_grad(JaxTrainer.loss) w.r.t. the unconstrained leaves (reference src/trainer.py:126)."""
+    return _nlml_call("lfm_nlml_grad_unc", X, y, theta_unc, jitter, G, 3 * G + 3)
+
+
+def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):
+    """ExactLFM.latent_predict (reference src/model.py:420-463): returns (mean[T*], var[T*], info[1])."""
+    X = _rows3(X, "x")
+    Xs = _rows3(Xstar, "test_inputs")
+    y = _dev(y).reshape(-1)
+    variances = _dev(variances).reshape(-1)
+    theta = _theta(theta, G)
+    N, T = X.shape[0], Xs.shape[0]
+    if y.numel() != N or variances.numel() != N:
+        raise ValueError("y / variances do not match the number of training rows")
+    if N % G:
+        raise ValueError(f"{N} rows is not divisible by num_genes={G} (model.py:145-149)")
+    l = _lib.lib()
+    mean = torch.empty(T, dtype=F64, device=X.device)
+    var = torch.empty(T, dtype=F64, device=X.device)
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    if T == 0:
+        return mean, var, info
+    nbytes = l.lfm_latent_posterior_workspace_bytes(N, G, T)
+    ws = _workspace(nbytes, X.device, "post")
+    _lib.check(l.lfm_latent_posterior(_stream(), N, G, X.data_ptr(), y.data_ptr(), variances.data_ptr(),
+                                      theta.data_ptr(), float(jitter), T, Xs.data_ptr(), ws.data_ptr(), ws.numel(),
+                                      mean.data_ptr(), var.data_ptr(), info.data_ptr()), "lfm_latent_posterior")
+    return mean, var, info
+
+
+def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
+    """B independent value_and_grad evaluations.  theta_unc (B, P) -> (val[B], grad[B,P], info[B])."""
+    X = _rows3(X, "x")
+    y = _dev(y).reshape(-1)
+    u = _dev(theta_unc)
+    P = 3 * G + 2
+    if u.ndim != 2 or u.shape[1] != P:
+        raise ValueError(f"theta_unc must be (B, {P})")
+    B, N = u.shape[0], X.shape[0]
+    val = torch.empty(B, dtype=F64, device=X.device)
+    grad = torch.empty((B, P), dtype=F64, device=X.device)
+    info = torch.zeros(B, dtype=torch.int32, device=X.device)
+    if B == 0:
+        return val, grad, info
+    _lib.check(_lib.lib().lfm_batched_nlml_grad_unc(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), u.data_ptr(),
+                                                    float(jitter), val.data_ptr(), grad.data_ptr(), info.data_ptr()),
+               "lfm_batched_nlml_grad_unc")
+    return val, grad, info
+
+
+class BatchedFitState:
+    """Device-resident state of B independent fits (iterates, Adam moments, loss history)."""
+
+    def __init__(self, theta0, G: int, total_steps: int):
+        theta0 = _dev(theta0)
+        self.G, self.P = G, 3 * G + 2
+        if theta0.ndim != 2 or theta0.shape[1] != self.P:
+            raise ValueError(f"theta0 must be (B, {self.P}) constrained start points")
+        self.B = theta0.shape[0]
+        self.total_steps = int(total_steps)
+        dev = theta0.device
+        self.u = unconstrain(theta0, G)  # trainer.py:75
+        self.adam = torch.zeros((self.B, 2 * self.P), dtype=F64, device=dev)
+        self.hist = torch.full((self.B, max(1, self.total_steps)), float("nan"), dtype=F64, device=dev)
+        self.theta = torch.empty((self.B, self.P), dtype=F64, device=dev)
+        self.info = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        self.step = 0
+
+
+def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
+                      b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
+                      steps_per_epoch: int = 1000) -> None:
+    """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216)."""
+    X = _rows3(X, "x")
+    y = _dev(y).reshape(-1)
+    if state.B == 0 or steps <= 0:
+        return
+    steps = min(steps, state.total_steps - state.step)
+    _lib.check(_lib.lib().lfm_batched_fit(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
+                                          state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
+                                          state.step, steps, state.total_steps, int(bool(fix_params)),
+                                          int(steps_per_epoch), state.hist.data_ptr(), state.hist.shape[1],
+                                          state.theta.data_ptr(), state.info.data_ptr()), "lfm_batched_fit")
+    state.step += steps
+
+
+def debug_dgemm_nt(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """C = A B^T through the library's DMMA kernel (roofline helper)."""
+    A, B = _dev(A), _dev(B)
+    M, K = A.shape
+    N = B.shape[0]
+    Cm = torch.empty((M, N), dtype=F64, device=A.device)
+    _lib.check(_lib.lib().lfm_debug_dgemm_nt(_stream(), M, N, K, A.data_ptr(), B.data_ptr(), Cm.data_ptr()),
+               "lfm_debug_dgemm_nt")
+    return Cm
+
+
+def debug_potrf_potri(A: torch.Tensor, want_inverse: bool = True):
+    """In-place Cholesky (+ inverse) of a dense SPD matrix; returns (L, Sinv_lower or None, info)."""
+    A = _dev(A)
+    n = A.shape[0]
+    W = torch.zeros_like(A)
+    Sinv = torch.zeros_like(A) if want_inverse else None
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    _lib.check(_lib.lib().lfm_debug_potrf_potri(_stream(), n, A.data_ptr(), W.data_ptr(),
+                                                Sinv.data_ptr() if want_inverse else None, info.data_ptr()),
+               "lfm_debug_potrf_potri")
+    return A, Sinv, info

@@ -1,0 +1,159 @@
+/* lfm_b200.h -- C-ABI of the B200-native latent-force-model (LFM) hot path.
+ *
+ * Drop-in boundary for wejpurvis/DIS_project's GP latent force model.  The reference has no FFI
+ * of its own: its "operator API" is four Python call shapes.  Every entry point
+ * below names the reference call site (file:line under the reference repo) whose numerics it
+ * replaces; INTEGRATION.md shows the reference-side binding (jax.ffi / ctypes).
+ *
+ * Conventions
+ *   - all arithmetic is IEEE fp64 (the reference runs with jax_enable_x64, src/dataset.py:18);
+ *   - every pointer is a DEVICE pointer unless the function name ends in _host;
+ *   - calls are stream-ordered on `stream` (a cudaStream_t passed as void*), never synchronise,
+ *     never allocate: scratch comes from the caller through the *_workspace_bytes queries;
+ *   - inputs X / Xstar are the reference's (n,3) row-major arrays [time, gene_index, flag]
+ *     (src/dataset.py:358-399, src/utils.py:268-287), gene index and flag stored as doubles;
+ *   - theta is the CONSTRAINED hyper-parameter vector [true_d(G), true_s(G), true_b(G), l,
+ *     obs_stddev] (src/model.py:64-121), P = 3G+2 doubles; theta_unc is the same vector in the
+ *     unconstrained space of the tfp bijectors (softplus on all but l, Sigmoid(0.5,3.5) on l);
+ *   - return value: LFM_OK or a negative lfm_status.  Numerical failure (Sigma not positive
+ *     definite) is reported asynchronously through the device word `info` (0 = ok, k>0 = 1-based
+ *     failing pivot), exactly like LAPACK; the outputs are then NaN, as in the reference
+ *     (JAX's Cholesky returns NaN instead of raising).
+ */
+#ifndef LFM_B200_H
+#define LFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lfm_stream_t; /* cudaStream_t */
+
+typedef enum lfm_status {
+  LFM_OK = 0,
+  LFM_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size, N % G != 0 ...) */
+  LFM_ERR_CUDA = -2,        /* a CUDA runtime call failed; cudaGetLastError has the detail      */
+  LFM_ERR_UNSUPPORTED = -3, /* size outside what the kernels support (e.g. batched N > 128)     */
+  LFM_ERR_WORKSPACE = -4,   /* workspace too small                                             */
+  LFM_ERR_NO_DEVICE = -5    /* no sm_100 device: there is NO CPU fallback                       */
+} lfm_status;
+
+#define LFM_ABI_VERSION 1
+
+int lfm_abi_version(void);
+const char* lfm_status_string(int status);
+/* LFM_OK iff the current CUDA device exists and is compute capability 10.x. */
+int lfm_device_check(void);
+
+/* ---- (a) covariance blocks ------------------------------------------------------------------ */
+
+/* ExactLFM.cross_covariance(kernel, x, y) with ExactLFM.kernel (src/model.py:372-394, 152-195):
+ * flag-switched blend of k_xx (:197-235), k_xf (:237-282) and k_ff (:284-312).  out is N x M
+ * row-major with leading dimension ld_out >= M. */
+int lfm_cross_covariance(lfm_stream_t stream, int64_t N, int64_t M, const double* X, const double* Y,
+                         int G, const double* theta, double* out, int64_t ld_out);
+
+/* ExactLFM.gram(kernel, x) (src/model.py:396-414) == cross_covariance(x, x), full N x N. */
+int lfm_gram(lfm_stream_t stream, int64_t N, const double* X, int G, const double* theta, double* out,
+             int64_t ld_out);
+
+/* ExactLFM.mean_function(x) (src/model.py:124-149): (B/D)[i / (N/G)] * flag_i.  N % G must be 0. */
+int lfm_mean_function(lfm_stream_t stream, int64_t N, const double* X, int G, const double* theta,
+                      double* out);
+
+/* tfp bijector forward / inverse applied leaf-wise, as gpjax Module.constrain()/unconstrain()
+ * (src/trainer.py:75,103,218; bijectors at src/model.py:66,79,86,93,111).  B vectors of P=3G+2. */
+int lfm_constrain(lfm_stream_t stream, int64_t B, int G, const double* theta_unc, double* theta);
+int lfm_unconstrain(lfm_stream_t stream, int64_t B, int G, const double* theta, double* theta_unc);
+
+/* ---- (b,c) objective and its gradient ------------------------------------------------------- */
+
+size_t lfm_nlml_workspace_bytes(int64_t N, int G);
+
+/* CustomConjMLL(negative=True)(model, Dataset(X, y)) (src/objectives.py:21-78):
+ * Sigma = K + jitter I + sigma^2 I; out[0] = 1/2 [N log 2pi + log det Sigma + z^T Sigma^-1 z]. */
+int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+             const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info);
+
+/* jax.value_and_grad(JaxTrainer.loss) (src/trainer.py:86-103,126) in CONSTRAINED coordinates:
+ * out[0] = NLML, out[1..P] = dNLML/dtheta.  dK/dtheta blocks are contracted with
+ * K_bar = 1/2 (Sigma^-1 - alpha alpha^T) on the fly and never materialised. */
+int lfm_nlml_grad(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                  const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info);
+
+/* Same, differentiated w.r.t. the UNCONSTRAINED leaves -- the exact quantity the optimiser in
+ * src/trainer.py:126-128 consumes.  out[0] = NLML, out[1..P] = gradient. */
+int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                      const double* theta_unc, double jitter, void* ws, size_t ws_bytes, double* out,
+                      int* info);
+
+/* ---- (d) latent posterior -------------------------------------------------------------------- */
+
+size_t lfm_latent_posterior_workspace_bytes(int64_t N, int G, int64_t Tstar);
+
+/* ExactLFM.latent_predict(test_inputs, train_data) (src/model.py:420-463):
+ * Sigma_p = K + diag(variances) + jitter I; mean = mean_t + K_fx Sigma_p^-1 (y - mean_x);
+ * var_i = k(t*_i,t*_i) + 2 jitter - k_i^T Sigma_p^-1 k_i.  Only the diagonal of the predictive
+ * covariance is produced (the reference builds T* x T* and keeps the diagonal, :459-461). */
+int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                         const double* variances, const double* theta, double jitter, int64_t Tstar,
+                         const double* Xstar, void* ws, size_t ws_bytes, double* out_mean,
+                         double* out_var, int* info);
+
+/* ---- batched multi-start path (many independent small LFMs per GPU) -------------------------- */
+
+/* B independent value_and_grad evaluations sharing (X, y): theta_unc is B x P, out_val B,
+ * out_grad B x P, info B ints.  N <= 128. */
+int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                              const double* y, const double* theta_unc, double jitter, double* out_val,
+                              double* out_grad, int* info);
+
+/* B independent JaxTrainer.fit loops (src/trainer.py:162-228) with optax.adam(lr) restated
+ * (b1,b2,eps as given; src/main.py:45) and the "fix p21" hook of trainer.py:133-160,205-210,218-220.
+ * theta_unc_io is B x P UNCONSTRAINED (in: start / current iterate, out: iterate after the last step
+ * of this call).  The fit may be split into chunks of steps [first_step, first_step + steps) of a
+ * total_steps-long fit (with a collective in between); adam_state (B x 2P doubles: m then v) carries
+ * the moments between calls and may be NULL only when the whole fit is one call.  out_hist
+ * (B x ld_hist) receives the loss at every step at column first_step + s.  When the call reaches
+ * total_steps, out_theta (B x P, may be NULL) receives constrain(theta_unc) with the constrained-space
+ * hook of trainer.py:218-220 applied. */
+int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                    double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
+                    double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
+                    int steps_per_epoch, double* out_hist, int64_t ld_hist, double* out_theta, int* info);
+
+/* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
+ * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */
+
+typedef struct lfm_handle lfm_handle;
+int lfm_handle_create(lfm_handle** out);
+int lfm_handle_destroy(lfm_handle* h);
+
+int lfm_nlml_grad_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
+                       const double* theta, double jitter, int unconstrained, double* out, int* info);
+int lfm_latent_posterior_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
+                              const double* variances, const double* theta, double jitter,
+                              int64_t Tstar, const double* Xstar, double* out_mean, double* out_var,
+                              int* info);
+int lfm_batched_fit_host(lfm_handle* h, int64_t B, int64_t N, int G, const double* X, const double* y,
+                         const double* theta0, double jitter, double lr, double b1, double b2,
+                         double eps, int steps, int fix_params, int steps_per_epoch, double* out_theta,
+                         double* out_hist, int* info);
+
+/* ---- diagnostics used by bench.py for the roofline denominators ------------------------------ */
+
+/* Plain C = A B^T fp64 GEMM through the library's own DMMA kernel (M,N % 128 == 0, K % 16 == 0). */
+int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int64_t K, const double* A,
+                       const double* B, double* C);
+/* In-place dense lower Cholesky / inverse of an n x n row-major matrix (n % 128 == 0): after the
+ * call A holds L (lower), and if Sinv != NULL it receives Sigma^-1 (lower triangle valid).
+ * W is an n x n scratch matrix. */
+int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv, int* info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LFM_B200_H */
