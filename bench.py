@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the LFM hot path (BASELINE.json metric: NLML+grad evaluations / second, fp64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at every N: BASELINE config 2, synthetic LFM 50 genes x 80 time points (N = 4000), one
+"step" = one NLML + gradient evaluation at the reference's initial hyper-parameters.  A single
+large-N evaluation does not shard (north_star: "no cross-GPU split"), so --gpus N runs N independent
+replicas (weak scaling, no data-path collective); the batched multi-start path, which does shard,
+is reported beside it under "secondary" (4096 p53-shaped restarts x 150 Adam steps over all ranks
+with its per-chunk all-reduce), together with the N = 32768 evaluation (config 3) on rank 0.
+
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy/scipy/LAPACK with all
+host threads) on the same config; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+G_C2, T_C2 = 50, 80          # config 2: N = 4000
+G_C3, T_C3 = 256, 128        # config 3: N = 32768
+JITTER = 1e-4
+METRIC = "LFM NLML+grad evals/sec (fp64), N=4000 (50 genes x 80 time points)"
+UNIT = "evals/s"
+
+
+# synthetic inputs built here so that the product arm never imports oracle/
+class _Inputs:
+    @staticmethod
+    def make_problem(G, T, seed=42):
+        times = np.linspace(0.0, 12.0, T)
+        X = np.stack((np.tile(times, G), np.repeat(np.arange(G), T).astype(np.float64), np.ones(G * T)), axis=-1)
+        rng = np.random.default_rng(seed)
+        d = rng.uniform(0.2, 1.0, G)
+        b = rng.uniform(0.01, 0.1, G)
+        # y = mean + smooth latent response + unit noise: cheap O(N) draw with the right scales
+        f = np.interp(times, np.linspace(0, 12, 7), [0.18, 1.18, 1.62, 0.82, 0.69, -0.18, 0.51])
+        y = np.repeat(b / d, T) + np.tile(f, G) * np.repeat(rng.uniform(0.5, 1.5, G), T) + rng.standard_normal(G * T)
+        theta = np.concatenate([np.full(G, 0.4), np.full(G, 1.0), np.full(G, 0.05), [2.5, 1.0]])
+        return X, y, theta
+
+
+
+def clocks_start(path):
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    try:
+        fh = open(path, "w")
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                stdout=fh, stderr=subprocess.DEVNULL)
+    except Exception:
+        return None
+
+
+def clocks_parse(path, dev_index):
+    sm, mx, reasons = [], [], set()
+    try:
+        for line in open(path):
+            p = [c.strip() for c in line.split(",")]
+            if len(p) < 9 or not p[0].isdigit() or int(p[0]) != dev_index:
+                continue
+            sm.append(float(p[1])); mx.append(float(p[2]))
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+    except Exception:
+        pass
+    if not sm:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    # "under load": the upper half of the samples (idle samples before/after the region drop out)
+    load = sorted(sm)[len(sm) // 2:]
+    return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of the reference path on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import lfm_oracle as o
+    X, y, theta = _Inputs.make_problem(G_C2, T_C2)
+    p = o.Params.unpack(theta, JITTER)
+    cores = os.cpu_count() or 1
+    budget = 150.0
+    t0 = time.perf_counter(); o.nlml_and_grad(p, X, y, threads=cores); t1 = time.perf_counter() - t0
+    warm_done = 1
+    while warm_done < args.warmup and (warm_done + 1) * t1 < 0.25 * budget:
+        o.nlml_and_grad(p, X, y, threads=cores); warm_done += 1
+    steps_exec = int(max(1, min(args.steps, (budget - warm_done * t1) // max(t1, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps_exec):
+        o.nlml_and_grad(p, X, y, threads=cores)
+    dt = time.perf_counter() - t0
+    val = steps_exec / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "steps_executed": steps_exec, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / steps_exec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad", "N": 4000,
+                       "G": G_C2, "T": T_C2},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps_exec} full NLML+grad evaluations at N=4000 (oracle/lfm_oracle.py, "
+                                       "numpy+scipy+LAPACK, row chunks over all host threads)"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true", help="skip the batched / N=32768 secondary measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dis_project_b200 import _lib, ops
+    from dis_project_b200.batched import make_restarts, multi_start_fit
+    from dis_project_b200.dataset import JaxP53Data, dataset_3d
+
+    _lib.require_device()
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- inputs resident in HBM --------------------------------------------------------------------
+    Xh, yh, thh = _Inputs.make_problem(G_C2, T_C2, seed=42 + rank)  # every replica its own data
+    N = Xh.shape[0]
+    P = 3 * G_C2 + 2
+    X, y, th = (torch.as_tensor(a).to(dev) for a in (Xh, yh, thh))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        return ops.nlml_grad(X, y, th, JITTER, G_C2)
+
+    # ---- FP64 roofline denominator: cuBLAS Dgemm, measured here (MEASURED_PEAKS.json has no FP64 entry) ----
+    peak_tf = None
+    if rank == 0:
+        n = 8192
+        A = torch.randn(n, n, dtype=torch.float64, device=dev)
+        Bm = torch.randn(n, n, dtype=torch.float64, device=dev)
+        torch.matmul(A, Bm)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(A, Bm); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        peak_tf = 2 * n**3 / best / 1e12
+        del A, Bm
+        torch.cuda.empty_cache()
+
+    # ---- warm-up, then the timed region ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        out, info = step()
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0 and bool(torch.isfinite(out).all()), "warm-up evaluation failed"
+    clk_path = os.path.join(tempfile.gettempdir(), f"lfm_clocks_{rank}.csv")
+    clk = clocks_start(clk_path) if rank == 0 else None
+    time.sleep(0.3 if clk else 0.0)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    launches0 = lib.lfm_debug_launch_count()
+    wall0 = time.perf_counter()
+    for e0, e1 in evs:
+        flush.zero_()           # L2 flush between timed iterations (outside the per-step events)
+        e0.record()
+        out, info = step()
+        e1.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = lib.lfm_debug_launch_count() - launches0
+    dev_s = sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
+    dev_s = max_over_ranks(dev_s)
+    value = world * args.steps / dev_s
+
+    # ---- e2e: the host-buffer C-ABI call (H2D of X, y, theta and D2H of NLML+grad inside the timed region) ----
+    import ctypes as C
+    h = C.c_void_p()
+    _lib.check(lib.lfm_handle_create(C.byref(h)), "lfm_handle_create")
+    out_h = np.empty(1 + P)
+    info_h = C.c_int(0)
+
+    def host_step():
+        _lib.check(lib.lfm_nlml_grad_host(h, N, G_C2, Xh.ctypes.data, yh.ctypes.data, thh.ctypes.data, JITTER, 0,
+                                          out_h.ctypes.data, C.byref(info_h)), "lfm_nlml_grad_host")
+
+    for _ in range(args.warmup):
+        host_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = world * args.steps / e2e_s
+    assert abs(out_h[0] - float(out[0].item())) <= 1e-9 * abs(out_h[0]), "host and device entry points disagree"
+    lib.lfm_handle_destroy(h)
+    if clk:
+        clk.terminate(); clk.wait()
+
+    # ---- roofline of the dominant kernel (lfm_dgemm_kernel, DMMA): CUDA events around every launch -----------
+    roof = None
+    if rank == 0:
+        lib.lfm_debug_profile_begin()
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(args.steps):
+            step()
+        pe1.record()
+        ms, fl, nl = C.c_double(0), C.c_double(0), C.c_longlong(0)
+        _lib.check(lib.lfm_debug_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)), "profile_end")
+        alg_flops = float(N) ** 3  # N^3/3 (POTRF) + 2N^3/3 (explicit inverse) per evaluation
+        gemm_s = ms.value * 1e-3 / args.steps
+        achieved = alg_flops / gemm_s / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_r1.json"))).get("dgemm_dram_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "lfm_dgemm_kernel (mma.sync m8n8k4 f64 = SASS DMMA)", "achieved": achieved,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": traffic,
+                "peak_source": "cuBLAS Dgemm 8192^3 best of 5, measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                "algorithmic_flops_per_eval": alg_flops, "executed_flops_per_eval": fl.value / args.steps,
+                "launches_per_eval": nl.value / args.steps, "kernel_s_per_eval": gemm_s,
+                "kernel_share_of_step": gemm_s / (pe0.elapsed_time(pe1) * 1e-3 / args.steps),
+                "step_tflops": alg_flops / (dev_s / args.steps) / 1e12}
+
+    # ---- secondary: batched multi-start (config 4, sharded) and N = 32768 (config 3) ----------------------
+    secondary = {}
+    if not args.no_secondary:
+        data = JaxP53Data.synthetic()
+        xb, yb, _ = dataset_3d(data)
+        TH = make_restarts(np.concatenate([np.full(5, 0.4), np.ones(5), np.full(5, 0.05), [2.5, 1.0]]), 4096)
+        multi_start_fit(xb, yb.reshape(-1), TH[: 64 * world], JITTER, num_iters=5, chunk=5)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        res = multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, chunk=10)
+        bt = max_over_ranks(time.perf_counter() - t0)
+        secondary["batched"] = {"workload": "config 4: 4096 p53-shaped restarts (N=105, G=5) x 150 Adam steps, sharded "
+                                            f"over {world} GPU(s), best-objective all-reduce every 10 steps",
+                                "restarts_per_s": 4096 / bt, "seconds": bt, "best_nlml": res.best_loss,
+                                "evals_per_s": 4096 * 150 / bt}
+        if rank == 0:
+            try:
+                X3h, y3h, th3h = _Inputs.make_problem(G_C3, T_C3)
+                X3, y3, th3 = (torch.as_tensor(a).to(dev) for a in (X3h, y3h, th3h))
+                ops.nlml_grad(X3, y3, th3, JITTER, G_C3)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); o3, i3 = ops.nlml_grad(X3, y3, th3, JITTER, G_C3); e1.record(); torch.cuda.synchronize()
+                s3 = e0.elapsed_time(e1) * 1e-3
+                secondary["n32768"] = {"workload": "config 3: 256 genes x 128 time points (N=32768) NLML+grad",
+                                       "evals_per_s": 1.0 / s3, "seconds": s3, "dense_tflops": 32768.0**3 / s3 / 1e12,
+                                       "frac_of_dgemm_peak": 32768.0**3 / s3 / 1e12 / peak_tf if peak_tf else None,
+                                       "info": int(i3.item()), "finite": bool(torch.isfinite(o3).all())}
+                del X3, y3, th3
+                ops.release_workspaces()
+                torch.cuda.empty_cache()
+            except Exception as exc:  # pragma: no cover
+                secondary["n32768"] = {"error": repr(exc)}
+        barrier()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import lfm_oracle as o
+        cores = os.cpu_count() or 1
+        pc = o.Params.unpack(thh, JITTER)
+        o.nlml_and_grad(pc, Xh, yh, threads=cores)
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            vc, gc = o.nlml_and_grad(pc, Xh, yh, threads=cores)
+        ct = (time.perf_counter() - t0) / reps
+        cpu = {"value": 1.0 / ct, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{reps} full NLML+grad evaluations at N=4000 (oracle/lfm_oracle.py: numpy/scipy/LAPACK, all host threads)",
+               "parity_rel_err_nlml": abs(vc - out_h[0]) / abs(vc),
+               "parity_rel_err_grad": float(np.max(np.abs(gc - out_h[1:])) / np.max(np.abs(gc)))}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad at the "
+                                       "reference's initial hyper-parameters", "N": N, "G": G_C2, "T": T_C2,
+                           "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
+                           "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((4 * N + P) * 8),
+                        "d2h_bytes_per_step": int((1 + P) * 8 + 4), "ms_per_step": 1e3 * e2e_s / args.steps,
+                        "api": "lfm_nlml_grad_host (C-ABI, host buffers)"},
+                "gpu_launches": int(launches), "wall_s_timed_region": wall,
+                "clocks": clocks_parse(clk_path, local), "roofline": roof, "cpu_baseline": cpu, "secondary": secondary}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,7 @@ SIGNATURES = {
     "lfm_device_check": (_int, []),
     "lfm_cross_covariance": (_int, [_ptr, _i64, _i64, _ptr, _ptr, _int, _ptr, _ptr, _i64]),
     "lfm_gram": (_int, [_ptr, _i64, _ptr, _int, _ptr, _ptr, _i64]),
+    "lfm_h": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _ptr]),
     "lfm_mean_function": (_int, [_ptr, _i64, _ptr, _int, _ptr, _ptr]),
     "lfm_constrain": (_int, [_ptr, _i64, _int, _ptr, _ptr]),
     "lfm_unconstrain": (_int, [_ptr, _i64, _int, _ptr, _ptr]),
@@ -60,6 +61,9 @@ SIGNATURES = {
                                          _ptr, _ptr]),
     "lfm_batched_fit_host": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                     _int, _int, _int, _ptr, _ptr, _ptr]),
+    "lfm_debug_launch_count": (C.c_ulonglong, []),
+    "lfm_debug_profile_begin": (_int, []),
+    "lfm_debug_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "lfm_debug_dgemm_nt": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "lfm_debug_potrf_potri": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
 }

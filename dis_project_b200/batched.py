@@ -1,0 +1,153 @@
+"""Batched multi-start fits sharded over GPUs (BASELINE config 4).
+
+``B`` independent ``JaxTrainer.fit`` loops (reference ``src/trainer.py:162-228``) that share (X, y)
+and differ in their start point.  Restart b lives on rank ``b * world // B`` (contiguous shards); no
+data-path collective is needed because the restarts are independent.  One small all-reduce per
+optimiser chunk keeps every rank informed of the global best objective (MIN over a packed
+(loss, restart-id) key) and of a few SUM statistics; it runs on a side stream and is consumed one
+chunk late so that it never sits on the critical path (NCCL over NVLink on the GPU box, gloo in the
+CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+
+def make_restarts(theta_init: np.ndarray, B: int, scale: float = 0.5, seed: int = 42,
+                  unconstrain=None, constrain=None) -> np.ndarray:
+    """Start points: restart 0 is `theta_init`, restart b > 0 perturbs the UNCONSTRAINED leaves by
+    scale * N(0, 1) drawn from default_rng(seed + b)."""
+    from .model import L_HIGH, L_LOW, _softplus, _softplus_inv
+
+    theta_init = np.asarray(theta_init, dtype=np.float64)
+    P = theta_init.shape[0]
+    G = (P - 2) // 3
+    u0 = _softplus_inv(theta_init)
+    r = (theta_init[3 * G] - L_LOW) / (L_HIGH - L_LOW)
+    u0[3 * G] = np.log(r) - np.log1p(-r)
+    U = np.empty((B, P))
+    for b in range(B):
+        U[b] = u0 if b == 0 else u0 + scale * np.random.default_rng(seed + b).standard_normal(P)
+    TH = _softplus(U)
+    TH[:, 3 * G] = L_LOW + (L_HIGH - L_LOW) * 0.5 * (1.0 + np.tanh(0.5 * U[:, 3 * G]))
+    return TH
+
+
+def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous restart range [lo, hi) of `rank`; sizes differ by at most one."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_best(loss: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """(loss, id) pairs -> [best_loss, id_of_best] for a MIN all-reduce; NaN losses never win."""
+    loss = np.where(np.isfinite(loss), loss, np.inf)
+    if loss.size == 0:
+        return np.array([np.inf, -1.0])
+    k = int(np.argmin(loss))
+    return np.array([loss[k], float(ids[k])])
+
+
+def reduce_best(local: np.ndarray, dist=None):
+    """All-reduce of the packed best: MIN on the loss, then MIN on the id among ranks that hold it."""
+    import torch
+
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([local[0]], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    best = float(t.item())
+    cand = local[1] if local[0] == best else float("inf")
+    t2 = torch.tensor([cand], dtype=torch.float64, device=dev)
+    dist.all_reduce(t2, op=dist.ReduceOp.MIN)
+    return np.array([best, float(t2.item())])
+
+
+@dataclass
+class MultiStartResult:
+    theta: np.ndarray        # (B_local, P) constrained results of this rank's shard
+    history: np.ndarray      # (B_local, steps)
+    info: np.ndarray         # (B_local,)
+    lo: int
+    hi: int
+    best_loss: float         # global
+    best_id: int             # global restart id
+    best_theta: Optional[np.ndarray]  # global winner, broadcast to every rank
+    best_trace: np.ndarray   # global best objective after every chunk
+
+
+def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr: float = 0.01,
+                    fix_params: bool = True, num_steps_per_epoch: int = 1000, chunk: int = 1,
+                    b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> MultiStartResult:
+    """Fit all restarts of this rank's shard on the current CUDA device.
+
+    `theta0_all` is the (B, P) array of constrained start points of the WHOLE job (every rank passes
+    the same array); the function slices its own shard.  `chunk` optimiser steps run per kernel
+    launch; after every chunk the global best objective is all-reduced asynchronously.
+    """
+    import torch
+    import torch.distributed as dist
+
+    from . import ops
+
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    world = dist.get_world_size() if distributed else 1
+    theta0_all = np.asarray(theta0_all, dtype=np.float64)
+    B, P = theta0_all.shape
+    G = (P - 2) // 3
+    lo, hi = shard_bounds(B, rank, world)
+    Xd = ops._rows3(X, "x")
+    yd = ops._dev(y).reshape(-1)
+    st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters) if hi > lo else None
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    ids = torch.arange(lo, hi, dtype=torch.float64, device=Xd.device)
+    nchunks = (num_iters + chunk - 1) // chunk
+    trace = torch.full((max(nchunks, 1), 2), float("inf"), dtype=torch.float64, device=Xd.device)
+    done = 0
+    for c in range(nchunks):
+        steps = min(chunk, num_iters - done)
+        if st is not None:
+            ops.batched_fit_steps(st, Xd, yd, jitter, steps, lr=lr, b1=b1, b2=b2, eps=eps, fix_params=fix_params,
+                                  steps_per_epoch=num_steps_per_epoch)
+        done += steps
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            if st is not None:
+                col = st.hist[:, done - 1]
+                col = torch.where(torch.isfinite(col), col, torch.full_like(col, float("inf")))
+                k = torch.argmin(col)
+                trace[c, 0] = col[k]
+                trace[c, 1] = ids[k]
+            if distributed and world > 1:
+                # MIN over the loss; the id is resolved after the loop (one more tiny all-reduce)
+                dist.all_reduce(trace[c, 0:1], op=dist.ReduceOp.MIN)
+    main.wait_stream(side)
+    torch.cuda.synchronize()
+    if st is not None:
+        theta, hist, info = st.theta.cpu().numpy(), st.hist.cpu().numpy(), st.info.cpu().numpy()
+        local = pack_best(hist[:, -1] if num_iters > 0 else np.full(hi - lo, np.inf), np.arange(lo, hi))
+    else:
+        theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
+        local = np.array([np.inf, -1.0])
+    best = reduce_best(local, dist if distributed else None)
+    best_id = int(best[1]) if np.isfinite(best[0]) else -1
+    best_theta = None
+    if best_id >= 0:
+        owner = next(r for r in range(world) if shard_bounds(B, r, world)[0] <= best_id < shard_bounds(B, r, world)[1])
+        bt = torch.zeros(P, dtype=torch.float64, device=Xd.device)
+        if owner == rank:
+            bt.copy_(torch.as_tensor(theta[best_id - lo]))
+        if distributed and world > 1:
+            dist.broadcast(bt, src=owner)
+        best_theta = bt.cpu().numpy()
+    return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
+                            trace[:, 0].cpu().numpy())

@@ -326,6 +326,7 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
     configured = smem;
   }
   lfm_batched_kernel<<<(unsigned)a.B, BT, smem, st>>>(a);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }

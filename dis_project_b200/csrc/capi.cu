@@ -7,6 +7,9 @@
 int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X, const double* Y, int G,
                          const double* theta, double* out, int64_t ld);
 
+unsigned long long g_lfm_launches = 0;
+extern "C" unsigned long long lfm_debug_launch_count(void) { return g_lfm_launches; }
+
 extern "C" int lfm_abi_version(void) { return LFM_ABI_VERSION; }
 
 extern "C" const char* lfm_status_string(int status) {

@@ -7,7 +7,7 @@
 // Recursive (cache-oblivious) formulation so that almost all flops land in large DMMA GEMMs:
 //   potrf(A) : potrf(A11); A21 <- A21 L11^-T (recursive TRSM); A22 -= A21 A21^T (SYRK); potrf(A22)
 //   trtri(L) : W21 = -W22 (L21 W11)                        (two triangular GEMMs)
-//   lauum(W) : S11 = W11^T W11 + W21^T W21; S21 = W22^T W21; S22 = W22^T W22
+//   lauum(W) : S_ij = sum_{k >= i} W_ki^T W_kj for every lower tile, one launch
 // The 128 x 128 leaves are factorised AND inverted by one CTA in shared memory; the inverted
 // diagonal blocks turn every leaf-level TRSM into a GEMM.
 #include "lfm_common.cuh"
@@ -95,6 +95,7 @@ static int leaf(cudaStream_t st, double* A, int64_t lda, double* W, int64_t ldw,
     configured = true;
   }
   lfm_potrf_leaf_kernel<<<1, NB, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -158,17 +159,9 @@ int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* 
   return lfm_dgemm(st, mk(0, 1, n2, n1, n2, W22, ldw, Tt, ldw, W21, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW));
 }
 
-// S (lower) = W^T W, out of place.
+// S (lower) = W^T W, out of place: every lower tile (i,j) is an independent TN product over the
+// block rows k >= i, so the whole N^3/3 is ONE launch (W's diagonal blocks have exact zeros above
+// the diagonal, and the scratch that lfm_trtri leaves in W's strict upper blocks is never read).
 int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds) {
-  if (n == NB) {
-    return lfm_dgemm(st, mk(1, 0, NB, NB, NB, W, ldw, W, ldw, S, lds, 1.0, 0.0, 1, LFM_K_FULL));
-  }
-  const int64_t n1 = split(n), n2 = n - n1;
-  const double* W21 = W + n1 * ldw;
-  const double* W22 = W21 + n1;
-  LFM_TRY(lfm_lauum(st, n1, W, ldw, S, lds));
-  LFM_TRY(lfm_dgemm(st, mk(1, 0, n1, n1, n2, W21, ldw, W21, ldw, S, lds, 1.0, 1.0, 1, LFM_K_FULL)));
-  // S21[i][j] = sum_{k >= i} W22[k][i] W21[k][j]
-  LFM_TRY(lfm_dgemm(st, mk(1, 0, n2, n1, n2, W22, ldw, W21, ldw, S + n1 * lds, lds, 1.0, 0.0, 0, LFM_K_GE_ROW)));
-  return lfm_lauum(st, n2, W22, ldw, S + n1 * lds + n1, lds);
+  return lfm_dgemm(st, mk(1, 0, n, n, n, W, ldw, W, ldw, S, lds, 1.0, 0.0, 1, LFM_K_GE_ROWCOL));
 }

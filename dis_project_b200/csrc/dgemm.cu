@@ -62,7 +62,9 @@ __global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_
   if (g.lower_only) {
     // blockIdx.x enumerates lower-triangle tiles, largest rows first (they carry the longest k-ranges)
     const int64_t total = (int64_t)gridDim.x;
-    const int64_t t = total - 1 - (int64_t)blockIdx.x;
+    // longest k-range first: row tiles descending, except when the k-range starts at the row tile
+    const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL);
+    const int64_t t = asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x;
     int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
@@ -158,6 +160,66 @@ __global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_
   }
 }
 
+// ---- optional per-launch timing (CUDA events on the launching stream) -----------------------------
+#include <vector>
+struct GemmProf {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  double flops = 0.0;            // flops the launched tiles execute (tile-granular k-ranges)
+  long long launches = 0;
+};
+static GemmProf g_prof;
+
+static double gemm_exec_flops(const LfmGemm& g) {
+  const int64_t tm = g.M / BM, tn = g.N / BN;
+  double f = 0.0;
+  for (int64_t i = 0; i < tm; ++i) {
+    const int64_t jn = g.lower_only ? (i + 1) : tn;
+    for (int64_t j = 0; j < jn; ++j) {
+      int64_t kb = 0, ke = g.K;
+      const int64_t row0 = i * BM, col0 = j * BN;
+      switch (g.kmode) {
+        case LFM_K_LE_ROW: ke = g.K < row0 + BM ? g.K : row0 + BM; break;
+        case LFM_K_GE_COL: kb = col0; break;
+        case LFM_K_GE_ROW: kb = row0; break;
+        case LFM_K_GE_ROWCOL: kb = row0 > col0 ? row0 : col0; break;
+        default: break;
+      }
+      if (ke > kb) f += 2.0 * BM * BN * (double)(ke - kb);
+    }
+  }
+  return f;
+}
+
+extern "C" int lfm_debug_profile_begin(void) {
+  g_prof.on = true; g_prof.used = 0; g_prof.flops = 0.0; g_prof.launches = 0;
+  return LFM_OK;
+}
+// Synchronises the device; returns summed GEMM kernel time (ms), executed flops and launch count.
+extern "C" int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches) {
+  g_prof.on = false;
+  LFM_CUDA_OK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
+    float t = 0.f;
+    LFM_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (exec_flops) *exec_flops = g_prof.flops;
+  if (launches) *launches = g_prof.launches;
+  return LFM_OK;
+}
+static cudaEvent_t prof_event() {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    g_prof.ev.push_back(e);
+  }
+  return g_prof.ev[g_prof.used++];
+}
+
 template <int TA, int TBN>
 static int launch(cudaStream_t st, const LfmGemm& g) {
   static bool configured = false;
@@ -170,7 +232,14 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   if (tiles <= 0) return LFM_OK;
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
+  if (g_prof.on) {
+    cudaEventRecord(prof_event(), st);
+    g_prof.flops += gemm_exec_flops(g);
+    g_prof.launches += 1;
+  }
   lfm_dgemm_kernel<TA, TBN><<<(unsigned)tiles, 256, GEMM_SMEM_BYTES, st>>>(g, (int)tn);
+  if (g_prof.on) cudaEventRecord(prof_event(), st);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }

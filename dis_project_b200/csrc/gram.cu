@@ -97,6 +97,7 @@ int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X,
   dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT));
   if (grid.y > 65535) return LFM_ERR_UNSUPPORTED;
   lfm_gram_tile_kernel<0><<<grid, dim3(32, 8), 0, st>>>(N, M, X, Y, G, theta, out, ld, nullptr, 0.0, 0, 0);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -108,6 +109,7 @@ int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const doubl
   dim3 grid((unsigned)(Npad / GT), (unsigned)(Npad / GT));
   lfm_gram_tile_kernel<1><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
                                                        add_sigma2, Npad);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -316,6 +318,34 @@ int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G,
                                                                         colpart, pt);
   LFM_CUDA_OK(cudaGetLastError());
   lfm_grad_finish_kernel<<<G + 1, 256, 0, st>>>(N, X, G, theta, pt, lpart, ntile * nchunk, alpha, Sinv, ld, grad);
+  LFM_LAUNCHED(3);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
+
+// Elementwise ExactLFM.h(j, k, t1, t2) (src/model.py:315-365) for n argument tuples.
+__global__ void lfm_h_kernel(int64_t n, const double* __restrict__ j, const double* __restrict__ k,
+                             const double* __restrict__ t1, const double* __restrict__ t2, int G,
+                             const double* __restrict__ theta, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double l = theta[3 * G];
+  double ra[3] = {t1[i], j[i], 1.0};
+  double rb[3] = {t2[i], k[i], 1.0};
+  const LfmPoint pa = lfm_make_point(ra, G, theta, theta + G, l, false);
+  const LfmPoint pb = lfm_make_point(rb, G, theta, theta + G, l, false);
+  double H, u0, u1, u2;
+  lfm_h<false>(pa, pb, l, 1.0 / l, H, u0, u1, u2);
+  out[i] = H;
+}
+
+extern "C" int lfm_h(lfm_stream_t stream, int64_t n, const double* j, const double* k, const double* t1,
+                     const double* t2, int G, const double* theta, double* out) {
+  if (n < 0 || G <= 0 || !theta) return LFM_ERR_INVALID;
+  if (n == 0) return LFM_OK;
+  if (!j || !k || !t1 || !t2 || !out) return LFM_ERR_INVALID;
+  lfm_h_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(n, j, k, t1, t2, G, theta, out);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }

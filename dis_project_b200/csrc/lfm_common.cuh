@@ -20,6 +20,10 @@
     if (_s != LFM_OK) return _s; \
   } while (0)
 
+// Launch accounting (bench.py's gpu_launches) and optional per-launch CUDA-event timing of the GEMM kernel.
+extern unsigned long long g_lfm_launches;
+#define LFM_LAUNCHED(n) (g_lfm_launches += (unsigned long long)(n))
+
 // Dense block size: every dense matrix is padded to a multiple of LFM_NB rows/cols.
 #define LFM_NB 128
 

@@ -130,12 +130,14 @@ static int trsv_rec(cudaStream_t st, int64_t n, const double* L, int64_t ldl, co
                     double* z) {
   if (n == LFM_NB) {
     lfm_leaf_trmv_kernel<<<1, 128, 0, st>>>(Wd, ldw, z);
+    LFM_LAUNCHED(1);
     LFM_CUDA_OK(cudaGetLastError());
     return LFM_OK;
   }
   const int64_t n1 = (n / LFM_NB / 2) * LFM_NB, n2 = n - n1;
   LFM_TRY(trsv_rec(st, n1, L, ldl, Wd, ldw, z));
   lfm_gemv_sub_kernel<<<(unsigned)((n2 + 7) / 8), 256, 0, st>>>(n2, n1, L + n1 * ldl, ldl, z, z + n1);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return trsv_rec(st, n2, L + n1 * ldl + n1, ldl, Wd + n1 * ldw + n1, ldw, z + n1);
 }
@@ -198,6 +200,7 @@ __global__ void lfm_chain_kernel(int G, const double* __restrict__ u, double* __
 int lfm_launch_residual(cudaStream_t st, int64_t N, int64_t Npad, const double* X, const double* y, int G,
                         const double* theta, double* z, double* out_mean) {
   lfm_residual_kernel<<<(unsigned)((Npad + 255) / 256), 256, 0, st>>>(N, Npad, X, y, G, theta, z, out_mean);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -206,11 +209,14 @@ size_t lfm_alpha_part_doubles(int64_t Np) { return (size_t)((Np + TC_ROWS - 1) /
 int lfm_launch_alpha(cudaStream_t st, int64_t Np, const double* W, const double* z, double* w, double* part,
                      double* alpha) {
   lfm_trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, st>>>(Np, W, Np, z, w);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   const int nchunk = (int)((Np + TC_ROWS - 1) / TC_ROWS);
   lfm_trmv_lowerT_kernel<<<dim3((unsigned)(Np / 128), (unsigned)nchunk), 128, 0, st>>>(Np, W, Np, w, part);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   lfm_sum_partials_kernel<<<(unsigned)((Np + 255) / 256), 256, 0, st>>>(Np, nchunk, part, alpha);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -269,6 +275,7 @@ extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, 
   LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, info));
   LFM_TRY(trsv_rec(st, s.Np, s.A, s.Np, s.W, s.Np, s.z));  // z <- L^-1 z
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.z, info, out);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -280,10 +287,12 @@ static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, co
   LFM_TRY(lfm_trtri(st, s.Np, s.A, s.Np, s.W, s.Np));
   LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
   LFM_TRY(lfm_launch_grad_contract(st, N, X, G, theta, s.A, s.Np, s.alpha, s.gscratch, out + 1));
   lfm_poison_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, info, out + 1);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -304,9 +313,11 @@ extern "C" int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const do
   const NlmlWs s = nlml_ws_layout(N, G, ws);
   const int P = 3 * G + 2;
   lfm_constrain_kernel<<<(P + 127) / 128, 128, 0, st>>>(1, G, theta_unc, s.theta);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   LFM_TRY(nlml_grad_impl(st, N, G, X, y, s.theta, jitter, s, out, info));
   lfm_chain_kernel<<<(P + 127) / 128, 128, 0, st>>>(G, theta_unc, out + 1);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -315,6 +326,7 @@ extern "C" int lfm_constrain(lfm_stream_t stream, int64_t B, int G, const double
   if (B <= 0 || G <= 0 || !theta_unc || !theta) return LFM_ERR_INVALID;
   const int64_t n = B * (3 * (int64_t)G + 2);
   lfm_constrain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, G, theta_unc, theta);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -322,6 +334,7 @@ extern "C" int lfm_unconstrain(lfm_stream_t stream, int64_t B, int G, const doub
   if (B <= 0 || G <= 0 || !theta_unc || !theta) return LFM_ERR_INVALID;
   const int64_t n = B * (3 * (int64_t)G + 2);
   lfm_unconstrain_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, G, theta, theta_unc);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -332,6 +345,7 @@ extern "C" int lfm_mean_function(lfm_stream_t stream, int64_t N, const double* X
   if (N % G) return LFM_ERR_INVALID;
   lfm_residual_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(N, N, X, nullptr, G, theta,
                                                                                    nullptr, out);
+  LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }

@@ -151,10 +151,12 @@ extern "C" int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const
     LFM_TRY(lfm_dgemm(st, g));
     lfm_post_colred_kernel<<<dim3((unsigned)(ncp / 128), (unsigned)nrch), 128, 0, st>>>(Np, PC_COLS, s.Kxf, s.V,
                                                                                       PC_COLS, s.alpha, s.pm, s.pq);
+    LFM_LAUNCHED(1);
     LFM_CUDA_OK(cudaGetLastError());
     lfm_post_finish_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(nc, PC_COLS, nrch, s.pm, s.pq, Xstar, t0,
                                                                         Tstar, G, theta, jitter, info, out_mean,
                                                                         out_var);
+    LFM_LAUNCHED(1);
     LFM_CUDA_OK(cudaGetLastError());
   }
   return LFM_OK;

@@ -56,6 +56,19 @@ __device__ __forceinline__ LfmPoint lfm_make_point(const double* __restrict__ ro
   return p;
 }
 
+// erf(a) + erf(b) without catastrophic cancellation.  In h and k_xf this sum multiplies
+// exp(-D dt) with dt < 0 (up to e^13 in the p53 regime) exactly when erf(a) ~ -1 and erf(b) ~ +1
+// (SURVEY Q7): the literal sum then carries ~1e-16 * e^(D|dt|) absolute noise.  For opposite-sign
+// arguments that are both beyond 0.5 the identical quantity erfc(-n) - erfc(p) is used instead.  The
+// oracle (oracle/lfm_oracle.py:erfsum) uses the same rule with the same threshold.
+__device__ __forceinline__ double lfm_erfsum(double a, double b) {
+  if (a * b < 0.0 && fmin(fabs(a), fabs(b)) > 0.5) {
+    const double p = fmax(a, b), n = fmin(a, b);
+    return erfc(-n) - erfc(p);
+  }
+  return erf(a) + erf(b);
+}
+
 // H(a,b,u,v) = h(j=a, k=b, t1=u, t2=v) of model.py:315-365, with "b" the gene whose gamma enters.
 // pa is the point (u, gene a), pb the point (v, gene b).
 //   H = E0 (A1 R1 - A2 R2),  E0 = exp(gam_b^2)/(d_a+d_b), A1 = exp(-d_b (v-u)),
@@ -69,7 +82,7 @@ __device__ __forceinline__ void lfm_h(const LfmPoint& pa, const LfmPoint& pb, do
   const double A1 = exp(-pb.d * delta);
   const double x1 = delta * inv_l - pb.gam;
   const double x2 = pa.t * inv_l + pb.gam;
-  const double R1 = erf(x1) + erf(x2);
+  const double R1 = lfm_erfsum(x1, x2);
   const double A2 = pa.e * pb.e;
   const double R2 = pb.q;
   const double A1R1 = A1 * R1;
@@ -117,7 +130,7 @@ __device__ __forceinline__ void lfm_kxx_grad(const LfmPoint& pi, const LfmPoint&
 __device__ __forceinline__ double lfm_kxf(const LfmPoint& pg, double t_latent, double l, double inv_l) {
   const double t_dist = pg.t - t_latent;
   return (0.5 * l * LFM_SQRT_PI * pg.s) * pg.eg2 * exp(-pg.d * t_dist) *
-         (erf(t_dist * inv_l - pg.gam) + erf(t_latent * inv_l + pg.gam));
+         lfm_erfsum(t_dist * inv_l - pg.gam, t_latent * inv_l + pg.gam);
 }
 
 // k_ff, latent RBF with the reference's 2*l denominator (model.py:304-312).

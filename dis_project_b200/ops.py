@@ -80,6 +80,17 @@ def gram(X, theta, G: int) -> torch.Tensor:
     return cross_covariance(X, X, theta, G)
 
 
+def h_terms(j, k, t1, t2, theta, G: int) -> torch.Tensor:
+    """ExactLFM.h(j, k, t1, t2), elementwise (reference src/model.py:315-365)."""
+    j, k, t1, t2 = (_dev(torch.as_tensor(a, dtype=F64).reshape(-1)) for a in (j, k, t1, t2))
+    theta = _theta(theta, G)
+    n = j.numel()
+    out = torch.empty(n, dtype=F64, device=j.device)
+    _lib.check(_lib.lib().lfm_h(_stream(), n, j.data_ptr(), k.data_ptr(), t1.data_ptr(), t2.data_ptr(), G,
+                                theta.data_ptr(), out.data_ptr()), "lfm_h")
+    return out
+
+
 def mean_function(X, theta, G: int) -> torch.Tensor:
     """ExactLFM.mean_function(x) (reference src/model.py:124-149); shape (N, 1)."""
     X = _rows3(X, "x")

@@ -1,0 +1,45 @@
+"""Host-side helpers that define input layouts (reference ``src/utils.py:237-314``)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def generate_test_times(t: Optional[int] = 100) -> np.ndarray:
+    """(t, 3) latent test inputs [linspace(0, 13, t), -1, 0] (reference utils.py:268-287)."""
+    times = np.linspace(0, 13, t)
+    return np.stack((times, np.repeat(-1.0, t), np.repeat(0.0, t)), axis=-1)
+
+
+def generate_test_times_pred(t: Optional[int] = 100, num_genes: int = 5) -> np.ndarray:
+    """(t * num_genes, 3) gene-expression test inputs with gene indices 1..G and flag 1
+    (reference utils.py:290-314; the off-by-one indices are the reference's)."""
+    times = np.tile(np.linspace(0, 13, t), num_genes)
+    genes = np.repeat(np.arange(1, num_genes + 1), t).astype(np.float64)
+    return np.stack((times, genes, np.ones(times.shape[0])), axis=1)
+
+
+def print_hyperparams(model, dataset, file: Optional[str] = None) -> list:
+    """Table of learned B, S, D per gene plus l (reference utils.py:237-265).  Returns the rows;
+    writes a CSV when `file` is given."""
+    rows = [[name, float(model.true_b[i]), float(model.true_s[i]), float(model.true_d[i])]
+            for i, name in enumerate(dataset.gene_names)]
+    rows.append(["lengthscale", float(np.asarray(model.l)), "", ""])
+    headers = ["Gene", "B", "S", "D"]
+    try:
+        from tabulate import tabulate
+
+        print(tabulate(rows, headers=headers))
+    except Exception:  # pragma: no cover
+        print(headers)
+        for r in rows:
+            print(r)
+    if file:
+        import csv
+
+        with open(file, "w", newline="") as fh:
+            w = csv.writer(fh)
+            w.writerow(headers)
+            w.writerows(rows)
+    return rows

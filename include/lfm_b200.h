@@ -60,6 +60,11 @@ int lfm_cross_covariance(lfm_stream_t stream, int64_t N, int64_t M, const double
 int lfm_gram(lfm_stream_t stream, int64_t N, const double* X, int G, const double* theta, double* out,
              int64_t ld_out);
 
+/* ExactLFM.h(j, k, t1, t2) (src/model.py:315-365), elementwise over n tuples; j, k are gene indices
+ * stored as doubles like the gene column of X. */
+int lfm_h(lfm_stream_t stream, int64_t n, const double* j, const double* k, const double* t1,
+          const double* t2, int G, const double* theta, double* out);
+
 /* ExactLFM.mean_function(x) (src/model.py:124-149): (B/D)[i / (N/G)] * flag_i.  N % G must be 0. */
 int lfm_mean_function(lfm_stream_t stream, int64_t N, const double* X, int G, const double* theta,
                       double* out);
@@ -152,6 +157,14 @@ int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int64_t K, con
  * call A holds L (lower), and if Sinv != NULL it receives Sigma^-1 (lower triangle valid).
  * W is an n x n scratch matrix. */
 int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv, int* info);
+
+/* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
+unsigned long long lfm_debug_launch_count(void);
+/* Bracket every DMMA GEMM launch with CUDA events on its stream between begin and end; end
+ * synchronises the device and reports the summed kernel time, the flops the tiles executed and the
+ * number of launches. */
+int lfm_debug_profile_begin(void);
+int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches);
 
 #ifdef __cplusplus
 }

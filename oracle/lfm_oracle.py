@@ -33,7 +33,7 @@ import math
 from dataclasses import dataclass, field, replace
 
 import numpy as np
-from scipy.special import erf
+from scipy.special import erf, erfc
 from scipy.linalg import cho_solve, cholesky, solve_triangular
 from scipy.linalg.lapack import dpotrf, dpotri
 
@@ -138,6 +138,29 @@ def constrain_jac(theta_unc: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 # kernels (model.py:152-369) -- broadcasting numpy versions
 # --------------------------------------------------------------------------- #
+LITERAL_ERF_SUMS = False  # True: evaluate erf(a)+erf(b) exactly as written in the reference
+
+
+def erfsum(a, b):
+    """erf(a) + erf(b).
+
+    The reference writes the literal sum (model.py:276-278, 349-351).  Where it multiplies
+    exp(-D dt) with dt << 0, erf(a) ~ -1 and erf(b) ~ +1 cancel and the literal form carries
+    ~1e-16 * e^(D |dt|) absolute rounding noise (~2e-11 on O(1) entries in the p53
+    regime, which a posterior mean amplifies to ~1e-9 relative).  Parity to 1e-9 is only defined
+    up to that noise, so the checker evaluates the mathematically identical, cancellation-free
+    erfc(-n) - erfc(p) for opposite-sign arguments beyond 0.5.  `LITERAL_ERF_SUMS = True` restores
+    the reference's literal arithmetic; tests/test_oracle.py bounds the difference between the two.
+    """
+    a, b = np.broadcast_arrays(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64))
+    lit = erf(a) + erf(b)
+    if LITERAL_ERF_SUMS:
+        return lit
+    opp = (a * b < 0.0) & (np.minimum(np.abs(a), np.abs(b)) > 0.5)
+    acc = erfc(-np.minimum(a, b)) - erfc(np.maximum(a, b))
+    return np.where(opp, acc, lit)
+
+
 def gamma(p: Params, k):
     """model.py:367-369."""
     return p.d[k] * p.l / 2.0
@@ -149,7 +172,7 @@ def h(p: Params, j, k, t1, t2):
     g = gamma(p, k)
     multiplier = np.exp(g**2) / (p.d[j] + p.d[k])
     first_multiplier = np.exp(-p.d[k] * t_dist)
-    first_erf_terms = erf(t_dist / p.l - g) + erf(t1 / p.l + g)
+    first_erf_terms = erfsum(t_dist / p.l - g, t1 / p.l + g)
     second_multiplier = np.exp(-(p.d[k] * t2 + p.d[j] * t1))
     second_erf_terms = erf(t2 / p.l - g) + erf(g)
     return multiplier * (first_multiplier * first_erf_terms - second_multiplier * second_erf_terms)
@@ -165,9 +188,8 @@ def kernel_xf(p: Params, t_gene, j, t_latent):
     """model.py:237-282 after the flag-based argument resolution (:262-263)."""
     t_dist = t_gene - t_latent
     g = gamma(p, j)
-    return (0.5 * p.l * SQRT_PI * p.s[j]) * np.exp(g**2) * np.exp(-p.d[j] * t_dist) * (
-        erf(t_dist / p.l - g) + erf(t_latent / p.l + g)
-    )
+    return (0.5 * p.l * SQRT_PI * p.s[j]) * np.exp(g**2) * np.exp(-p.d[j] * t_dist) * erfsum(
+        t_dist / p.l - g, t_latent / p.l + g)
 
 
 def kernel_ff(p: Params, t, tp):
@@ -271,7 +293,7 @@ def _h_partials(p: Params, a, b, u, v):
     E0 = np.exp(g * g) * inv
     A1 = np.exp(-db * delta)
     x1, x2, x3 = delta / l - g, u / l + g, v / l - g
-    R1 = erf(x1) + erf(x2)
+    R1 = erfsum(x1, x2)
     A2 = np.exp(-(db * v + da * u))
     R2 = erf(x3) + erf(g)
     c = 2.0 / SQRT_PI
@@ -286,12 +308,17 @@ def _h_partials(p: Params, a, b, u, v):
     return H, dH_da, dH_db, dH_dl
 
 
-def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 2048):
+def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 256, threads: int | None = None):
     """Closed-form NLML and gradient w.r.t. the CONSTRAINED theta=[d,s,b,l,sigma].
 
     K_bar = 1/2 (S^-1 - a a^T); dNLML/dtheta = sum_ij K_bar_ij dK_ij/dtheta (+ mean terms).
-    Training rows only (all flags 1).  Row-chunked so N=32768 fits in RAM.
+    Training rows only (all flags 1).  Row-chunked (so N=32768 fits in RAM) and the chunks are
+    spread over `threads` host threads (numpy ufuncs and LAPACK release the GIL).
     """
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    threads = threads or os.cpu_count() or 1
     x = np.asarray(x, dtype=np.float64)
     y = np.asarray(y, dtype=np.float64).reshape(-1)
     if not np.all(x[:, 2] == 1):
@@ -301,54 +328,61 @@ def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 2048)
     t = x[:, 0]
     gi = _gene_index(x[:, 1])
     S = np.empty((n, n))
-    for r0 in range(0, n, chunk):
-        r1 = min(n, r0 + chunk)
+    bounds = [(r0, min(n, r0 + chunk)) for r0 in range(0, n, chunk)]
+
+    def build(b):
+        r0, r1 = b
         S[r0:r1] = kernel_xx(p, t[r0:r1, None], gi[r0:r1, None], t[None, :], gi[None, :])
-    S[np.diag_indices(n)] += p.jitter
-    S[np.diag_indices(n)] += p.sigma**2
-    mu = mean_function(p, x)
-    z = y - mu
-    c, info = dpotrf(S, lower=1, overwrite_a=1, clean=0)
-    if info != 0:
-        raise np.linalg.LinAlgError(f"Sigma not positive definite at pivot {info}")
-    logdet = 2.0 * np.sum(np.log(np.diag(c)))
-    alpha = cho_solve((c, True), z)
-    val = 0.5 * (n * math.log(2.0 * math.pi) + logdet + z @ alpha)
-    Sinv, info = dpotri(c, lower=1, overwrite_c=1)
-    # fill the upper triangle row-chunk-wise on use: Sinv is valid in the lower triangle
-    gd = np.zeros(G)
-    gs = np.zeros(G)
-    gl = 0.0
-    trK = 0.0
-    mult0 = p.l * SQRT_PI * 0.5
-    for r0 in range(0, n, chunk):
-        r1 = min(n, r0 + chunk)
-        rows = slice(r0, r1)
-        # symmetric completion of this row block
-        Kb = Sinv[rows, :].copy()
-        Kb[:, r1:] = Sinv[r1:, rows].T
-        blk = Sinv[rows, rows]
-        Kb[:, rows] = np.tril(blk) + np.tril(blk, -1).T
-        trK += np.trace(Kb[:, rows])
-        Kb = 0.5 * (Kb - np.outer(alpha[rows], alpha))
-        j = gi[rows, None]
-        k = gi[None, :]
-        tt = t[rows, None]
-        tp = t[None, :]
-        # k_xx = S_j S_k mult0 [ H(k,j,t',t) + H(j,k,t,t') ]
-        H1, dH1_da, dH1_db, dH1_dl = _h_partials(p, k, j, tp, tt)  # a=k (col gene), b=j (row gene)
-        H2, dH2_da, dH2_db, dH2_dl = _h_partials(p, j, k, tt, tp)  # a=j (row gene), b=k (col gene)
-        ss = p.s[j] * p.s[k]
-        kxx = ss * mult0 * (H1 + H2)
-        w = Kb * ss * mult0
-        d_row = w * (dH1_db + dH2_da)  # derivative through the ROW gene's decay
-        d_col = w * (dH1_da + dH2_db)  # ... through the COLUMN gene's decay
-        np.add.at(gd, gi[rows], d_row.sum(axis=1))
-        np.add.at(gd, gi, d_col.sum(axis=0))
-        kk = Kb * kxx
-        np.add.at(gs, gi[rows], kk.sum(axis=1) / p.s[gi[rows]])
-        np.add.at(gs, gi, kk.sum(axis=0) / p.s[gi])
-        gl += np.sum(w * (dH1_dl + dH2_dl)) + np.sum(kk) / p.l
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(build, bounds))
+        S[np.diag_indices(n)] += p.jitter
+        S[np.diag_indices(n)] += p.sigma**2
+        mu = mean_function(p, x)
+        z = y - mu
+        c, info = dpotrf(S, lower=1, overwrite_a=1, clean=0)
+        if info != 0:
+            raise np.linalg.LinAlgError(f"Sigma not positive definite at pivot {info}")
+        logdet = 2.0 * np.sum(np.log(np.diag(c)))
+        alpha = cho_solve((c, True), z)
+        val = 0.5 * (n * math.log(2.0 * math.pi) + logdet + z @ alpha)
+        Sinv, info = dpotri(c, lower=1, overwrite_c=1)  # valid in the lower triangle
+        mult0 = p.l * SQRT_PI * 0.5
+
+        def contract(b):
+            r0, r1 = b
+            rows = slice(r0, r1)
+            Kb = Sinv[rows, :].copy()  # symmetric completion of this row block
+            Kb[:, r1:] = Sinv[r1:, rows].T
+            blk = Sinv[rows, rows]
+            Kb[:, rows] = np.tril(blk) + np.tril(blk, -1).T
+            tr = np.trace(Kb[:, rows])
+            Kb = 0.5 * (Kb - np.outer(alpha[rows], alpha))
+            j = gi[rows, None]
+            k = gi[None, :]
+            tt = t[rows, None]
+            tp = t[None, :]
+            # k_xx = S_j S_k mult0 [ H(k,j,t',t) + H(j,k,t,t') ]
+            H1, dH1_da, dH1_db, dH1_dl = _h_partials(p, k, j, tp, tt)  # a=k (col gene), b=j (row gene)
+            H2, dH2_da, dH2_db, dH2_dl = _h_partials(p, j, k, tt, tp)  # a=j (row gene), b=k (col gene)
+            ss = p.s[j] * p.s[k]
+            kxx = ss * mult0 * (H1 + H2)
+            w = Kb * ss * mult0
+            gd = np.zeros(G)
+            gs = np.zeros(G)
+            np.add.at(gd, gi[rows], (w * (dH1_db + dH2_da)).sum(axis=1))  # through the ROW gene's decay
+            np.add.at(gd, gi, (w * (dH1_da + dH2_db)).sum(axis=0))        # through the COLUMN gene's decay
+            kk = Kb * kxx
+            np.add.at(gs, gi[rows], kk.sum(axis=1) / p.s[gi[rows]])
+            np.add.at(gs, gi, kk.sum(axis=0) / p.s[gi])
+            gl = np.sum(w * (dH1_dl + dH2_dl)) + np.sum(kk) / p.l
+            return gd, gs, gl, tr
+
+        parts = list(ex.map(contract, bounds))
+    gd = np.sum([q[0] for q in parts], axis=0)
+    gs = np.sum([q[1] for q in parts], axis=0)
+    gl = float(np.sum([q[2] for q in parts]))
+    trK = float(np.sum([q[3] for q in parts]))
     trKbar = 0.5 * (trK - alpha @ alpha)
     gsig = 2.0 * p.sigma * trKbar
     # mean terms: d/dB_m = -sum_{i in block m} alpha_i / D_m ; d/dD_m += sum alpha_i B_m / D_m^2
