@@ -8,84 +8,201 @@
 //   potrf(A) : potrf(A11); A21 <- A21 L11^-T (recursive TRSM); A22 -= A21 A21^T (SYRK); potrf(A22)
 //   trtri(L) : W21 = -W22 (L21 W11)                        (two triangular GEMMs)
 //   lauum(W) : S_ij = sum_{k >= i} W_ki^T W_kj for every lower tile, one launch
-// The 128 x 128 leaves are factorised AND inverted by one CTA in shared memory; the inverted
-// diagonal blocks turn every leaf-level TRSM into a GEMM.
+// The 128 x 128 leaves are factorised AND inverted by one CTA in shared memory (4 x 4 blocking over
+// 32 x 32 sub-blocks: warp-shuffle Cholesky on the diagonal sub-blocks, DMMA for everything else);
+// the inverted diagonal blocks turn every leaf-level TRSM into a GEMM.
 #include "lfm_common.cuh"
 
 #define NB LFM_NB
-#define LEAF_LD (NB + 1)
-#define LEAF_SMEM (NB * LEAF_LD * 8)
+#define LB 32                       // sub-block edge inside a leaf
+#define S_LD 132                    // == 4 (mod 16): conflict-free m8n8k4 fragment reads
+#define WD_LD 36                    // == 4 (mod 16)
+#define LEAF_THREADS 256
+#define LEAF_SMEM ((NB * S_LD + 4 * LB * WD_LD) * 8)
 
-// One CTA, 128 threads (thread i <-> row i / column i).
-__global__ void __launch_bounds__(NB) lfm_potrf_leaf_kernel(double* __restrict__ A, int64_t lda,
-                                                          double* __restrict__ W, int64_t ldw,
-                                                          int* __restrict__ info, int pivot_base) {
-  extern __shared__ double S[];  // [NB][LEAF_LD]; lower = L, strict upper (shifted) = W^T
-  __shared__ double piv;
-  const int tid = threadIdx.x;
-  for (int r = 0; r < NB; ++r) S[r * LEAF_LD + tid] = (tid <= r) ? A[(int64_t)r * lda + tid] : 0.0;
+__device__ __forceinline__ void leaf_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
+}
+
+// One warp: acc(32x32) += A(32x32, row-major lda) * op(B); TB = 1: B stored [n][k], TB = 0: B stored [k][n].
+template <int TB>
+__device__ __forceinline__ void warp_gemm32(double (&acc)[4][4][2], const double* __restrict__ A, int lda,
+                                            const double* __restrict__ B, int ldb, int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+  for (int k4 = 0; k4 < LB; k4 += 4) {
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = A[(8 * i + fr) * lda + k4 + fc];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = TB ? B[(8 * j + fr) * ldb + k4 + fc] : B[(k4 + fc) * ldb + 8 * j + fr];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) leaf_dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+__device__ __forceinline__ void warp_zero32(double (&acc)[4][4][2]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+}
+// C = alpha * acc + beta * C
+__device__ __forceinline__ void warp_store32(const double (&acc)[4][4][2], double* C, int ldc, double alpha,
+                                             double beta, int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double* p = C + (8 * i + fr) * ldc + 8 * j + 2 * fc;
+      if (beta != 0.0) {
+        p[0] = alpha * acc[i][j][0] + beta * p[0];
+        p[1] = alpha * acc[i][j][1] + beta * p[1];
+      } else {
+        p[0] = alpha * acc[i][j][0];
+        p[1] = alpha * acc[i][j][1];
+      }
+    }
+}
+
+// One warp factorises a 32 x 32 diagonal block held one row per lane in registers (shuffle-broadcast
+// right-looking Cholesky), then inverts it by forward substitution, one column per lane.
+// Returns the first failing pivot (0-based) or -1.
+__device__ __forceinline__ int warp_potrf_inv32(double* __restrict__ D, int ldd, double* __restrict__ Winv,
+                                                int lane) {
+  double r[LB];
+#pragma unroll
+  for (int j = 0; j < LB; ++j) r[j] = D[lane * ldd + j];
+  double mydinv = 0.0;
+  int fail = -1;
+#pragma unroll
+  for (int k = 0; k < LB; ++k) {
+    const double akk = __shfl_sync(0xffffffffu, r[k], k);
+    if (!(akk > 0.0) && fail < 0) fail = k;
+    const double dk = sqrt(akk);
+    const double rk = 1.0 / dk;
+    const double lik = (lane == k) ? dk : r[k] * rk;
+    r[k] = lik;
+    if (lane == k) mydinv = rk;
+#pragma unroll
+    for (int j = k + 1; j < LB; ++j) {
+      const double ljk = __shfl_sync(0xffffffffu, lik, j);
+      r[j] = fma(-lik, ljk, r[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LB; ++j) D[lane * ldd + j] = (j <= lane) ? r[j] : 0.0;
+  // inverse: lane c owns column c of W = L^-1; w[i] = W[i][c]
+  double w[LB];
+  w[0] = (lane == 0) ? mydinv : 0.0;
+#pragma unroll
+  for (int i = 1; i < LB; ++i) {
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      const double lik = __shfl_sync(0xffffffffu, r[k], i);
+      const double wk = (k == lane) ? mydinv : w[k];
+      if (k & 1) acc1 = (k >= lane) ? fma(lik, wk, acc1) : acc1;
+      else acc0 = (k >= lane) ? fma(lik, wk, acc0) : acc0;
+    }
+    const double dinv_i = __shfl_sync(0xffffffffu, mydinv, i);
+    w[i] = (i > lane) ? -(acc0 + acc1) * dinv_i : ((i == lane) ? mydinv : 0.0);
+  }
+#pragma unroll
+  for (int i = 0; i < LB; ++i) Winv[i * WD_LD + lane] = w[i];
+  return fail;
+}
+
+// Leaf: in-place Cholesky of one 128 x 128 diagonal block AND its inverse, one CTA of 8 warps.
+// Blocked 4 x 4 over 32 x 32 sub-blocks; all sub-block products run on DMMA from shared memory.
+__global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double* __restrict__ A, int64_t lda,
+                                                                       double* __restrict__ W, int64_t ldw,
+                                                                       int* __restrict__ info, int pivot_base) {
+  extern __shared__ __align__(16) double S[];   // [NB][S_LD] then Wd[4][LB][WD_LD]
+  double* Wd = S + NB * S_LD;
+  __shared__ int failed;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) failed = -1;
+  // load the lower triangle (coalesced 128-double rows), zero above the diagonal
+#pragma unroll 8
+  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    S[r * S_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+  }
   __syncthreads();
-  // left-looking column Cholesky: thread i owns row i
-  for (int k = 0; k < NB; ++k) {
+  for (int kb = 0; kb < 4; ++kb) {
+    double* Dkk = S + (kb * LB) * S_LD + kb * LB;
+    if (warp == 0) {
+      const int f = warp_potrf_inv32(Dkk, S_LD, Wd + kb * LB * WD_LD, lane);
+      if (lane == 0 && f >= 0 && failed < 0) failed = kb * LB + f;
+    }
+    __syncthreads();
+    // panel: S[ib][kb] <- S[ib][kb] * Winv_kk^T
+    if (warp >= 1 && kb + warp < 4) {
+      double* C = S + ((kb + warp) * LB) * S_LD + kb * LB;
+      double acc[4][4][2];
+      warp_zero32(acc);
+      warp_gemm32<1>(acc, C, S_LD, Wd + kb * LB * WD_LD, WD_LD, lane);
+      __syncwarp();
+      warp_store32(acc, C, S_LD, 1.0, 0.0, lane);
+    }
+    __syncthreads();
+    // trailing update: S[ib][jb] -= S[ib][kb] S[jb][kb]^T for ib >= jb > kb
+    {
+      int cnt = 0;
+      for (int ib = kb + 1; ib < 4; ++ib)
+        for (int jb = kb + 1; jb <= ib; ++jb, ++cnt)
+          if (cnt == warp) {
+            double acc[4][4][2];
+            warp_zero32(acc);
+            warp_gemm32<1>(acc, S + (ib * LB) * S_LD + kb * LB, S_LD, S + (jb * LB) * S_LD + kb * LB, S_LD, lane);
+            warp_store32(acc, S + (ib * LB) * S_LD + jb * LB, S_LD, -1.0, 1.0, lane);
+          }
+    }
+    __syncthreads();
+  }
+  // L out (strict upper blocks are still the zeros of the load)
+#pragma unroll 8
+  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    A[(int64_t)r * lda + c] = S[r * S_LD + c];
+  }
+  // W = L^-1 by block forward substitution; W_ij (i > j) is built in the free upper block (j, i):
+  //   W_ij = -Winv_ii * sum_{k=j}^{i-1} L_ik W_kj
+  for (int d = 1; d < 4; ++d) {
+    const int j = warp, i = warp + d;
+    if (i < 4) {
+      double* dst = S + (j * LB) * S_LD + i * LB;
+      double acc[4][4][2];
+      warp_zero32(acc);
+      for (int k = j; k < i; ++k) {
+        const double* Lik = S + (i * LB) * S_LD + k * LB;
+        if (k == j) warp_gemm32<0>(acc, Lik, S_LD, Wd + j * LB * WD_LD, WD_LD, lane);
+        else warp_gemm32<0>(acc, Lik, S_LD, S + (j * LB) * S_LD + k * LB, S_LD, lane);
+      }
+      warp_store32(acc, dst, S_LD, 1.0, 0.0, lane);
+      __syncwarp();
+      warp_zero32(acc);
+      warp_gemm32<0>(acc, Wd + i * LB * WD_LD, WD_LD, dst, S_LD, lane);
+      __syncwarp();
+      warp_store32(acc, dst, S_LD, -1.0, 0.0, lane);
+    }
+    __syncthreads();
+  }
+#pragma unroll 8
+  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
+    const int r = idx >> 7, c = idx & 127;
+    const int bi = r >> 5, bj = c >> 5;
     double v = 0.0;
-    if (tid >= k) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      const double* ri = S + tid * LEAF_LD;
-      const double* rk = S + k * LEAF_LD;
-      int m = 0;
-      for (; m + 4 <= k; m += 4) {
-        s0 += ri[m] * rk[m];
-        s1 += ri[m + 1] * rk[m + 1];
-        s2 += ri[m + 2] * rk[m + 2];
-        s3 += ri[m + 3] * rk[m + 3];
-      }
-      for (; m < k; ++m) s0 += ri[m] * rk[m];
-      v = ri[k] - ((s0 + s1) + (s2 + s3));
-      if (tid == k) piv = v;
-    }
-    __syncthreads();
-    const double p = piv;
-    if (tid == k && !(p > 0.0)) atomicCAS(info, 0, pivot_base + k + 1);
-    if (tid >= k) {
-      const double dk = sqrt(p);
-      S[tid * LEAF_LD + k] = (tid == k) ? dk : v / dk;
-    }
-    __syncthreads();
+    if (bi == bj) v = Wd[bi * LB * WD_LD + (r & 31) * WD_LD + (c & 31)];
+    else if (bi > bj) v = S[(bj * LB + (r & 31)) * S_LD + bi * LB + (c & 31)];
+    W[(int64_t)r * ldw + c] = v;
   }
-  // write L (zero strict upper)
-  for (int r = 0; r < NB; ++r) A[(int64_t)r * lda + tid] = (tid <= r) ? S[r * LEAF_LD + tid] : 0.0;
-  // inverse by forward substitution, thread c owns column c of W = L^-1.
-  // W[i][c] (i > c) is kept at S[c][i + 1] (the unused strict upper part, shifted by one column).
-  {
-    const int c = tid;
-    const double wcc = 1.0 / S[c * LEAF_LD + c];
-    const int cmin = (tid >> 5) << 5;  // warp-uniform loop bounds -> broadcast reads of L
-    double* wc = S + c * LEAF_LD + 1;  // wc[k] = W[k][c]
-    for (int i = cmin + 1; i < NB; ++i) {
-      const double* li = S + i * LEAF_LD;
-      double s0 = 0.0, s1 = 0.0;
-      int k = cmin;
-      for (; k + 2 <= i; k += 2) {
-        const double w0 = (k == c) ? wcc : wc[k];
-        const double w1 = (k + 1 == c) ? wcc : wc[k + 1];
-        if (k >= c) s0 += li[k] * w0;
-        if (k + 1 >= c) s1 += li[k + 1] * w1;
-      }
-      for (; k < i; ++k) {
-        const double w0 = (k == c) ? wcc : wc[k];
-        if (k >= c) s0 += li[k] * w0;
-      }
-      if (i > c) wc[i] = -(s0 + s1) / li[i];
-    }
-    __syncthreads();
-    for (int r = 0; r < NB; ++r) {
-      double v;
-      if (tid < r) v = S[tid * LEAF_LD + r + 1];
-      else if (tid == r) v = 1.0 / S[r * LEAF_LD + r];
-      else v = 0.0;
-      W[(int64_t)r * ldw + tid] = v;
-    }
-  }
+  if (tid == 0 && failed >= 0) atomicCAS(info, 0, pivot_base + failed + 1);
 }
 
 static int leaf(cudaStream_t st, double* A, int64_t lda, double* W, int64_t ldw, int* info, int64_t pivot_base) {
@@ -94,7 +211,7 @@ static int leaf(cudaStream_t st, double* A, int64_t lda, double* W, int64_t ldw,
     LFM_CUDA_OK(cudaFuncSetAttribute(lfm_potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
     configured = true;
   }
-  lfm_potrf_leaf_kernel<<<1, NB, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base);
+  lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;

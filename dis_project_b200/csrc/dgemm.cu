@@ -9,14 +9,9 @@
 // inverted diagonal blocks) without multiplying structural zeros at tile granularity.
 #include "lfm_common.cuh"
 
-#define BM 128
-#define BN 128
 #define BK 16
 #define STAGES 4
-#define LDK (BK + 4)    // [row][k] layout, 20 doubles per row
-#define LDM (BM + 4)    // [k][row] layout, 132 doubles per row
-#define STAGE_DOUBLES (BM * LDK)  // 2560 doubles = 20480 B >= 16*132 = 2112
-#define GEMM_SMEM_BYTES (2 * STAGES * STAGE_DOUBLES * 8)
+#define LDK (BK + 4)    // [row][k] layout: 20 doubles per row, == 4 (mod 16) -> conflict-free fragment reads
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -32,37 +27,41 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
       : "d"(a), "d"(b));
 }
 
-// Load one operand tile (128 "rows" x 16 k) into a stage.
+// Load one operand tile (ROWS "rows" x 16 k) into a stage.
 //  TRANS == 0: operand stored [row][k] in global (k contiguous)  -> smem [row][LDK]
-//  TRANS == 1: operand stored [k][row] in global (row contiguous) -> smem [k][LDM]
-template <int TRANS>
+//  TRANS == 1: operand stored [k][row] in global (row contiguous) -> smem [k][ROWS + 4]
+template <int TRANS, int ROWS>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t row0,
                                           int64_t k0, int tid) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < ROWS / 32; ++i) {
     const int id = tid + 256 * i;
     if (TRANS == 0) {
       const int r = id >> 3, kc = id & 7;
       cp_async16(s + r * LDK + kc * 2, g + (row0 + r) * ld + k0 + kc * 2);
     } else {
-      const int kr = id >> 6, mc = id & 63;
-      cp_async16(s + kr * LDM + mc * 2, g + (k0 + kr) * ld + row0 + mc * 2);
+      const int kr = id / (ROWS / 2), mc = id % (ROWS / 2);
+      cp_async16(s + kr * (ROWS + 4) + mc * 2, g + (k0 + kr) * ld + row0 + mc * 2);
     }
   }
 }
 
-template <int TA, int TBN>  // TA: op(A)=A^T ; TBN = 1 when B is stored N x K ("NT"), 0 when stored K x N
-__global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
+// CTA tile (16 WM) x (32 WN): 8 warps as 2 x 4, each warp (8 WM) x (8 WN).
+//   <8,4> 128 x 128 (large problems), <4,4> 64 x 128 (in-place panel), <4,2> 64 x 64 (small problems, 2 CTAs / SM)
+template <int TA, int TBN, int WM, int WN>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: stored K x N
+__global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
+  constexpr int BM = 16 * WM, BN = 32 * WN;
+  constexpr int A_STAGE = BM * LDK, B_STAGE = BN * LDK;  // >= 16 * (BM + 4), 16 * (BN + 4)
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
-  double* sB = smem + STAGES * STAGE_DOUBLES;
+  double* sB = smem + STAGES * A_STAGE;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   int tm, tn;
   if (g.lower_only) {
-    // blockIdx.x enumerates lower-triangle tiles, largest rows first (they carry the longest k-ranges)
+    // blockIdx.x enumerates lower-triangle tiles, longest k-range first: row tiles descending, except
+    // when the k-range starts at the row tile
     const int64_t total = (int64_t)gridDim.x;
-    // longest k-range first: row tiles descending, except when the k-range starts at the row tile
     const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL);
     const int64_t t = asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x;
     int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
@@ -85,21 +84,21 @@ __global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_
   }
   const int nk = (int)((ke - kb) / BK);
 
-  double acc[8][4][2];
+  double acc[WM][WN][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    for (int j = 0; j < WN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-  const int wm = (warp >> 2) * 64;
-  const int wn = (warp & 3) * 32;
+  const int wm = (warp >> 2) * (8 * WM);
+  const int wn = (warp & 3) * (8 * WN);
   const int fr = lane >> 2, fc = lane & 3;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<TA>(sA + s * STAGE_DOUBLES, g.A, g.lda, row0, kb + (int64_t)s * BK, tid);
-      load_tile<TBN ? 0 : 1>(sB + s * STAGE_DOUBLES, g.B, g.ldb, col0, kb + (int64_t)s * BK, tid);
+      load_tile<TA, BM>(sA + s * A_STAGE, g.A, g.lda, row0, kb + (int64_t)s * BK, tid);
+      load_tile<TBN ? 0 : 1, BN>(sB + s * B_STAGE, g.B, g.ldb, col0, kb + (int64_t)s * BK, tid);
     }
     cp_async_commit();
   }
@@ -110,30 +109,30 @@ __global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_
       const int nx = kt + STAGES - 1;
       if (nx < nk) {
         const int slot = nx % STAGES;
-        load_tile<TA>(sA + slot * STAGE_DOUBLES, g.A, g.lda, row0, kb + (int64_t)nx * BK, tid);
-        load_tile<TBN ? 0 : 1>(sB + slot * STAGE_DOUBLES, g.B, g.ldb, col0, kb + (int64_t)nx * BK, tid);
+        load_tile<TA, BM>(sA + slot * A_STAGE, g.A, g.lda, row0, kb + (int64_t)nx * BK, tid);
+        load_tile<TBN ? 0 : 1, BN>(sB + slot * B_STAGE, g.B, g.ldb, col0, kb + (int64_t)nx * BK, tid);
       }
       cp_async_commit();
     }
-    const double* a_s = sA + (kt % STAGES) * STAGE_DOUBLES;
-    const double* b_s = sB + (kt % STAGES) * STAGE_DOUBLES;
+    const double* a_s = sA + (kt % STAGES) * A_STAGE;
+    const double* b_s = sB + (kt % STAGES) * B_STAGE;
 #pragma unroll
     for (int k4 = 0; k4 < BK; k4 += 4) {
-      double af[8], bf[4];
+      double af[WM], bf[WN];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < WM; ++i) {
         if (TA == 0) af[i] = a_s[(wm + i * 8 + fr) * LDK + k4 + fc];
-        else af[i] = a_s[(k4 + fc) * LDM + wm + i * 8 + fr];
+        else af[i] = a_s[(k4 + fc) * (BM + 4) + wm + i * 8 + fr];
       }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < WN; ++j) {
         if (TBN) bf[j] = b_s[(wn + j * 8 + fr) * LDK + k4 + fc];
-        else bf[j] = b_s[(k4 + fc) * LDM + wn + j * 8 + fr];
+        else bf[j] = b_s[(k4 + fc) * (BN + 4) + wn + j * 8 + fr];
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
   }
   cp_async_wait<0>();
@@ -141,10 +140,10 @@ __global__ void __launch_bounds__(256, 1) lfm_dgemm_kernel(LfmGemm g, int tiles_
   // epilogue: thread holds C[row = 8i + lane/4][col = 8j + 2*(lane%4) + {0,1}]
   const double alpha = g.alpha, beta = g.beta;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < WM; ++i) {
     const int64_t r = row0 + wm + i * 8 + fr;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < WN; ++j) {
       const int64_t c = col0 + wn + j * 8 + fc * 2;
       double2* p = reinterpret_cast<double2*>(g.C + r * g.ldc + c);
       double2 o;
@@ -171,7 +170,7 @@ struct GemmProf {
 };
 static GemmProf g_prof;
 
-static double gemm_exec_flops(const LfmGemm& g) {
+static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
   const int64_t tm = g.M / BM, tn = g.N / BN;
   double f = 0.0;
   for (int64_t i = 0; i < tm; ++i) {
@@ -220,12 +219,14 @@ static cudaEvent_t prof_event() {
   return g_prof.ev[g_prof.used++];
 }
 
-template <int TA, int TBN>
+template <int TA, int TBN, int WM, int WN>
 static int launch(cudaStream_t st, const LfmGemm& g) {
+  constexpr int BM = 16 * WM, BN = 32 * WN;
+  constexpr int SMEM = STAGES * (BM + BN) * LDK * 8;
   static bool configured = false;
   if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     GEMM_SMEM_BYTES));
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SMEM));
     configured = true;
   }
   const int64_t tm = g.M / BM, tn = g.N / BN;
@@ -234,21 +235,36 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   if (g_prof.on) {
     cudaEventRecord(prof_event(), st);
-    g_prof.flops += gemm_exec_flops(g);
+    g_prof.flops += gemm_exec_flops(g, BM, BN);
     g_prof.launches += 1;
   }
-  lfm_dgemm_kernel<TA, TBN><<<(unsigned)tiles, 256, GEMM_SMEM_BYTES, st>>>(g, (int)tn);
+  lfm_dgemm_kernel<TA, TBN, WM, WN><<<(unsigned)tiles, 256, SMEM, st>>>(g, (int)tn);
   if (g_prof.on) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
 
+template <int WM, int WN>
+static int dispatch(cudaStream_t st, const LfmGemm& g) {
+  if (g.transA == 0 && g.transB == 1) return launch<0, 1, WM, WN>(st, g);
+  if (g.transA == 0 && g.transB == 0) return launch<0, 0, WM, WN>(st, g);
+  if (g.transA == 1 && g.transB == 0) return launch<1, 0, WM, WN>(st, g);
+  return launch<1, 1, WM, WN>(st, g);
+}
+
+// Tile-shape heuristic: 128 x 128 tiles once they fill >= 3 waves of the 148 SMs, else 64 x 64 tiles
+// (two CTAs per SM) so that small trailing updates and panels still spread over the whole chip.
+// C aliasing A (in-place panel multiply) needs one tile across the full width N = 128.
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
-  if (g.M % BM || g.N % BN || g.K % BK) return LFM_ERR_INVALID;
+  if (g.M % 128 || g.N % 128 || g.K % BK) return LFM_ERR_INVALID;
   if (g.lower_only && g.M != g.N) return LFM_ERR_INVALID;
-  if (g.transA == 0 && g.transB == 1) return launch<0, 1>(st, g);
-  if (g.transA == 0 && g.transB == 0) return launch<0, 0>(st, g);
-  if (g.transA == 1 && g.transB == 0) return launch<1, 0>(st, g);
-  return launch<1, 1>(st, g);
+  const int64_t t128 = g.lower_only ? (g.M / 128) * (g.M / 128 + 1) / 2 : (g.M / 128) * (g.N / 128);
+  const bool inplace = (const double*)g.C == g.A;
+  if (inplace) {
+    if (g.N != 128) return LFM_ERR_INVALID;
+    return (t128 >= 148) ? dispatch<8, 4>(st, g) : dispatch<4, 4>(st, g);
+  }
+  if (t128 >= 3 * 148) return dispatch<8, 4>(st, g);
+  return dispatch<4, 2>(st, g);
 }
