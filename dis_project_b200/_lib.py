@@ -61,6 +61,7 @@ SIGNATURES = {
                                          _ptr, _ptr]),
     "lfm_batched_fit_host": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                     _int, _int, _int, _ptr, _ptr, _ptr]),
+    "lfm_debug_leaf_profile": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr]),
     "lfm_debug_launch_count": (C.c_ulonglong, []),
     "lfm_debug_profile_begin": (_int, []),
     "lfm_debug_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -11,6 +11,7 @@
 // The 128 x 128 leaves are factorised AND inverted by one CTA in shared memory (4 x 4 blocking over
 // 32 x 32 sub-blocks: warp-shuffle Cholesky on the diagonal sub-blocks, DMMA for everything else);
 // the inverted diagonal blocks turn every leaf-level TRSM into a GEMM.
+#include <cstdlib>
 #include "lfm_common.cuh"
 
 #define NB LFM_NB
@@ -18,7 +19,7 @@
 #define S_LD 132                    // == 4 (mod 16): conflict-free m8n8k4 fragment reads
 #define WD_LD 36                    // == 4 (mod 16)
 #define LEAF_THREADS 256
-#define LEAF_SMEM ((NB * S_LD + 4 * LB * WD_LD) * 8)
+#define LEAF_SMEM ((NB * S_LD + 4 * LB * WD_LD + LB * 33) * 8)
 
 __device__ __forceinline__ void leaf_dmma(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -69,64 +70,96 @@ __device__ __forceinline__ void warp_store32(const double (&acc)[4][4][2], doubl
     }
 }
 
-// One warp factorises a 32 x 32 diagonal block held one row per lane in registers (shuffle-broadcast
-// right-looking Cholesky), then inverts it by forward substitution, one column per lane.
-// Returns the first failing pivot (0-based) or -1.
-__device__ __forceinline__ int warp_potrf_inv32(double* __restrict__ D, int ldd, double* __restrict__ Winv,
-                                                int lane) {
-  double r[LB];
-#pragma unroll
-  for (int j = 0; j < LB; ++j) r[j] = D[lane * ldd + j];
-  double mydinv = 0.0;
+// Diagonal 32 x 32 sub-block: warp 0 factorises it, warp 1 inverts it one pivot behind.
+// Single-warp code on an otherwise idle SM sub-partition runs at several cycles per instruction, so the
+// two rank-1 update streams (row i of L on lane i of warp 0; column c of Y = L^-1 on lane c of warp 1)
+// are put on different schedulers and coupled only by a progress counter in shared memory: after
+// pivot k, warp 0 publishes column k of L (in the [32][33] scratch T, bank-conflict free for column
+// reads) and 1/L_kk; warp 1 then computes W[k][c] = Y[k][c] / L_kk and Y[i][c] -= L[i][k] W[k][c].
+#define DP_LD 33
+__device__ __forceinline__ int warp_potrf32(double* __restrict__ D, int ldd, double* __restrict__ T,
+                                            double* __restrict__ rdiag, volatile int* prog, int base, int lane) {
   int fail = -1;
-#pragma unroll
+#pragma unroll 8
+  for (int r = 0; r < LB; ++r) T[r * DP_LD + lane] = D[r * ldd + lane];
+  __syncwarp();
+  double* myrow = T + lane * DP_LD;
   for (int k = 0; k < LB; ++k) {
-    const double akk = __shfl_sync(0xffffffffu, r[k], k);
+    const double akk = T[k * DP_LD + k];
     if (!(akk > 0.0) && fail < 0) fail = k;
-    const double dk = sqrt(akk);
-    const double rk = 1.0 / dk;
-    const double lik = (lane == k) ? dk : r[k] * rk;
-    r[k] = lik;
-    if (lane == k) mydinv = rk;
-#pragma unroll
-    for (int j = k + 1; j < LB; ++j) {
-      const double ljk = __shfl_sync(0xffffffffu, lik, j);
-      r[j] = fma(-lik, ljk, r[j]);
+    const double rk = rsqrt(akk);
+    double lik = 0.0;
+    if (lane >= k) {
+      lik = (lane == k) ? akk * rk : myrow[k] * rk;
+      myrow[k] = lik;
+      if (lane == k) rdiag[k] = rk;
     }
-  }
+    __syncwarp();
+    if (lane == 0) { __threadfence_block(); *prog = base + k + 1; }
+    for (int j0 = k + 1; j0 < LB; j0 += 8) {
+      double l[8], a[8];
 #pragma unroll
-  for (int j = 0; j < LB; ++j) D[lane * ldd + j] = (j <= lane) ? r[j] : 0.0;
-  // inverse: lane c owns column c of W = L^-1; w[i] = W[i][c]
-  double w[LB];
-  w[0] = (lane == 0) ? mydinv : 0.0;
+      for (int q = 0; q < 8; ++q) {
+        const int j = (j0 + q < LB) ? j0 + q : LB - 1;
+        l[q] = T[j * DP_LD + k];  // L[j][k], broadcast
+        a[q] = myrow[j];
+      }
 #pragma unroll
-  for (int i = 1; i < LB; ++i) {
-    double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) {
-      const double lik = __shfl_sync(0xffffffffu, r[k], i);
-      const double wk = (k == lane) ? mydinv : w[k];
-      if (k & 1) acc1 = (k >= lane) ? fma(lik, wk, acc1) : acc1;
-      else acc0 = (k >= lane) ? fma(lik, wk, acc0) : acc0;
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + q;
+        if (j < LB && lane >= j) myrow[j] = fma(-lik, l[q], a[q]);
+      }
     }
-    const double dinv_i = __shfl_sync(0xffffffffu, mydinv, i);
-    w[i] = (i > lane) ? -(acc0 + acc1) * dinv_i : ((i == lane) ? mydinv : 0.0);
+    __syncwarp();
   }
-#pragma unroll
-  for (int i = 0; i < LB; ++i) Winv[i * WD_LD + lane] = w[i];
+#pragma unroll 8
+  for (int r = 0; r < LB; ++r) D[r * ldd + lane] = (lane <= r) ? T[r * DP_LD + lane] : 0.0;
   return fail;
+}
+
+__device__ __forceinline__ void warp_trtri32(const double* __restrict__ T, double* __restrict__ Winv,
+                                             const double* __restrict__ rdiag, volatile int* prog, int base,
+                                             int lane) {
+#pragma unroll 8
+  for (int r = 0; r < LB; ++r) Winv[r * WD_LD + lane] = (r == lane) ? 1.0 : 0.0;
+  for (int k = 0; k < LB; ++k) {
+    while (*prog < base + k + 1) {}
+    __threadfence_block();
+    const double wk = Winv[k * WD_LD + lane] * rdiag[k];
+    Winv[k * WD_LD + lane] = wk;
+    for (int i0 = k + 1; i0 < LB; i0 += 8) {
+      double l[8], y[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = (i0 + q < LB) ? i0 + q : LB - 1;
+        l[q] = T[i * DP_LD + k];
+        y[q] = Winv[i * WD_LD + lane];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int i = i0 + q;
+        if (i < LB) Winv[i * WD_LD + lane] = fma(-l[q], wk, y[q]);
+      }
+    }
+  }
 }
 
 // Leaf: in-place Cholesky of one 128 x 128 diagonal block AND its inverse, one CTA of 8 warps.
 // Blocked 4 x 4 over 32 x 32 sub-blocks; all sub-block products run on DMMA from shared memory.
 __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double* __restrict__ A, int64_t lda,
                                                                        double* __restrict__ W, int64_t ldw,
-                                                                       int* __restrict__ info, int pivot_base) {
+                                                                       int* __restrict__ info, int pivot_base,
+                                                                       long long* __restrict__ stamps) {
   extern __shared__ __align__(16) double S[];   // [NB][S_LD] then Wd[4][LB][WD_LD]
+  int nstamp = 0;
+#define LEAF_STAMP() do { if (stamps && threadIdx.x == 0) stamps[nstamp++] = clock64(); } while (0)
+  LEAF_STAMP();
   double* Wd = S + NB * S_LD;
   __shared__ int failed;
+  __shared__ int progress;
+  __shared__ double rdiag[LB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) failed = -1;
+  if (tid == 0) { failed = -1; progress = 0; }
   // load the lower triangle (coalesced 128-double rows), zero above the diagonal
 #pragma unroll 8
   for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
@@ -134,13 +167,17 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
     S[r * S_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
   }
   __syncthreads();
+  LEAF_STAMP();
   for (int kb = 0; kb < 4; ++kb) {
     double* Dkk = S + (kb * LB) * S_LD + kb * LB;
     if (warp == 0) {
-      const int f = warp_potrf_inv32(Dkk, S_LD, Wd + kb * LB * WD_LD, lane);
+      const int f = warp_potrf32(Dkk, S_LD, Wd + 4 * LB * WD_LD, rdiag, &progress, kb * LB, lane);
       if (lane == 0 && f >= 0 && failed < 0) failed = kb * LB + f;
+    } else if (warp == 1) {
+      warp_trtri32(Wd + 4 * LB * WD_LD, Wd + kb * LB * WD_LD, rdiag, &progress, kb * LB, lane);
     }
     __syncthreads();
+    LEAF_STAMP();
     // panel: S[ib][kb] <- S[ib][kb] * Winv_kk^T
     if (warp >= 1 && kb + warp < 4) {
       double* C = S + ((kb + warp) * LB) * S_LD + kb * LB;
@@ -164,6 +201,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
           }
     }
     __syncthreads();
+    LEAF_STAMP();
   }
   // L out (strict upper blocks are still the zeros of the load)
 #pragma unroll 8
@@ -171,6 +209,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
     const int r = idx >> 7, c = idx & 127;
     A[(int64_t)r * lda + c] = S[r * S_LD + c];
   }
+  LEAF_STAMP();
   // W = L^-1 by block forward substitution; W_ij (i > j) is built in the free upper block (j, i):
   //   W_ij = -Winv_ii * sum_{k=j}^{i-1} L_ik W_kj
   for (int d = 1; d < 4; ++d) {
@@ -192,6 +231,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
       warp_store32(acc, dst, S_LD, -1.0, 0.0, lane);
     }
     __syncthreads();
+    LEAF_STAMP();
   }
 #pragma unroll 8
   for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
@@ -202,6 +242,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
     else if (bi > bj) v = S[(bj * LB + (r & 31)) * S_LD + bi * LB + (c & 31)];
     W[(int64_t)r * ldw + c] = v;
   }
+  LEAF_STAMP();
   if (tid == 0 && failed >= 0) atomicCAS(info, 0, pivot_base + failed + 1);
 }
 
@@ -211,7 +252,7 @@ static int leaf(cudaStream_t st, double* A, int64_t lda, double* W, int64_t ldw,
     LFM_CUDA_OK(cudaFuncSetAttribute(lfm_potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
     configured = true;
   }
-  lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base);
+  lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base, nullptr);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
@@ -225,6 +266,7 @@ static LfmGemm mk(int ta, int tb, int64_t M, int64_t N, int64_t K, const double*
   g.transA = ta; g.transB = tb; g.M = M; g.N = N; g.K = K;
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.alpha = alpha; g.beta = beta; g.lower_only = lower; g.kmode = kmode;
+  g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
   return g;
 }
 
@@ -242,9 +284,37 @@ static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ld
   return trsm_rec(st, m, n2, B + n1, ldb, L + n1 * ldl + n1, ldl, Wd + n1 * ldw + n1, ldw);
 }
 
+// Right-looking blocked Cholesky with 128-wide panels for small / medium n: every step is a leaf, one
+// in-place panel multiply by the inverted diagonal block and one fat trailing SYRK (3 launches per
+// block column instead of the O(log) tiny TRSM launches of the recursion).
+static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
+                               int64_t pivot_base) {
+  for (int64_t k = 0; k < n; k += NB) {
+    double* Akk = A + k * lda + k;
+    double* Wkk = W + k * ldw + k;
+    LFM_TRY(leaf(st, Akk, lda, Wkk, ldw, info, pivot_base + k));
+    const int64_t m = n - k - NB;
+    if (m <= 0) break;
+    double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
+    LFM_TRY(lfm_dgemm(st, mk(0, 1, m, NB, NB, P, lda, Wkk, ldw, P, lda, 1.0, 0.0, 0, LFM_K_FULL)));
+    LFM_TRY(lfm_dgemm(st, mk(0, 1, m, m, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 1, LFM_K_FULL)));
+  }
+  return LFM_OK;
+}
+
+static int64_t rl_threshold() {
+  static int64_t v = -1;
+  if (v < 0) {
+    const char* e = getenv("LFM_RL_THRESHOLD");
+    v = e ? atoll(e) : 4096;
+  }
+  return v;
+}
+
 static int potrf_rec(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
                      int64_t pivot_base) {
   if (n == NB) return leaf(st, A, lda, W, ldw, info, pivot_base);
+  if (n <= rl_threshold()) return potrf_right_looking(st, n, A, lda, W, ldw, info, pivot_base);
   const int64_t n1 = split(n), n2 = n - n1;
   LFM_TRY(potrf_rec(st, n1, A, lda, W, ldw, info, pivot_base));
   double* A21 = A + n1 * lda;
@@ -262,8 +332,12 @@ int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int
 
 // W (lower) = L^-1; diagonal 128-blocks of W already hold the leaf inverses.  The strictly upper
 // block W12 of every recursion node is used as scratch for T^T = W11^T L21^T.
+static int trtri_levels(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw);
+
 int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw) {
   if (n == NB) return LFM_OK;
+  const int64_t nblk = n / NB;
+  if ((nblk & (nblk - 1)) == 0 && ldl == ldw) return trtri_levels(st, n, L, ldl, W, ldw);
   const int64_t n1 = split(n), n2 = n - n1;
   LFM_TRY(lfm_trtri(st, n1, L, ldl, W, ldw));
   LFM_TRY(lfm_trtri(st, n2, L + n1 * ldl + n1, ldl, W + n1 * ldw + n1, ldw));
@@ -276,9 +350,39 @@ int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* 
   return lfm_dgemm(st, mk(0, 1, n2, n1, n2, W22, ldw, Tt, ldw, W21, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW));
 }
 
+// Power-of-two block counts: the recursion tree is regular, so all nodes of one level (independent
+// diagonal blocks, identical shapes, constant stride along the diagonal) run as ONE batched launch:
+// 2 log2(n / 128) launches in total.
+static int trtri_levels(cudaStream_t st, int64_t n, const double* L, int64_t ld, double* W, int64_t ldw) {
+  for (int64_t m = NB; m < n; m *= 2) {  // m = half size of the nodes at this level
+    const int64_t count = n / (2 * m);
+    const int64_t stride = 2 * m * (ld + 1);
+    LfmGemm g1 = mk(1, 1, m, m, m, W, ldw, L + m * ld, ld, W + m, ldw, 1.0, 0.0, 0, LFM_K_GE_ROW);
+    g1.batch = (int)count; g1.strideA = stride; g1.strideB = stride; g1.strideC = stride;
+    LFM_TRY(lfm_dgemm(st, g1));
+    LfmGemm g2 = mk(0, 1, m, m, m, W + m * ldw + m, ldw, W + m, ldw, W + m * ldw, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW);
+    g2.batch = (int)count; g2.strideA = stride; g2.strideB = stride; g2.strideC = stride;
+    LFM_TRY(lfm_dgemm(st, g2));
+  }
+  return LFM_OK;
+}
+
 // S (lower) = W^T W, out of place: every lower tile (i,j) is an independent TN product over the
 // block rows k >= i, so the whole N^3/3 is ONE launch (W's diagonal blocks have exact zeros above
 // the diagonal, and the scratch that lfm_trtri leaves in W's strict upper blocks is never read).
 int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds) {
   return lfm_dgemm(st, mk(1, 0, n, n, n, W, ldw, W, ldw, S, lds, 1.0, 0.0, 1, LFM_K_GE_ROWCOL));
+}
+
+// Debug: one leaf with clock64() stamps at its phase boundaries (16 values: start, loaded, then per
+// sub-block [diag, trailing] x 4, L stored, 3 inverse levels, W stored).
+extern "C" int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info, long long* stamps) {
+  static bool configured = false;
+  if (!configured) {
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+    configured = true;
+  }
+  lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, (cudaStream_t)stream>>>(A, NB, W, NB, info, 0, stamps);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
 }

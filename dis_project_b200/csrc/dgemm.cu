@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(
     tn = blockIdx.x % tiles_n;
   }
   const int64_t row0 = (int64_t)tm * BM, col0 = (int64_t)tn * BN;
+  const double* __restrict__ gA = g.A + (int64_t)blockIdx.y * g.strideA;
+  const double* __restrict__ gB = g.B + (int64_t)blockIdx.y * g.strideB;
+  double* __restrict__ gC = g.C + (int64_t)blockIdx.y * g.strideC;
   int64_t kb = 0, ke = g.K;
   switch (g.kmode) {
     case LFM_K_LE_ROW: ke = min(g.K, row0 + BM); break;
@@ -97,8 +100,8 @@ __global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_tile<TA, BM>(sA + s * A_STAGE, g.A, g.lda, row0, kb + (int64_t)s * BK, tid);
-      load_tile<TBN ? 0 : 1, BN>(sB + s * B_STAGE, g.B, g.ldb, col0, kb + (int64_t)s * BK, tid);
+      load_tile<TA, BM>(sA + s * A_STAGE, gA, g.lda, row0, kb + (int64_t)s * BK, tid);
+      load_tile<TBN ? 0 : 1, BN>(sB + s * B_STAGE, gB, g.ldb, col0, kb + (int64_t)s * BK, tid);
     }
     cp_async_commit();
   }
@@ -109,8 +112,8 @@ __global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(
       const int nx = kt + STAGES - 1;
       if (nx < nk) {
         const int slot = nx % STAGES;
-        load_tile<TA, BM>(sA + slot * A_STAGE, g.A, g.lda, row0, kb + (int64_t)nx * BK, tid);
-        load_tile<TBN ? 0 : 1, BN>(sB + slot * B_STAGE, g.B, g.ldb, col0, kb + (int64_t)nx * BK, tid);
+        load_tile<TA, BM>(sA + slot * A_STAGE, gA, g.lda, row0, kb + (int64_t)nx * BK, tid);
+        load_tile<TBN ? 0 : 1, BN>(sB + slot * B_STAGE, gB, g.ldb, col0, kb + (int64_t)nx * BK, tid);
       }
       cp_async_commit();
     }
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(
 #pragma unroll
     for (int j = 0; j < WN; ++j) {
       const int64_t c = col0 + wn + j * 8 + fc * 2;
-      double2* p = reinterpret_cast<double2*>(g.C + r * g.ldc + c);
+      double2* p = reinterpret_cast<double2*>(gC + r * g.ldc + c);
       double2 o;
       o.x = alpha * acc[i][j][0];
       o.y = alpha * acc[i][j][1];
@@ -235,10 +238,11 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   if (g_prof.on) {
     cudaEventRecord(prof_event(), st);
-    g_prof.flops += gemm_exec_flops(g, BM, BN);
+    g_prof.flops += gemm_exec_flops(g, BM, BN) * (g.batch > 1 ? g.batch : 1);
     g_prof.launches += 1;
   }
-  lfm_dgemm_kernel<TA, TBN, WM, WN><<<(unsigned)tiles, 256, SMEM, st>>>(g, (int)tn);
+  const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
+  lfm_dgemm_kernel<TA, TBN, WM, WN><<<grid, 256, SMEM, st>>>(g, (int)tn);
   if (g_prof.on) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
@@ -259,7 +263,9 @@ static int dispatch(cudaStream_t st, const LfmGemm& g) {
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
   if (g.M % 128 || g.N % 128 || g.K % BK) return LFM_ERR_INVALID;
   if (g.lower_only && g.M != g.N) return LFM_ERR_INVALID;
-  const int64_t t128 = g.lower_only ? (g.M / 128) * (g.M / 128 + 1) / 2 : (g.M / 128) * (g.N / 128);
+  const int64_t nb = g.batch > 1 ? g.batch : 1;
+  if (nb > 65535) return LFM_ERR_UNSUPPORTED;
+  const int64_t t128 = nb * (g.lower_only ? (g.M / 128) * (g.M / 128 + 1) / 2 : (g.M / 128) * (g.N / 128));
   const bool inplace = (const double*)g.C == g.A;
   if (inplace) {
     if (g.N != 128) return LFM_ERR_INVALID;

@@ -68,6 +68,8 @@ struct LfmGemm {
   double alpha, beta;
   int lower_only;      // skip output tiles strictly above the diagonal (requires square tiling of C)
   int kmode;
+  int batch;           // > 1: blockIdx.y-th problem uses A + y*strideA, B + y*strideB, C + y*strideC
+  int64_t strideA, strideB, strideC;
 };
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
 

@@ -356,6 +356,7 @@ extern "C" int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int
   LfmGemm g;
   g.transA = 0; g.transB = 1; g.M = M; g.N = N; g.K = K; g.A = A; g.lda = K; g.B = B; g.ldb = K;
   g.C = C; g.ldc = N; g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kmode = LFM_K_FULL;
+  g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
   return lfm_dgemm((cudaStream_t)stream, g);
 }
 extern "C" int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv,

@@ -148,6 +148,7 @@ extern "C" int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const
     g.transA = 0; g.transB = 0; g.M = Np; g.N = ncp; g.K = Np;
     g.A = s.W; g.lda = Np; g.B = s.Kxf; g.ldb = PC_COLS; g.C = s.V; g.ldc = PC_COLS;
     g.alpha = 1.0; g.beta = 0.0; g.lower_only = 0; g.kmode = LFM_K_LE_ROW;
+    g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
     LFM_TRY(lfm_dgemm(st, g));
     lfm_post_colred_kernel<<<dim3((unsigned)(ncp / 128), (unsigned)nrch), 128, 0, st>>>(Np, PC_COLS, s.Kxf, s.V,
                                                                                       PC_COLS, s.alpha, s.pm, s.pq);

@@ -158,6 +158,8 @@ int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int64_t K, con
  * W is an n x n scratch matrix. */
 int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv, int* info);
 
+/* One 128 x 128 leaf factorisation with clock64() stamps at its phase boundaries (16 values). */
+int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info, long long* stamps);
 /* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long lfm_debug_launch_count(void);
 /* Bracket every DMMA GEMM launch with CUDA events on its stream between begin and end; end

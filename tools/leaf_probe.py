@@ -1,0 +1,17 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from dis_project_b200 import _lib
+l=_lib.lib(); dev=torch.device("cuda:0")
+A0=torch.randn(128,128,dtype=torch.float64,device=dev); A0=A0@A0.T+128*torch.eye(128,dtype=torch.float64,device=dev)
+W=torch.zeros(128,128,dtype=torch.float64,device=dev); info=torch.zeros(1,dtype=torch.int32,device=dev)
+st=torch.zeros(32,dtype=torch.int64,device=dev)
+for it in range(3):
+    A=A0.clone()
+    st.zero_()
+    l.lfm_debug_leaf_profile(torch.cuda.current_stream().cuda_stream, A.data_ptr(), W.data_ptr(), info.data_ptr(), st.data_ptr())
+    torch.cuda.synchronize()
+    s=st.cpu().numpy()[:16]
+    print("cycles:", np.diff(s)[:14], "total", s[14]-s[0], "diag phases [dot, shfl, rsqrt, store+sync, inverse]:", st.cpu().numpy()[16:21])
+names=["load","diag0","trail0","diag1","trail1","diag2","trail2","diag3","trail3","(stamp)","storeL?","inv1","inv2","inv3","storeW"]
+print(names)
