@@ -7,6 +7,7 @@
 // in both operand orientations.  Per-tile k-ranges (kmode) let the same kernel serve every
 // triangular Level-3 shape of the blocked Cholesky / inverse (SYRK, TRMM, LAUUM, TRSM via
 // inverted diagonal blocks) without multiplying structural zeros at tile granularity.
+#include <cstdlib>
 #include "lfm_common.cuh"
 
 #define BK 16
@@ -30,12 +31,12 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Load one operand tile (ROWS "rows" x 16 k) into a stage.
 //  TRANS == 0: operand stored [row][k] in global (k contiguous)  -> smem [row][LDK]
 //  TRANS == 1: operand stored [k][row] in global (row contiguous) -> smem [k][ROWS + 4]
-template <int TRANS, int ROWS>
+template <int TRANS, int ROWS, int NT>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t row0,
                                           int64_t k0, int tid) {
 #pragma unroll
-  for (int i = 0; i < ROWS / 32; ++i) {
-    const int id = tid + 256 * i;
+  for (int i = 0; i < ROWS * 8 / NT; ++i) {
+    const int id = tid + NT * i;
     if (TRANS == 0) {
       const int r = id >> 3, kc = id & 7;
       cp_async16(s + r * LDK + kc * 2, g + (row0 + r) * ld + k0 + kc * 2);
@@ -46,11 +47,12 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
   }
 }
 
-// CTA tile (16 WM) x (32 WN): 8 warps as 2 x 4, each warp (8 WM) x (8 WN).
-//   <8,4> 128 x 128 (large problems), <4,4> 64 x 128 (in-place panel), <4,2> 64 x 64 (small problems, 2 CTAs / SM)
-template <int TA, int TBN, int WM, int WN>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: stored K x N
-__global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
-  constexpr int BM = 16 * WM, BN = 32 * WN;
+// CTA tile (8 WM GM) x (8 WN 4): GM x 4 warps, each warp (8 WM) x (8 WN).
+//   <8,4,2> 128 x 128, 8 warps     <4,4,4> 128 x 128, 16 warps (4 per scheduler: better DMMA/LDS overlap)
+//   <4,4,2> 64 x 128 (in-place panel)       <4,2,2> 64 x 64 (small problems, 2 CTAs / SM)
+template <int TA, int TBN, int WM, int WN, int GM>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: K x N
+__global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
+  constexpr int BM = 8 * WM * GM, BN = 32 * WN, NT = 128 * GM;
   constexpr int A_STAGE = BM * LDK, B_STAGE = BN * LDK;  // >= 16 * (BM + 4), 16 * (BN + 4)
   extern __shared__ __align__(16) double smem[];
   double* sA = smem;
@@ -93,49 +95,59 @@ __global__ void __launch_bounds__(256, (WM * WN <= 8) ? 2 : 1) lfm_dgemm_kernel(
 #pragma unroll
     for (int j = 0; j < WN; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
-  const int wm = (warp >> 2) * (8 * WM);
+  const int wm = (warp >> 2) * (8 * WM);  // warp row in the GM x 4 warp grid
   const int wn = (warp & 3) * (8 * WN);
   const int fr = lane >> 2, fc = lane & 3;
 
+  // Two k-tiles (32 deep) per barrier: the four stages form two units; unit u is computed while unit
+  // u+1 streams in, so there is one wait_group + one __syncthreads per 256 DMMAs of every warp.
+  auto issue_unit = [&](int uslot, int kt0) {
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nk) {
-      load_tile<TA, BM>(sA + s * A_STAGE, gA, g.lda, row0, kb + (int64_t)s * BK, tid);
-      load_tile<TBN ? 0 : 1, BN>(sB + s * B_STAGE, gB, g.ldb, col0, kb + (int64_t)s * BK, tid);
+    for (int t = 0; t < 2; ++t) {
+      if (kt0 + t < nk) {
+        const int slot = uslot * 2 + t;
+        load_tile<TA, BM, NT>(sA + slot * A_STAGE, gA, g.lda, row0, kb + (int64_t)(kt0 + t) * BK, tid);
+        load_tile<TBN ? 0 : 1, BN, NT>(sB + slot * B_STAGE, gB, g.ldb, col0, kb + (int64_t)(kt0 + t) * BK, tid);
+      }
     }
     cp_async_commit();
-  }
-  for (int kt = 0; kt < nk; ++kt) {
-    cp_async_wait<STAGES - 2>();
+  };
+  issue_unit(0, 0);
+  for (int u = 0; 2 * u < nk; ++u) {
+    cp_async_wait<0>();
     __syncthreads();
-    {
-      const int nx = kt + STAGES - 1;
-      if (nx < nk) {
-        const int slot = nx % STAGES;
-        load_tile<TA, BM>(sA + slot * A_STAGE, gA, g.lda, row0, kb + (int64_t)nx * BK, tid);
-        load_tile<TBN ? 0 : 1, BN>(sB + slot * B_STAGE, gB, g.ldb, col0, kb + (int64_t)nx * BK, tid);
-      }
-      cp_async_commit();
-    }
-    const double* a_s = sA + (kt % STAGES) * A_STAGE;
-    const double* b_s = sB + (kt % STAGES) * B_STAGE;
-#pragma unroll
-    for (int k4 = 0; k4 < BK; k4 += 4) {
-      double af[WM], bf[WN];
+    issue_unit((u + 1) & 1, 2 * (u + 1));
+    // the unit's (up to) 8 k4-steps with explicitly double-buffered fragments: the LDS of step s+1
+    // are issued before the 32 DMMAs of step s
+    const int nsteps = (2 * u + 1 < nk) ? 8 : 4;
+    const double* a_u = sA + ((u & 1) * 2) * A_STAGE;
+    const double* b_u = sB + ((u & 1) * 2) * B_STAGE;
+    double af[2][WM], bf[2][WN];
+    auto load_frags = [&](int buf, int step) {
+      const double* a_s = a_u + (step >> 2) * A_STAGE;
+      const double* b_s = b_u + (step >> 2) * B_STAGE;
+      const int k4 = (step & 3) * 4;
 #pragma unroll
       for (int i = 0; i < WM; ++i) {
-        if (TA == 0) af[i] = a_s[(wm + i * 8 + fr) * LDK + k4 + fc];
-        else af[i] = a_s[(k4 + fc) * (BM + 4) + wm + i * 8 + fr];
+        if (TA == 0) af[buf][i] = a_s[(wm + i * 8 + fr) * LDK + k4 + fc];
+        else af[buf][i] = a_s[(k4 + fc) * (BM + 4) + wm + i * 8 + fr];
       }
 #pragma unroll
       for (int j = 0; j < WN; ++j) {
-        if (TBN) bf[j] = b_s[(wn + j * 8 + fr) * LDK + k4 + fc];
-        else bf[j] = b_s[(k4 + fc) * (BN + 4) + wn + j * 8 + fr];
+        if (TBN) bf[buf][j] = b_s[(wn + j * 8 + fr) * LDK + k4 + fc];
+        else bf[buf][j] = b_s[(k4 + fc) * (BN + 4) + wn + j * 8 + fr];
       }
+    };
+    load_frags(0, 0);
 #pragma unroll
-      for (int i = 0; i < WM; ++i)
+    for (int step = 0; step < 8; ++step) {
+      if (step < nsteps) {
+        if (step + 1 < nsteps) load_frags((step + 1) & 1, step + 1);
 #pragma unroll
-        for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int i = 0; i < WM; ++i)
+#pragma unroll
+          for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[step & 1][i], bf[step & 1][j]);
+      }
     }
   }
   cp_async_wait<0>();
@@ -222,13 +234,13 @@ static cudaEvent_t prof_event() {
   return g_prof.ev[g_prof.used++];
 }
 
-template <int TA, int TBN, int WM, int WN>
+template <int TA, int TBN, int WM, int WN, int GM>
 static int launch(cudaStream_t st, const LfmGemm& g) {
-  constexpr int BM = 16 * WM, BN = 32 * WN;
+  constexpr int BM = 8 * WM * GM, BN = 32 * WN;
   constexpr int SMEM = STAGES * (BM + BN) * LDK * 8;
   static bool configured = false;
   if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      SMEM));
     configured = true;
   }
@@ -242,19 +254,24 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
     g_prof.launches += 1;
   }
   const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
-  lfm_dgemm_kernel<TA, TBN, WM, WN><<<grid, 256, SMEM, st>>>(g, (int)tn);
+  lfm_dgemm_kernel<TA, TBN, WM, WN, GM><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
   if (g_prof.on) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
 
-template <int WM, int WN>
+template <int WM, int WN, int GM>
 static int dispatch(cudaStream_t st, const LfmGemm& g) {
-  if (g.transA == 0 && g.transB == 1) return launch<0, 1, WM, WN>(st, g);
-  if (g.transA == 0 && g.transB == 0) return launch<0, 0, WM, WN>(st, g);
-  if (g.transA == 1 && g.transB == 0) return launch<1, 0, WM, WN>(st, g);
-  return launch<1, 1, WM, WN>(st, g);
+  if (g.transA == 0 && g.transB == 1) return launch<0, 1, WM, WN, GM>(st, g);
+  if (g.transA == 0 && g.transB == 0) return launch<0, 0, WM, WN, GM>(st, g);
+  if (g.transA == 1 && g.transB == 0) return launch<1, 0, WM, WN, GM>(st, g);
+  return launch<1, 1, WM, WN, GM>(st, g);
+}
+static int big_variant() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LFM_GEMM_BIG"); v = e ? atoi(e) : 1; }
+  return v;
 }
 
 // Tile-shape heuristic: 128 x 128 tiles once they fill >= 3 waves of the 148 SMs, else 64 x 64 tiles
@@ -269,8 +286,8 @@ int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
   const bool inplace = (const double*)g.C == g.A;
   if (inplace) {
     if (g.N != 128) return LFM_ERR_INVALID;
-    return (t128 >= 148) ? dispatch<8, 4>(st, g) : dispatch<4, 4>(st, g);
+    return (t128 >= 148) ? dispatch<8, 4, 2>(st, g) : dispatch<4, 4, 2>(st, g);
   }
-  if (t128 >= 3 * 148) return dispatch<8, 4>(st, g);
-  return dispatch<4, 2>(st, g);
+  if (t128 >= 3 * 148) return big_variant() ? dispatch<4, 4, 4>(st, g) : dispatch<8, 4, 2>(st, g);
+  return dispatch<4, 2, 2>(st, g);
 }
