@@ -3,16 +3,25 @@
 //
 // Per step (JaxTrainer.step, src/trainer.py:105-131, inside the scan of :201-216):
 //   theta = constrain(u)                                   (trainer.py:103)
-//   Sigma = k_xx(X,X) + (jitter + sigma^2) I = L L^T        (objectives.py:70-73)
-//   W = L^-1 (columns in parallel), Sigma^-1 = W^T W (entries in parallel), alpha = W^T W z
-//   NLML = 1/2 [N log 2pi + 2 sum log L_ii + |W z|^2]       (objectives.py:76-78)
-//   grad = sum_ab K_bar_ab dK_ab/dtheta, K_bar = 1/2 (Sigma^-1 - alpha alpha^T)   (AD of trainer.py:126)
+//   Sigma = k_xx(X,X) + (jitter + sigma^2) I                (objectives.py:70-73)
+//   NLML  = 1/2 [N log 2pi + log det Sigma + z^T Sigma^-1 z] (objectives.py:76-78)
+//   grad  = sum_ab K_bar_ab dK_ab/dtheta, K_bar = 1/2 (Sigma^-1 - alpha alpha^T)   (AD of trainer.py:126)
 //   u <- adam(u, grad * dtheta/du); "fix p21" hook          (trainer.py:127-128, 133-160, 205-210)
 //
-// Shared-memory matrix S[N][ld] is used in three roles over a step: lower = Sigma -> L -> Sigma^-1 ->
-// K_bar-weighted row-gene derivative; upper = W^T -> column-gene derivative.  The sensitivity gradient
-// uses the identity diag(K_bar K) = 1/2 (1 - c Sinv_aa - alpha_a z_a + c alpha_a^2), c = jitter + sigma^2,
-// so no second copy of K is needed.  Every reduction has a fixed order: results are bit-reproducible.
+// Duplicate-row compression (exact).  The p53 layout repeats every (time, gene) row once per replicate
+// (dataset.py:380-391), so Sigma = c I + P K_u P^T with K_u the U x U Gram of the UNIQUE rows, P the
+// N x U 0/1 incidence and P^T P = R I (R = replicates), c = jitter + sigma^2.  With M = c I + R K_u:
+//   log det Sigma = (N - U) log c + log det M
+//   P^T Sigma^-1 P = R M^-1,   beta := P^T alpha = M^-1 q,  q = P^T z,   K_u beta = (q - c beta) / R
+//   z^T Sigma^-1 z = (z^T z - q^T K_u beta) / c,   alpha = (z - P K_u beta) / c
+//   sum_ij K_bar_ij dSigma_ij = sum_uv 1/2 (R M^-1 - beta beta^T)_uv dK_u,uv
+// so every O(N^3) / O(N^2 transcendental) term shrinks to U.  Rows without uniform duplication use
+// the same code with U = N, R = 1 (then M = Sigma, beta = alpha).  The sensitivity gradient uses
+// diag(P^T K_bar P K_u)_u = 1/2 (1 - c M^-1_uu - beta_u (K_u beta)_u): no second copy of K is kept.
+//
+// The U x U shared-memory matrix S changes role over a step: lower = M -> L -> M^-1 -> weighted
+// row-gene derivative; upper = W^T (W = L^-1) -> column-gene derivative.  Every reduction has a fixed
+// order: results are bit-reproducible.
 #include "sim_math.cuh"
 
 #define BT 256  // threads per CTA
@@ -46,29 +55,39 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
+__device__ __forceinline__ void pair_decode(int p, int& r, int& c) {
+  r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+  while ((r + 1) * (r + 2) / 2 <= p) ++r;
+  while (r * (r + 1) / 2 > p) --r;
+  c = p - r * (r + 1) / 2;
+}
+
 __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, G = a.G, P = 3 * G + 2;
-  const int ld = N | 1;
   const int tid = threadIdx.x;
   const int64_t bidx = blockIdx.x;
-  // carve shared memory
+  // ---- carve shared memory (matrix sized for the worst case U = N) ---------------------------------
   double* S = reinterpret_cast<double*>(smem_raw);
-  double* z = S + (size_t)N * ld;
-  double* w = z + N;
-  double* alpha = w + N;
-  double* wdiag = alpha + N;   // 1 / L_ii
-  double* sdiag = wdiag + N;   // Sinv_ii
-  double* dsum = sdiag + N;    // diagonal derivative term / per-point totals
-  double* th = dsum + N;       // P constrained
-  double* u = th + P;          // P unconstrained
-  double* gr = u + P;          // P gradient (constrained, then unconstrained)
-  double* am = gr + P;         // P adam m
-  double* av = am + P;         // P adam v
-  double* red = av + P;        // 8 + 2
+  double* q = S + (size_t)N * (N | 1);  // P^T z              (U)
+  double* w = q + N;                    // W q                (U)
+  double* beta = w + N;                 // M^-1 q             (U)
+  double* kb = beta + N;                // K_u beta           (U)
+  double* wdiag = kb + N;               // 1 / L_ii           (U)
+  double* sdiag = wdiag + N;            // M^-1_uu            (U)
+  double* dsum = sdiag + N;             // per-point decay-gradient totals (U)
+  double* th = dsum + N;                // P constrained
+  double* u = th + P;                   // P unconstrained
+  double* gr = u + P;                   // P gradient
+  double* am = gr + P;                  // P adam m
+  double* av = am + P;                  // P adam v
+  double* mu = av + P;                  // G positional means B/D
+  double* red = mu + G;                 // 16
   LfmPoint* pts = reinterpret_cast<LfmPoint*>(red + 16);
+  int* umap = reinterpret_cast<int*>(pts + N);  // row -> unique index      (N)
+  int* urow = umap + N;                         // unique index -> first row (N)
   __shared__ double piv;
-  __shared__ int fail;
+  __shared__ int fail, sU, sR;
 
   if (tid < P) {
     u[tid] = a.u_io[bidx * P + tid];
@@ -77,11 +96,63 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
     av[tid] = have ? a.adam[bidx * 2 * P + P + tid] : 0.0;
   }
   if (tid == 0) fail = 0;
+  // ---- duplicate-row detection (once): rep = first identical row; uniform multiplicity R? ----------
+  if (tid < N) {
+    int rep = tid;
+    const double t0 = a.X[3 * tid], g0 = a.X[3 * tid + 1], f0 = a.X[3 * tid + 2];
+    for (int j = 0; j < tid; ++j)
+      if (a.X[3 * j] == t0 && a.X[3 * j + 1] == g0 && a.X[3 * j + 2] == f0) { rep = j; break; }
+    umap[tid] = rep;  // temporarily the representative row
+  }
+  __syncthreads();
+  if (tid < N) {
+    int idx = 0, cnt = 0;
+    const int rep = umap[tid];
+    for (int j = 0; j < N; ++j) {
+      if (j < rep && umap[j] == j) ++idx;   // unique rows before my representative
+      if (umap[j] == rep) ++cnt;            // multiplicity of my class
+    }
+    urow[tid] = (rep == tid) ? idx : -1;    // temporarily: compact index if I am a representative
+    dsum[tid] = (double)cnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int U = 0, R = (int)dsum[0], uniform = 1;
+    for (int j = 0; j < N; ++j) {
+      if (urow[j] >= 0) ++U;
+      if ((int)dsum[j] != R) uniform = 0;
+    }
+    if (!uniform || R == 1) { U = N; R = 1; }
+    sU = U; sR = R;
+  }
+  __syncthreads();
+  const int U = sU, R = sR;
+  {
+    int mine = 0, first = 0;
+    if (tid < N) {
+      if (R == 1) { mine = tid; }
+      else {
+        const int rep = umap[tid];
+        int idx = 0;
+        for (int j = 0; j < rep; ++j) if (umap[j] == j) ++idx;
+        mine = idx;
+      }
+      first = (R == 1) ? 1 : (umap[tid] == tid);
+    }
+    __syncthreads();
+    if (tid < N) {
+      umap[tid] = mine;
+      if (first) urow[mine] = tid;
+    }
+  }
   __syncthreads();
 
-  const int npairs = N * (N + 1) / 2;
+  const int ld = U | 1;
+  const int npairs = U * (U + 1) / 2;
   const bool eval_only = a.eval_val != nullptr;
   const int nsteps = eval_only ? 1 : a.steps;
+  const int blk = N / G;  // rows per positional mean block (model.py:145)
+  const double dR = (double)R;
 
   for (int sidx = 0; sidx < nsteps; ++sidx) {
     const int step = a.first_step + sidx;
@@ -89,33 +160,45 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
     if (tid < P) th[tid] = (tid == 3 * G) ? lfm_l_forward(u[tid]) : lfm_softplus(u[tid]);
     __syncthreads();
     const double l = th[3 * G], inv_l = 1.0 / l, sigma = th[3 * G + 1];
-    const double cdiag = a.jitter + sigma * sigma;
-    // ---- B. points, residual -----------------------------------------------------------------
-    if (tid < N) {
-      pts[tid] = lfm_make_point(a.X + 3 * tid, G, th, th + G, l, true);
-      int block = N / G;
-      int m = tid / block;
-      if (m > G - 1) m = G - 1;
-      z[tid] = a.y[tid] - th[2 * G + m] / th[m] * (double)((int)a.X[3 * tid + 2]);
-    }
+    const double c = a.jitter + sigma * sigma;
+    // ---- B. unique points, q = P^T z, z^T z ------------------------------------------------------
+    if (tid < G) mu[tid] = th[2 * G + tid] / th[tid];
+    if (tid < U) pts[tid] = lfm_make_point(a.X + 3 * urow[tid], G, th, th + G, l, true);
     __syncthreads();
-    // ---- C. Sigma (lower + diagonal) ------------------------------------------------------------
+    double zz_part = 0.0;
+    if (tid < N) {
+      int m = tid / blk;
+      if (m > G - 1) m = G - 1;
+      const double zi = a.y[tid] - mu[m] * (double)((int)a.X[3 * tid + 2]);
+      zz_part = zi * zi;
+    }
+    const double zz = block_sum(zz_part, red);
+    if (tid < U) {
+      double acc = 0.0;
+      for (int i = 0; i < N; ++i) {
+        if (umap[i] == tid) {
+          int m = i / blk;
+          if (m > G - 1) m = G - 1;
+          acc += a.y[i] - mu[m] * (double)((int)a.X[3 * i + 2]);
+        }
+      }
+      q[tid] = acc;
+    }
+    // ---- C. M = c I + R K_u (lower + diagonal) -------------------------------------------------------
     for (int p = tid; p < npairs; p += BT) {
-      int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-      while ((r + 1) * (r + 2) / 2 <= p) ++r;
-      while (r * (r + 1) / 2 > p) --r;
-      const int c = p - r * (r + 1) / 2;
-      double k = lfm_kxx(pts[r], pts[c], l, inv_l);
-      if (r == c) k += cdiag;
-      S[r * ld + c] = k;
+      int r, cc;
+      pair_decode(p, r, cc);
+      double k = dR * lfm_kxx(pts[r], pts[cc], l, inv_l);
+      if (r == cc) k += c;
+      S[r * ld + cc] = k;
     }
     __syncthreads();
     // ---- D. Cholesky, left-looking, two threads per row -----------------------------------------
     {
       const int row = tid >> 1, half = tid & 1;
-      for (int k = 0; k < N; ++k) {
+      for (int k = 0; k < U; ++k) {
         double v = 0.0;
-        if (row >= k && row < N) {
+        if (row >= k && row < U) {
           const double* ri = S + row * ld;
           const double* rk = S + k * ld;
           double s0 = 0.0, s1 = 0.0;
@@ -125,112 +208,113 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
           v = s0 + s1;
         }
         v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if (row >= k && row < N) {
+        if (row >= k && row < U) {
           v = S[row * ld + k] - v;
           if (row == k && half == 0) piv = v;
         }
         __syncthreads();
         const double p = piv;
         if (tid == 0 && !(p > 0.0) && fail == 0) fail = k + 1;
-        if (row >= k && row < N && half == 0) {
+        if (row >= k && row < U && half == 0) {
           const double dk = sqrt(p);
           S[row * ld + k] = (row == k) ? dk : v / dk;
         }
         __syncthreads();
       }
     }
-    // ---- E. log det, W = L^-1 into the upper triangle (thread c owns column c) -------------------
+    // ---- E. log det M, W = L^-1 into the upper triangle (thread cc owns column cc) -----------------
     double logdet_part = 0.0;
-    if (tid < N) {
+    if (tid < U) {
       const double lii = S[tid * ld + tid];
       logdet_part = log(lii);
       wdiag[tid] = 1.0 / lii;
     }
-    const double logdet = 2.0 * block_sum(logdet_part, red);
-    if (tid < N) {
-      const int c = tid;
-      const double wcc = wdiag[c];
+    const double logdetM = 2.0 * block_sum(logdet_part, red);
+    if (tid < U) {
+      const int cc = tid;
+      const double wcc = wdiag[cc];
       const int cmin = (tid >> 5) << 5;
-      double* wc = S + c * ld;  // wc[i] = W[i][c] for i > c (row c of the upper triangle)
-      for (int i = cmin + 1; i < N; ++i) {
+      double* wc = S + cc * ld;  // wc[i] = W[i][cc] for i > cc (row cc of the upper triangle)
+      for (int i = cmin + 1; i < U; ++i) {
         const double* li = S + i * ld;
         double s0 = 0.0, s1 = 0.0;
         int k = cmin;
         for (; k + 2 <= i; k += 2) {
-          const double w0 = (k == c) ? wcc : wc[k];
-          const double w1 = (k + 1 == c) ? wcc : wc[k + 1];
-          if (k >= c) s0 += li[k] * w0;
-          if (k + 1 >= c) s1 += li[k + 1] * w1;
+          const double w0 = (k == cc) ? wcc : wc[k];
+          const double w1 = (k + 1 == cc) ? wcc : wc[k + 1];
+          if (k >= cc) s0 += li[k] * w0;
+          if (k + 1 >= cc) s1 += li[k + 1] * w1;
         }
         for (; k < i; ++k) {
-          const double w0 = (k == c) ? wcc : wc[k];
-          if (k >= c) s0 += li[k] * w0;
+          const double w0 = (k == cc) ? wcc : wc[k];
+          if (k >= cc) s0 += li[k] * w0;
         }
-        if (i > c) wc[i] = -(s0 + s1) * wdiag[i];
+        if (i > cc) wc[i] = -(s0 + s1) * wdiag[i];
       }
     }
     __syncthreads();
-    // ---- F. w = W z, alpha = W^T w ------------------------------------------------------------------
-    double quad_part = 0.0;
-    if (tid < N) {
-      double acc = wdiag[tid] * z[tid];
-      for (int k = 0; k < tid; ++k) acc += S[k * ld + tid] * z[k];
+    // ---- F. w = W q, beta = W^T w, K_u beta = (q - c beta) / R ------------------------------------------
+    if (tid < U) {
+      double acc = wdiag[tid] * q[tid];
+      for (int k = 0; k < tid; ++k) acc += S[k * ld + tid] * q[k];
       w[tid] = acc;
-      quad_part = acc * acc;
     }
-    const double quad = block_sum(quad_part, red);
-    if (tid < N) {
+    __syncthreads();
+    double qkb_part = 0.0, kbkb_part = 0.0;
+    if (tid < U) {
       double acc = wdiag[tid] * w[tid];
       const double* uj = S + tid * ld;
-      for (int i = tid + 1; i < N; ++i) acc += uj[i] * w[i];
-      alpha[tid] = acc;
+      for (int i = tid + 1; i < U; ++i) acc += uj[i] * w[i];
+      beta[tid] = acc;
+      const double kbv = (q[tid] - c * acc) / dR;
+      kb[tid] = kbv;
+      qkb_part = q[tid] * kbv;
+      kbkb_part = kbv * kbv;
     }
-    const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + logdet + quad);
-    // ---- G. Sigma^-1 = W^T W into the lower triangle (+ sdiag), every entry independent ------------
+    const double qkb = block_sum(qkb_part, red);
+    const double kbkb = block_sum(kbkb_part, red);
+    const double quad = (zz - qkb) / c;
+    const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
+    // ---- G. M^-1 = W^T W into the lower triangle (+ sdiag), every entry independent --------------------
     for (int p = tid; p < npairs; p += BT) {
-      int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-      while ((r + 1) * (r + 2) / 2 <= p) ++r;
-      while (r * (r + 1) / 2 > p) --r;
-      const int c = p - r * (r + 1) / 2;
-      // Sinv[r][c] = sum_{k >= r} W[k][r] W[k][c];  W[k][r] = S[r][k] (k > r), W[r][r] = wdiag[r]
+      int r, cc;
+      pair_decode(p, r, cc);
+      // Minv[r][cc] = sum_{k >= r} W[k][r] W[k][cc];  W[k][r] = S[r][k] (k > r), W[r][r] = wdiag[r]
       const double* ur = S + r * ld;
-      const double* uc = S + c * ld;
-      double s0 = wdiag[r] * ((r == c) ? wdiag[r] : uc[r]);
+      const double* uc = S + cc * ld;
+      double s0 = wdiag[r] * ((r == cc) ? wdiag[r] : uc[r]);
       double s1 = 0.0;
       int k = r + 1;
-      for (; k + 2 <= N; k += 2) { s0 += ur[k] * uc[k]; s1 += ur[k + 1] * uc[k + 1]; }
-      for (; k < N; ++k) s0 += ur[k] * uc[k];
+      for (; k + 2 <= U; k += 2) { s0 += ur[k] * uc[k]; s1 += ur[k + 1] * uc[k + 1]; }
+      for (; k < U; ++k) s0 += ur[k] * uc[k];
       const double v = s0 + s1;
-      if (r == c) sdiag[r] = v;
-      else S[r * ld + c] = v;  // lower; L is dead
+      if (r == cc) sdiag[r] = v;
+      else S[r * ld + cc] = v;  // lower; L is dead
     }
     __syncthreads();
-    // ---- H/I. fused derivative contraction over the lower triangle ----------------------------------
+    // ---- H. fused derivative contraction over the lower triangle of the unique pairs --------------------
     double dl_part = 0.0;
     for (int p = tid; p < npairs; p += BT) {
-      int r = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
-      while ((r + 1) * (r + 2) / 2 <= p) ++r;
-      while (r * (r + 1) / 2 > p) --r;
-      const int c = p - r * (r + 1) / 2;
-      const double sinv = (r == c) ? sdiag[r] : S[r * ld + c];
-      const double wgt = ((r == c) ? 0.5 : 1.0) * (sinv - alpha[r] * alpha[c]);
+      int r, cc;
+      pair_decode(p, r, cc);
+      const double minv = (r == cc) ? sdiag[r] : S[r * ld + cc];
+      const double wgt = ((r == cc) ? 0.5 : 1.0) * (dR * minv - beta[r] * beta[cc]);
       double k, dr, dc, dl;
-      lfm_kxx_grad(pts[r], pts[c], l, inv_l, k, dr, dc, dl);
+      lfm_kxx_grad(pts[r], pts[cc], l, inv_l, k, dr, dc, dl);
       dl_part += wgt * dl;
-      if (r == c) dsum[r] = wgt * (dr + dc);
-      else { S[r * ld + c] = wgt * dr; S[c * ld + r] = wgt * dc; }
+      if (r == cc) dsum[r] = wgt * (dr + dc);
+      else { S[r * ld + cc] = wgt * dr; S[cc * ld + r] = wgt * dc; }
     }
     const double gl = block_sum(dl_part, red);
-    // per-point totals: full row sums
-    if (tid < N) {
+    if (tid < U) {  // per-point totals: full row sums
       const double* rp = S + tid * ld;
       double s0 = dsum[tid], s1 = 0.0;
-      int c = 0;
-      for (; c + 2 <= N; c += 2) {
-        s0 += (c == tid) ? 0.0 : rp[c];
-        s1 += (c + 1 == tid) ? 0.0 : rp[c + 1];
+      int cc = 0;
+      for (; cc + 2 <= U; cc += 2) {
+        s0 += (cc == tid) ? 0.0 : rp[cc];
+        s1 += (cc + 1 == tid) ? 0.0 : rp[cc + 1];
       }
-      for (; c < N; ++c) s0 += (c == tid) ? 0.0 : rp[c];
+      for (; cc < U; ++cc) s0 += (cc == tid) ? 0.0 : rp[cc];
       dsum[tid] = s0 + s1;
     }
     __syncthreads();
@@ -238,24 +322,28 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
     if (tid < G) {
       const int m = tid;
       double gd = 0.0, gs = 0.0, asum = 0.0;
-      for (int i = 0; i < N; ++i) {
+      for (int i = 0; i < U; ++i) {
         if (pts[i].gene == m) {
           gd += dsum[i];
-          gs += 1.0 - cdiag * sdiag[i] - alpha[i] * z[i] + cdiag * alpha[i] * alpha[i];
+          gs += 1.0 - c * sdiag[i] - beta[i] * kb[i];
         }
       }
-      const int block = N / G;
-      for (int i = m * block; i < (m + 1) * block; ++i) asum += alpha[i];
+      // asum_m = sum_{i in positional block m} alpha_i,  alpha_i = (z_i - (K_u beta)_{u(i)}) / c
+      for (int i = m * blk; i < (m + 1) * blk; ++i)
+        asum += a.y[i] - mu[m] * (double)((int)a.X[3 * i + 2]) - kb[umap[i]];
+      asum /= c;
       const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
       gr[m] = gd + asum * Bm / (D * D);
       gr[G + m] = gs / Sm;
       gr[2 * G + m] = -asum / D;
     }
     if (tid == G) {
-      double tr = 0.0, aa = 0.0;
-      for (int i = 0; i < N; ++i) { tr += sdiag[i]; aa += alpha[i] * alpha[i]; }
+      double tr = 0.0;
+      for (int i = 0; i < U; ++i) tr += sdiag[i];
+      const double trSinv = ((double)(N - U) + c * tr) / c;
+      const double aa = (zz - 2.0 * qkb + dR * kbkb) / (c * c);
       gr[3 * G] = gl;
-      gr[3 * G + 1] = sigma * (tr - aa);
+      gr[3 * G + 1] = sigma * (trSinv - aa);
     }
     __syncthreads();
     // ---- K. chain rule, Adam, hook ----------------------------------------------------------------
@@ -310,8 +398,8 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
 static size_t batched_smem_bytes(int N, int G) {
   const size_t P = 3 * (size_t)G + 2;
   const size_t ld = (size_t)(N | 1);
-  size_t d = (size_t)N * ld + 6 * (size_t)N + 5 * P + 16;
-  return d * 8 + (size_t)N * sizeof(LfmPoint);
+  size_t d = (size_t)N * ld + 7 * (size_t)N + 5 * P + (size_t)G + 16;
+  return d * 8 + (size_t)N * sizeof(LfmPoint) + 2 * (size_t)N * sizeof(int);
 }
 
 static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
