@@ -51,9 +51,10 @@ SIGNATURES = {
     "lfm_latent_posterior_workspace_bytes": (_sz, [_i64, _int, _i64]),
     "lfm_latent_posterior": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _ptr, _sz,
                                     _ptr, _ptr, _ptr]),
-    "lfm_batched_nlml_grad_unc": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _ptr, _ptr]),
+    "lfm_count_unique_rows": (_int, [_i64, _ptr]),
+    "lfm_batched_nlml_grad_unc": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _dbl, _int, _ptr, _ptr, _ptr]),
     "lfm_batched_fit": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
-                               _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr]),
+                               _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr]),
     "lfm_handle_create": (_int, [C.POINTER(_ptr)]),
     "lfm_handle_destroy": (_int, [_ptr]),
     "lfm_nlml_grad_host": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _int, _ptr, _ptr]),

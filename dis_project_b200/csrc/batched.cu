@@ -24,7 +24,6 @@
 // order: results are bit-reproducible.
 #include "sim_math.cuh"
 
-#define BT 256  // threads per CTA
 
 struct BatchedArgs {
   int64_t B;
@@ -40,8 +39,10 @@ struct BatchedArgs {
   double* eval_val;   // eval-only mode: B
   double* eval_grad;  // eval-only mode: B x P
   int* info;
+  int max_unique;     // shared-memory matrix is sized for this many unique rows (N when unknown)
 };
 
+template <int BT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
   // fixed-order block reduction; all BT threads must call
 #pragma unroll
@@ -62,14 +63,17 @@ __device__ __forceinline__ void pair_decode(int p, int& r, int& c) {
   c = p - r * (r + 1) / 2;
 }
 
-__global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
+// BT = 128 when the unique rows fit 64 (two threads per row in the Cholesky), else 256.
+template <int BT>
+__global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(BatchedArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, G = a.G, P = 3 * G + 2;
   const int tid = threadIdx.x;
   const int64_t bidx = blockIdx.x;
   // ---- carve shared memory (matrix sized for the worst case U = N) ---------------------------------
+  const int MU = a.max_unique;
   double* S = reinterpret_cast<double*>(smem_raw);
-  double* q = S + (size_t)N * (N | 1);  // P^T z              (U)
+  double* q = S + (size_t)MU * (MU | 1);  // P^T z            (U)
   double* w = q + N;                    // W q                (U)
   double* beta = w + N;                 // M^-1 q             (U)
   double* kb = beta + N;                // K_u beta           (U)
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
       if ((int)dsum[j] != R) uniform = 0;
     }
     if (!uniform || R == 1) { U = N; R = 1; }
+    if (U > MU) { U = 0; fail = -1; }  // caller's unique-row bound was wrong: refuse (info = -1)
     sU = U; sR = R;
   }
   __syncthreads();
@@ -172,7 +177,7 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
       const double zi = a.y[tid] - mu[m] * (double)((int)a.X[3 * tid + 2]);
       zz_part = zi * zi;
     }
-    const double zz = block_sum(zz_part, red);
+    const double zz = block_sum<BT>(zz_part, red);
     if (tid < U) {
       double acc = 0.0;
       for (int i = 0; i < N; ++i) {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
       logdet_part = log(lii);
       wdiag[tid] = 1.0 / lii;
     }
-    const double logdetM = 2.0 * block_sum(logdet_part, red);
+    const double logdetM = 2.0 * block_sum<BT>(logdet_part, red);
     if (tid < U) {
       const int cc = tid;
       const double wcc = wdiag[cc];
@@ -271,8 +276,8 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
       qkb_part = q[tid] * kbv;
       kbkb_part = kbv * kbv;
     }
-    const double qkb = block_sum(qkb_part, red);
-    const double kbkb = block_sum(kbkb_part, red);
+    const double qkb = block_sum<BT>(qkb_part, red);
+    const double kbkb = block_sum<BT>(kbkb_part, red);
     const double quad = (zz - qkb) / c;
     const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
     // ---- G. M^-1 = W^T W into the lower triangle (+ sdiag), every entry independent --------------------
@@ -305,7 +310,7 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
       if (r == cc) dsum[r] = wgt * (dr + dc);
       else { S[r * ld + cc] = wgt * dr; S[cc * ld + r] = wgt * dc; }
     }
-    const double gl = block_sum(dl_part, red);
+    const double gl = block_sum<BT>(dl_part, red);
     if (tid < U) {  // per-point totals: full row sums
       const double* rp = S + tid * ld;
       double s0 = dsum[tid], s1 = 0.0;
@@ -395,25 +400,37 @@ __global__ void __launch_bounds__(BT) lfm_batched_kernel(BatchedArgs a) {
   }
 }
 
-static size_t batched_smem_bytes(int N, int G) {
+static size_t batched_smem_bytes(int N, int G, int MU) {
   const size_t P = 3 * (size_t)G + 2;
-  const size_t ld = (size_t)(N | 1);
-  size_t d = (size_t)N * ld + 7 * (size_t)N + 5 * P + (size_t)G + 16;
+  const size_t ld = (size_t)(MU | 1);
+  size_t d = (size_t)MU * ld + 7 * (size_t)N + 5 * P + (size_t)G + 16;
   return d * 8 + (size_t)N * sizeof(LfmPoint) + 2 * (size_t)N * sizeof(int);
 }
 
 static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
   if (a.B <= 0 || a.N <= 0 || a.G <= 0 || !a.X || !a.y || !a.u_io) return LFM_ERR_INVALID;
   if (a.N % a.G) return LFM_ERR_INVALID;
-  if (a.N > 128 || 3 * a.G + 2 > BT || a.B > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
-  const size_t smem = batched_smem_bytes(a.N, a.G);
+  if (a.N > 128 || a.B > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
+  BatchedArgs b = a;
+  if (b.max_unique <= 0 || b.max_unique > b.N) b.max_unique = b.N;
+  const size_t smem = batched_smem_bytes(b.N, b.G, b.max_unique);
   if (smem > 227 * 1024) return LFM_ERR_UNSUPPORTED;
-  static size_t configured = 0;
-  if (smem > configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  const bool small = b.max_unique <= 64 && b.N <= 128 && 3 * b.G + 2 <= 128;
+  if (!small && 3 * b.G + 2 > 256) return LFM_ERR_UNSUPPORTED;
+  static size_t conf128 = 0, conf256 = 0;
+  if (small) {
+    if (smem > conf128) {
+      LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conf128 = smem;
+    }
+    lfm_batched_kernel<128><<<(unsigned)b.B, 128, smem, st>>>(b);
+  } else {
+    if (smem > conf256) {
+      LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conf256 = smem;
+    }
+    lfm_batched_kernel<256><<<(unsigned)b.B, 256, smem, st>>>(b);
   }
-  lfm_batched_kernel<<<(unsigned)a.B, BT, smem, st>>>(a);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
@@ -421,14 +438,14 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
 
 extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
                                          const double* y, const double* theta_unc, double jitter,
-                                         double* out_val, double* out_grad, int* info) {
+                                         int unique_rows_hint, double* out_val, double* out_grad, int* info) {
   if (!out_val || !out_grad) return LFM_ERR_INVALID;
   BatchedArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y;
   a.u_io = const_cast<double*>(theta_unc);  // read-only in eval mode
   a.jitter = jitter; a.steps = 1; a.total_steps = 1; a.steps_per_epoch = 1;
-  a.eval_val = out_val; a.eval_grad = out_grad; a.info = info;
+  a.eval_val = out_val; a.eval_grad = out_grad; a.info = info; a.max_unique = unique_rows_hint;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
   return batched_launch((cudaStream_t)stream, a);
 }
@@ -436,8 +453,8 @@ extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t
 extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
                                double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                                double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
-                               int steps_per_epoch, double* out_hist, int64_t ld_hist, double* out_theta,
-                               int* info) {
+                               int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
+                               double* out_theta, int* info) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
@@ -447,6 +464,20 @@ extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G,
   a.jitter = jitter; a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
-  a.info = info;
+  a.info = info; a.max_unique = unique_rows_hint;
   return batched_launch((cudaStream_t)stream, a);
+}
+
+// Number of distinct (time, gene, flag) rows of a HOST copy of X: the `unique_rows_hint` that lets the
+// batched kernels size their shared memory by the compressed problem.
+extern "C" int lfm_count_unique_rows(int64_t N, const double* X_host) {
+  if (N <= 0 || !X_host) return 0;
+  int U = 0;
+  for (int64_t i = 0; i < N; ++i) {
+    bool dup = false;
+    for (int64_t j = 0; j < i && !dup; ++j)
+      dup = X_host[3 * j] == X_host[3 * i] && X_host[3 * j + 1] == X_host[3 * i + 1] && X_host[3 * j + 2] == X_host[3 * i + 2];
+    if (!dup) ++U;
+  }
+  return U;
 }

@@ -182,8 +182,18 @@ def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):
     return mean, var, info
 
 
+def unique_rows(X) -> int:
+    """Number of distinct (time, gene, flag) rows (host-side; X is at most 128 x 3 on this path)."""
+    import numpy as np
+
+    Xh = X.detach().cpu().numpy() if isinstance(X, torch.Tensor) else np.asarray(X, dtype=np.float64)
+    Xh = np.ascontiguousarray(Xh, dtype=np.float64)
+    return int(_lib.lib().lfm_count_unique_rows(Xh.shape[0], Xh.ctypes.data))
+
+
 def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
     """B independent value_and_grad evaluations.  theta_unc (B, P) -> (val[B], grad[B,P], info[B])."""
+    hint = unique_rows(X)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     u = _dev(theta_unc)
@@ -197,7 +207,8 @@ def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
     if B == 0:
         return val, grad, info
     _lib.check(_lib.lib().lfm_batched_nlml_grad_unc(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), u.data_ptr(),
-                                                    float(jitter), val.data_ptr(), grad.data_ptr(), info.data_ptr()),
+                                                    float(jitter), hint, val.data_ptr(), grad.data_ptr(),
+                                                    info.data_ptr()),
                "lfm_batched_nlml_grad_unc")
     return val, grad, info
 
@@ -219,12 +230,15 @@ class BatchedFitState:
         self.theta = torch.empty((self.B, self.P), dtype=F64, device=dev)
         self.info = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.step = 0
+        self.unique_hint = 0  # filled from X on the first batched_fit_steps call
 
 
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
                       b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
                       steps_per_epoch: int = 1000) -> None:
     """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216)."""
+    if state.unique_hint == 0:
+        state.unique_hint = unique_rows(X)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     if state.B == 0 or steps <= 0:
@@ -233,7 +247,8 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     _lib.check(_lib.lib().lfm_batched_fit(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
                                           state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
                                           state.step, steps, state.total_steps, int(bool(fix_params)),
-                                          int(steps_per_epoch), state.hist.data_ptr(), state.hist.shape[1],
+                                          int(steps_per_epoch), state.unique_hint, state.hist.data_ptr(),
+                                          state.hist.shape[1],
                                           state.theta.data_ptr(), state.info.data_ptr()), "lfm_batched_fit")
     state.step += steps
 

@@ -110,11 +110,17 @@ int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const double* X,
 
 /* ---- batched multi-start path (many independent small LFMs per GPU) -------------------------- */
 
+/* Number of distinct rows of a HOST copy of X.  Passing it as `unique_rows_hint` lets the batched
+ * kernels size their shared memory for the duplicate-row-compressed problem (the p53 layout repeats
+ * each (time, gene) row once per replicate); 0 means "unknown" (sized for N).  A hint smaller than
+ * the true count makes the kernels refuse with info = -1. */
+int lfm_count_unique_rows(int64_t N, const double* X_host);
+
 /* B independent value_and_grad evaluations sharing (X, y): theta_unc is B x P, out_val B,
  * out_grad B x P, info B ints.  N <= 128. */
 int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
-                              const double* y, const double* theta_unc, double jitter, double* out_val,
-                              double* out_grad, int* info);
+                              const double* y, const double* theta_unc, double jitter,
+                              int unique_rows_hint, double* out_val, double* out_grad, int* info);
 
 /* B independent JaxTrainer.fit loops (src/trainer.py:162-228) with optax.adam(lr) restated
  * (b1,b2,eps as given; src/main.py:45) and the "fix p21" hook of trainer.py:133-160,205-210,218-220.
@@ -128,7 +134,8 @@ int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, 
 int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
                     double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                     double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
-                    int steps_per_epoch, double* out_hist, int64_t ld_hist, double* out_theta, int* info);
+                    int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
+                    double* out_theta, int* info);
 
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */
