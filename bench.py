@@ -143,6 +143,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: ONE JSON line only
         dist.init_process_group("nccl", device_id=dev)
     from dis_project_b200 import _lib, ops
     from dis_project_b200.batched import make_restarts, multi_start_fit

@@ -51,6 +51,9 @@ SIGNATURES = {
     "lfm_latent_posterior_workspace_bytes": (_sz, [_i64, _int, _i64]),
     "lfm_latent_posterior": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _ptr, _sz,
                                     _ptr, _ptr, _ptr]),
+    "lfm_gene_posterior_workspace_bytes": (_sz, [_i64, _int, _i64]),
+    "lfm_gene_posterior": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _ptr, _sz,
+                                  _ptr, _ptr, _ptr, _ptr]),
     "lfm_count_unique_rows": (_int, [_i64, _ptr]),
     "lfm_batched_nlml_grad_unc": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _dbl, _int, _ptr, _ptr, _ptr]),
     "lfm_batched_fit": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
@@ -93,10 +96,18 @@ def check(status: int, where: str) -> None:
         raise LfmError(status, where)
 
 
+_device_ok = False
+
+
 def require_device() -> None:
-    """Fail loudly unless an sm_100 GPU is usable (no silent fallback)."""
+    """Fail loudly unless an sm_100 GPU is usable (no silent fallback).  The positive answer is cached:
+    cudaGetDeviceProperties costs milliseconds."""
+    global _device_ok
+    if _device_ok:
+        return
     import torch
 
     if not torch.cuda.is_available():
         raise RuntimeError("dis_project_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     check(lib().lfm_device_check(), "lfm_device_check")
+    _device_ok = True

@@ -192,6 +192,10 @@ class ExactLFM:
         return GaussianDistribution(mean, var)
 
     def multi_gene_predict(self, test_inputs, train_data: JaxP53Data) -> GaussianDistribution:
-        raise NotImplementedError(
-            "multi_gene_predict (reference model.py:465-514) is the first 'next' row of SURVEY.md 8(f); "
-            "not built in this round")
+        """Posterior of the gene expressions at `test_inputs` (reference model.py:465-514): noise model
+        K + diag(measurement variances) + obs_stddev^2 I (no jitter), full predictive covariance
+        K_tt - K_tx Sigma^-1 K_xt + jitter I."""
+        x, y, variances = dataset_3d(train_data)
+        t = _to_host(test_inputs)
+        mean, cov, var, info = ops.gene_posterior(x, y, variances, self.pack(), self.jitter, t, self.num_genes)
+        return GaussianDistribution(mean, cov)

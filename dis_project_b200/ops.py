@@ -182,6 +182,31 @@ def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):
     return mean, var, info
 
 
+def gene_posterior(X, y, variances, theta, jitter: float, Xstar, G: int, full_cov: bool = True):
+    """ExactLFM.multi_gene_predict (reference src/model.py:465-514): (mean[T*], cov[T*,T*] or None, var[T*], info)."""
+    X = _rows3(X, "x")
+    Xs = _rows3(Xstar, "test_inputs")
+    y = _dev(y).reshape(-1)
+    variances = _dev(variances).reshape(-1)
+    theta = _theta(theta, G)
+    N, T = X.shape[0], Xs.shape[0]
+    if y.numel() != N or variances.numel() != N:
+        raise ValueError("y / variances do not match the number of training rows")
+    if N % G or T % G:
+        raise ValueError("mean_function: rows must be divisible by num_genes (model.py:145-149)")
+    l = _lib.lib()
+    mean = torch.empty(T, dtype=F64, device=X.device)
+    var = torch.empty(T, dtype=F64, device=X.device)
+    cov = torch.empty((T, T), dtype=F64, device=X.device) if full_cov else None
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    ws = _workspace(l.lfm_gene_posterior_workspace_bytes(N, G, T), X.device, "gene")
+    _lib.check(l.lfm_gene_posterior(_stream(), N, G, X.data_ptr(), y.data_ptr(), variances.data_ptr(), theta.data_ptr(),
+                                    float(jitter), T, Xs.data_ptr(), ws.data_ptr(), ws.numel(), mean.data_ptr(),
+                                    cov.data_ptr() if full_cov else None, var.data_ptr(), info.data_ptr()),
+               "lfm_gene_posterior")
+    return mean, cov, var, info
+
+
 def unique_rows(X) -> int:
     """Number of distinct (time, gene, flag) rows (host-side; X is at most 128 x 3 on this path)."""
     import numpy as np

@@ -20,6 +20,37 @@ def generate_test_times_pred(t: Optional[int] = 100, num_genes: int = 5) -> np.n
     return np.stack((times, genes, np.ones(times.shape[0])), axis=1)
 
 
+class GeneExpressionPredictor:
+    """Gene-expression predictions of a trained model (reference utils.py:40-234), without the
+    matplotlib part: `predict()` returns what `plot_predictions` would draw."""
+
+    def __init__(self, model, p53_data, t: Optional[int] = 100):
+        self.model = model
+        self.p53_data = p53_data
+        self.num_genes = p53_data.num_genes
+        self.gene_names = p53_data.gene_names
+        self.t = t
+
+    def generate_test_times_pred(self) -> np.ndarray:
+        return generate_test_times_pred(self.t, self.num_genes)
+
+    def decompose_predictions(self, pred) -> tuple:
+        return tuple(pred[i * self.t:(i + 1) * self.t] for i in range(self.num_genes))
+
+    def decompose_predictions2(self, pred) -> tuple:
+        """Five-gene variant with blocks 3 and 4 swapped, as the reference does (utils.py:135-140)."""
+        n = self.t
+        g1, g2, g4, g3, g5 = pred[:n], pred[n:2 * n], pred[2 * n:3 * n], pred[3 * n:4 * n], pred[4 * n:]
+        return g1, g2, g3, g4, g5
+
+    def predict(self):
+        """(test_times, means per gene, stddevs per gene) -- reference utils.py:173-182."""
+        xpr_times = self.generate_test_times_pred()
+        dist = self.model.multi_gene_predict(xpr_times, self.p53_data)
+        split = self.decompose_predictions2 if self.num_genes == 5 else self.decompose_predictions
+        return xpr_times, split(dist.mean()), split(dist.stddev())
+
+
 def print_hyperparams(model, dataset, file: Optional[str] = None) -> list:
     """Table of learned B, S, D per gene plus l (reference utils.py:237-265).  Returns the rows;
     writes a CSV when `file` is given."""

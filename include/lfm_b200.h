@@ -108,6 +108,16 @@ int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const double* X,
                          const double* Xstar, void* ws, size_t ws_bytes, double* out_mean,
                          double* out_var, int* info);
 
+/* ExactLFM.multi_gene_predict(test_inputs, train_data) (src/model.py:465-514; SURVEY 8f "next" row 1):
+ * Sigma_g = K + diag(variances) + sigma^2 I (no jitter); mean = mean_t + K_tx Sigma_g^-1 (y - mean_x);
+ * cov = K_tt - K_tx Sigma_g^-1 K_xt + jitter I.  out_cov (T* x T* row-major) and out_var (its diagonal)
+ * may each be NULL.  Tstar % G must be 0 (mean_function's reshape). */
+size_t lfm_gene_posterior_workspace_bytes(int64_t N, int G, int64_t Tstar);
+int lfm_gene_posterior(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                       const double* variances, const double* theta, double jitter, int64_t Tstar,
+                       const double* Xstar, void* ws, size_t ws_bytes, double* out_mean, double* out_cov,
+                       double* out_var, int* info);
+
 /* ---- batched multi-start path (many independent small LFMs per GPU) -------------------------- */
 
 /* Number of distinct rows of a HOST copy of X.  Passing it as `unique_rows_hint` lets the batched

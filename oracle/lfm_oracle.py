@@ -197,9 +197,16 @@ def kernel_ff(p: Params, t, tp):
     return np.exp(-np.square(t - tp) / (2.0 * p.l))
 
 
-def _gene_index(col):
-    # .astype(int) on the float gene column (model.py:223-224); -1 wraps like jnp/np indexing
-    return np.asarray(col, dtype=np.float64).astype(np.int64)
+_CLAMP_G = None  # set by cross_covariance: jnp clamps out-of-range indices
+
+
+def _gene_index(col, G=None):
+    # .astype(int) on the float gene column (model.py:223-224); jnp indexing: negatives wrap, then clamp
+    g = np.asarray(col, dtype=np.float64).astype(np.int64)
+    if G is not None:
+        g = np.where(g < 0, g + G, g)
+        g = np.clip(g, 0, G - 1)
+    return g
 
 
 def cross_covariance(p: Params, x: np.ndarray, y: np.ndarray) -> np.ndarray:
@@ -209,8 +216,8 @@ def cross_covariance(p: Params, x: np.ndarray, y: np.ndarray) -> np.ndarray:
     y = np.asarray(y, dtype=np.float64)
     t = x[:, 0][:, None]
     tp = y[:, 0][None, :]
-    j = _gene_index(x[:, 1])[:, None]
-    k = _gene_index(y[:, 1])[None, :]
+    j = _gene_index(x[:, 1], p.num_genes)[:, None]
+    k = _gene_index(y[:, 1], p.num_genes)[None, :]
     f1 = x[:, 2].astype(np.int64)[:, None]
     f2 = y[:, 2].astype(np.int64)[None, :]
     kxx_sw = f1 * f2
@@ -468,6 +475,34 @@ def latent_predict(p: Params, test_inputs: np.ndarray, x: np.ndarray, y: np.ndar
         kdiag = np.array([float(cross_covariance(p, t[i:i + 1], t[i:i + 1])[0, 0]) for i in range(t.shape[0])])
     var = kdiag + p.jitter - np.sum(V * V, axis=0) + p.jitter
     return mean, var
+
+
+def multi_gene_predict(p: Params, test_inputs: np.ndarray, x: np.ndarray, y: np.ndarray, variances: np.ndarray):
+    """model.py:465-514: returns (mean (T*,), cov (T*,T*)).  Noise model K + diag(var) + sigma^2 I (Q2)."""
+    x = np.asarray(x, dtype=np.float64)
+    t = np.asarray(test_inputs, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    variances = np.asarray(variances, dtype=np.float64).reshape(-1)
+    mean_x = mean_function(p, x)
+    Sigma = gram(p, x)
+    Sigma[np.diag_indices_from(Sigma)] += variances
+    Sigma[np.diag_indices_from(Sigma)] += p.sigma**2
+    mean_t = mean_function(p, t)
+    Ktt = gram(p, t)
+    Kxt = cross_covariance(p, x, t)
+    L = cholesky(Sigma, lower=True)
+    Sinv_Kxt = cho_solve((L, True), Kxt)
+    mean = mean_t + Sinv_Kxt.T @ (y - mean_x)
+    cov = Ktt - Kxt.T @ Sinv_Kxt
+    cov[np.diag_indices_from(cov)] += p.jitter
+    return mean, cov
+
+
+def generate_test_times_pred(t: int = 100, num_genes: int = 5) -> np.ndarray:
+    """utils.py:290-314 / :81-99: gene indices 1..G (one past the end; jnp clamps), flag 1."""
+    times = np.tile(np.linspace(0, 13, t), num_genes)
+    genes = np.repeat(np.arange(1, num_genes + 1), t).astype(np.float64)
+    return np.stack((times, genes, np.ones(times.shape[0])), axis=1)
 
 
 def generate_test_times(t: int = 100) -> np.ndarray:

@@ -211,3 +211,38 @@ def test_config3_full_size_properties(cuda):
     assert relerr((Lt @ (Lt.T @ probe)).cpu().numpy(), Kp.cpu().numpy()) < 1e-11
     Si = torch.tril(Sinv) + torch.tril(Sinv, -1).T
     assert relerr((Si @ Kp).cpu().numpy(), probe.cpu().numpy()) < 1e-9
+
+
+@pytest.mark.parametrize("G,T,R,Ts", [(5, 7, 1, 100), (5, 7, 3, 100), (6, 50, 1, 30)])
+def test_multi_gene_predict(cuda, G, T, R, Ts):
+    """ExactLFM.multi_gene_predict (model.py:465-514) incl. the off-by-one gene
+    indices of generate_test_times_pred (clamped like jnp, Q6) and the third noise model (Q2)."""
+    from dis_project_b200 import ops
+    x, y, var, _ = o.synthetic_problem(G, T, R, seed=21)
+    rng = np.random.default_rng(22)
+    p = o.Params(d=rng.uniform(0.2, 1.0, G), s=rng.uniform(0.5, 1.5, G), b=rng.uniform(0.01, 0.1, G),
+                 l=float(rng.uniform(0.8, 3.2)), sigma=float(rng.uniform(0.6, 1.4)), jitter=1e-4)
+    t = o.generate_test_times_pred(Ts, G)
+    m_ref, c_ref = o.multi_gene_predict(p, t, x, y, var)
+    m, c, v, info = ops.gene_posterior(x, y, var, p.pack(), p.jitter, t, G)
+    assert int(info.item()) == 0
+    assert relerr(m.cpu().numpy(), m_ref) < RTOL
+    assert relerr(c.cpu().numpy(), c_ref) < RTOL
+    assert relerr(v.cpu().numpy(), np.diag(c_ref)) < RTOL
+    m2, c2, v2, _ = ops.gene_posterior(x, y, var, p.pack(), p.jitter, t, G, full_cov=False)
+    assert c2 is None and np.array_equal(v2.cpu().numpy(), v.cpu().numpy())
+
+
+def test_gene_expression_predictor(cuda):
+    from dis_project_b200.dataset import JaxP53Data, dataset_3d
+    from dis_project_b200.model import ExactLFM
+    from dis_project_b200.utils import GeneExpressionPredictor
+    data = JaxP53Data.synthetic(replicate=0)
+    model = ExactLFM(jitter=1e-4, data=data)
+    times, means, stds = GeneExpressionPredictor(model, data, t=40).predict()
+    x, y, var = dataset_3d(data)
+    m_ref, c_ref = o.multi_gene_predict(o.Params.reference_init(5), o.generate_test_times_pred(40, 5), x, y, var)
+    assert times.shape == (200, 3) and len(means) == 5 and means[0].shape == (40,)
+    assert relerr(means[0], m_ref[:40]) < RTOL
+    assert relerr(means[2], m_ref[120:160]) < RTOL  # blocks 3 and 4 swapped, as the reference does (utils.py:135-140)
+    assert relerr(stds[4], np.sqrt(np.diag(c_ref))[160:]) < RTOL
