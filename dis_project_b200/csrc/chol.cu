@@ -19,7 +19,7 @@
 #define S_LD 132                    // == 4 (mod 16): conflict-free m8n8k4 fragment reads
 #define WD_LD 36                    // == 4 (mod 16)
 #define LEAF_THREADS 256
-#define LEAF_SMEM ((NB * S_LD + 4 * LB * WD_LD + LB * 33) * 8)
+#define LEAF_SMEM ((NB * S_LD + 4 * LB * WD_LD + LB * 32) * 8)
 
 __device__ __forceinline__ void leaf_dmma(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -70,177 +70,310 @@ __device__ __forceinline__ void warp_store32(const double (&acc)[4][4][2], doubl
     }
 }
 
-// Diagonal 32 x 32 sub-block: warp 0 factorises it, warp 1 inverts it one pivot behind.
-// Single-warp code on an otherwise idle SM sub-partition runs at several cycles per instruction, so the
-// two rank-1 update streams (row i of L on lane i of warp 0; column c of Y = L^-1 on lane c of warp 1)
-// are put on different schedulers and coupled only by a progress counter in shared memory: after
-// pivot k, warp 0 publishes column k of L (in the [32][33] scratch T, bank-conflict free for column
-// reads) and 1/L_kk; warp 1 then computes W[k][c] = Y[k][c] / L_kk and Y[i][c] -= L[i][k] W[k][c].
-#define DP_LD 33
-__device__ __forceinline__ int warp_potrf32(double* __restrict__ D, int ldd, double* __restrict__ T,
-                                            double* __restrict__ rdiag, volatile int* prog, int base, int lane) {
+// Diagonal 32 x 32 sub-block: ONE warp factorises it and inverts it in the same instruction stream.
+// Lane i keeps row i of the block and column i of Y = L^-1 in REGISTERS; the pivot loop is fully
+// unrolled, so every register index is a compile-time constant.  Per pivot k the dependent chain is
+// one shuffle broadcast of a_kk, a branch-free rsqrt, the column scale, one shared-memory exchange of
+// column k (T[k][i] = L[i][k], zeros above the diagonal, read back as 16-byte broadcasts) and the
+// update of a[k+1]; the remaining rank-1 updates of the row and the whole update of the inverse
+// column, Y[i][c] -= L[i][k] W[k][c], are independent DFMAs that ptxas schedules into the latency
+// bubbles of that chain (a second warp coupled through a shared-memory flag was 2x slower: the
+// flag needs a MEMBAR per pivot).
+#define DP_LD 32
+// 1/sqrt(x), x > 0 normal: MUFU.RSQ64H seed + one third-order step (the arithmetic of CUDA's rsqrt()
+// without its special-case branch, which would split the pivot loop into basic blocks).
+__device__ __forceinline__ double leaf_rsqrt(double x) {
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const double e = fma(-(y0 * y0), x, 1.0);
+  const double t = fma(e, 0.375, 0.5);
+  return fma(t, y0 * e, y0);
+}
+__device__ __forceinline__ int warp_potrf_trtri32(double* __restrict__ D, int ldd, double* __restrict__ T,
+                                                  double* __restrict__ Winv, int lane) {
   int fail = -1;
-#pragma unroll 8
-  for (int r = 0; r < LB; ++r) T[r * DP_LD + lane] = D[r * ldd + lane];
-  __syncwarp();
-  double* myrow = T + lane * DP_LD;
-  for (int k = 0; k < LB; ++k) {
-    const double akk = T[k * DP_LD + k];
-    if (!(akk > 0.0) && fail < 0) fail = k;
-    const double rk = rsqrt(akk);
-    double lik = 0.0;
-    if (lane >= k) {
-      lik = (lane == k) ? akk * rk : myrow[k] * rk;
-      myrow[k] = lik;
-      if (lane == k) rdiag[k] = rk;
-    }
-    __syncwarp();
-    if (lane == 0) { __threadfence_block(); *prog = base + k + 1; }
-    for (int j0 = k + 1; j0 < LB; j0 += 8) {
-      double l[8], a[8];
+  double a[LB], y[LB];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = (j0 + q < LB) ? j0 + q : LB - 1;
-        l[q] = T[j * DP_LD + k];  // L[j][k], broadcast
-        a[q] = myrow[j];
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int j = j0 + q;
-        if (j < LB && lane >= j) myrow[j] = fma(-lik, l[q], a[q]);
-      }
-    }
-    __syncwarp();
+  for (int j = 0; j < LB; ++j) {
+    a[j] = (j <= lane) ? D[lane * ldd + j] : 0.0;
+    y[j] = (j == lane) ? 1.0 : 0.0;
   }
-#pragma unroll 8
-  for (int r = 0; r < LB; ++r) D[r * ldd + lane] = (lane <= r) ? T[r * DP_LD + lane] : 0.0;
+#pragma unroll
+  for (int k = 0; k < LB; ++k) {
+    const double akk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(akk > 0.0) && fail < 0) fail = k;
+    const double rk = leaf_rsqrt(akk);
+    const double lik = (lane == k) ? akk * rk : a[k] * rk;
+    a[k] = lik;
+    T[k * DP_LD + lane] = (lane >= k) ? lik : 0.0;
+    const double wk = y[k] * rk;
+    y[k] = wk;
+    __syncwarp();
+    if (k + 1 < LB) {
+      if ((k + 1) & 1) {
+        const double l1 = T[k * DP_LD + k + 1];
+        a[k + 1] = fma(-lik, l1, a[k + 1]);
+        y[k + 1] = fma(-l1, wk, y[k + 1]);
+      }
+#pragma unroll
+      for (int j = (k + 2) & ~1; j < LB; j += 2) {
+        const double2 l2 = *reinterpret_cast<const double2*>(T + k * DP_LD + j);
+        a[j] = fma(-lik, l2.x, a[j]);
+        a[j + 1] = fma(-lik, l2.y, a[j + 1]);
+        y[j] = fma(-l2.x, wk, y[j]);
+        y[j + 1] = fma(-l2.y, wk, y[j + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LB; ++j) {
+    D[lane * ldd + j] = (j <= lane) ? a[j] : 0.0;
+    Winv[j * WD_LD + lane] = y[j];
+  }
   return fail;
 }
 
-__device__ __forceinline__ void warp_trtri32(const double* __restrict__ T, double* __restrict__ Winv,
-                                             const double* __restrict__ rdiag, volatile int* prog, int base,
-                                             int lane) {
-#pragma unroll 8
-  for (int r = 0; r < LB; ++r) Winv[r * WD_LD + lane] = (r == lane) ? 1.0 : 0.0;
-  for (int k = 0; k < LB; ++k) {
-    while (*prog < base + k + 1) {}
-    __threadfence_block();
-    const double wk = Winv[k * WD_LD + lane] * rdiag[k];
-    Winv[k * WD_LD + lane] = wk;
-    for (int i0 = k + 1; i0 < LB; i0 += 8) {
-      double l[8], y[8];
+// ---- 8-row slices (one m8 fragment row): the chain-critical panel / diagonal-update tiles are split over the
+// four schedulers of the SM, 8 rows per warp, so that they cost a quarter of a 32 x 32 x 32 warp product.
+template <int TB>
+__device__ __forceinline__ void warp_gemm8(double (&acc)[4][2], const double* __restrict__ A, int lda,
+                                           const double* __restrict__ B, int ldb, int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int i = (i0 + q < LB) ? i0 + q : LB - 1;
-        l[q] = T[i * DP_LD + k];
-        y[q] = Winv[i * WD_LD + lane];
-      }
+  for (int k4 = 0; k4 < LB; k4 += 4) {
+    const double a = A[fr * lda + k4 + fc];
+    double b[4];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int i = i0 + q;
-        if (i < LB) Winv[i * WD_LD + lane] = fma(-l[q], wk, y[q]);
-      }
+    for (int j = 0; j < 4; ++j) b[j] = TB ? B[(8 * j + fr) * ldb + k4 + fc] : B[(k4 + fc) * ldb + 8 * j + fr];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) leaf_dmma(acc[j][0], acc[j][1], a, b[j]);
+  }
+}
+__device__ __forceinline__ void warp_store8(const double (&acc)[4][2], double* C, int ldc, double alpha, double beta,
+                                            int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double* p = C + fr * ldc + 8 * j + 2 * fc;
+    if (beta != 0.0) {
+      p[0] = alpha * acc[j][0] + beta * p[0];
+      p[1] = alpha * acc[j][1] + beta * p[1];
+    } else {
+      p[0] = alpha * acc[j][0];
+      p[1] = alpha * acc[j][1];
     }
   }
 }
+__device__ __forceinline__ void warp_load32(double (&acc)[4][4][2], const double* C, int ldc, int lane) {
+  const int fr = lane >> 2, fc = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double* p = C + (8 * i + fr) * ldc + 8 * j + 2 * fc;
+      acc[i][j][0] = p[0];
+      acc[i][j][1] = p[1];
+    }
+}
+
+__device__ __forceinline__ void leaf_cp16(void* smem, const void* gmem) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+// warps 1,2,3,5,6,7 (the "side" warps) synchronise among themselves inside a window
+__device__ __forceinline__ void leaf_side_barrier() { asm volatile("bar.sync 1, 192;" ::: "memory"); }
 
 // Leaf: in-place Cholesky of one 128 x 128 diagonal block AND its inverse, one CTA of 8 warps.
-// Blocked 4 x 4 over 32 x 32 sub-blocks; all sub-block products run on DMMA from shared memory.
+// Blocked 4 x 4 over 32 x 32 sub-blocks (i, j).  The dependent chain is
+//   D(k) [warp 0: factor + invert the diagonal sub-block]  ->  P(k+1, k) = A(k+1,k) Winv_kk^T  ->
+//   U(k+1, k+1) -= L(k+1,k) L(k+1,k)^T  ->  D(k+1),
+// with P and U split into 8-row slices over warps 0-3 (one per scheduler).  Everything else -- the
+// other panel tiles, the other trailing updates, the off-diagonal blocks of the inverse
+// (W_ij = -Winv_ii sum_{k=j}^{i-1} L_ik W_kj, accumulated in the free upper block (j, i)) and the
+// stores of finished block rows -- runs on warps 1-7 underneath the next D(k) (the "window"), so the
+// chain is 4 D + 3 (P + U) slices + the last row of the inverse.
+#define SBLK(i, j) (S + ((i)*LB) * S_LD + (j)*LB)
+#define WDI(i) (Wd + (i)*LB * WD_LD)
 __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double* __restrict__ A, int64_t lda,
                                                                        double* __restrict__ W, int64_t ldw,
                                                                        int* __restrict__ info, int pivot_base,
                                                                        long long* __restrict__ stamps) {
-  extern __shared__ __align__(16) double S[];   // [NB][S_LD] then Wd[4][LB][WD_LD]
+  extern __shared__ __align__(16) double S[];   // [NB][S_LD], then Wd[4][LB][WD_LD], then T[LB][DP_LD]
   int nstamp = 0;
 #define LEAF_STAMP() do { if (stamps && threadIdx.x == 0) stamps[nstamp++] = clock64(); } while (0)
   LEAF_STAMP();
   double* Wd = S + NB * S_LD;
+  double* T = Wd + 4 * LB * WD_LD;
   __shared__ int failed;
-  __shared__ int progress;
-  __shared__ double rdiag[LB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { failed = -1; progress = 0; }
-  // load the lower triangle (coalesced 128-double rows), zero above the diagonal
-#pragma unroll 8
-  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    S[r * S_LD + c] = (c <= r) ? A[(int64_t)r * lda + c] : 0.0;
+  if (tid == 0) failed = -1;
+  // ---- load: lower-triangle sub-blocks by cp.async; block (0,0) is its own group so that D(0) starts early
+  for (int q = tid; q < LB * (LB / 2); q += LEAF_THREADS) {
+    const int r = q >> 4, c = (q & 15) * 2;
+    leaf_cp16(S + r * S_LD + c, A + (int64_t)r * lda + c);
   }
+  asm volatile("cp.async.commit_group;\n" ::);
+  for (int q = tid; q < NB * (NB / 2); q += LEAF_THREADS) {
+    const int r = q >> 6, c = (q & 63) * 2;
+    if (r >= LB && (c >> 5) <= (r >> 5)) leaf_cp16(S + r * S_LD + c, A + (int64_t)r * lda + c);
+  }
+  asm volatile("cp.async.commit_group;\n" ::);
+  asm volatile("cp.async.wait_group 1;\n" ::);
   __syncthreads();
   LEAF_STAMP();
-  for (int kb = 0; kb < 4; ++kb) {
-    double* Dkk = S + (kb * LB) * S_LD + kb * LB;
-    if (warp == 0) {
-      const int f = warp_potrf32(Dkk, S_LD, Wd + 4 * LB * WD_LD, rdiag, &progress, kb * LB, lane);
-      if (lane == 0 && f >= 0 && failed < 0) failed = kb * LB + f;
-    } else if (warp == 1) {
-      warp_trtri32(Wd + 4 * LB * WD_LD, Wd + kb * LB * WD_LD, rdiag, &progress, kb * LB, lane);
-    }
-    __syncthreads();
-    LEAF_STAMP();
-    // panel: S[ib][kb] <- S[ib][kb] * Winv_kk^T
-    if (warp >= 1 && kb + warp < 4) {
-      double* C = S + ((kb + warp) * LB) * S_LD + kb * LB;
-      double acc[4][4][2];
-      warp_zero32(acc);
-      warp_gemm32<1>(acc, C, S_LD, Wd + kb * LB * WD_LD, WD_LD, lane);
-      __syncwarp();
-      warp_store32(acc, C, S_LD, 1.0, 0.0, lane);
-    }
-    __syncthreads();
-    // trailing update: S[ib][jb] -= S[ib][kb] S[jb][kb]^T for ib >= jb > kb
-    {
-      int cnt = 0;
-      for (int ib = kb + 1; ib < 4; ++ib)
-        for (int jb = kb + 1; jb <= ib; ++jb, ++cnt)
-          if (cnt == warp) {
-            double acc[4][4][2];
-            warp_zero32(acc);
-            warp_gemm32<1>(acc, S + (ib * LB) * S_LD + kb * LB, S_LD, S + (jb * LB) * S_LD + kb * LB, S_LD, lane);
-            warp_store32(acc, S + (ib * LB) * S_LD + jb * LB, S_LD, -1.0, 1.0, lane);
-          }
-    }
-    __syncthreads();
-    LEAF_STAMP();
-  }
-  // L out (strict upper blocks are still the zeros of the load)
-#pragma unroll 8
-  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    A[(int64_t)r * lda + c] = S[r * S_LD + c];
-  }
-  LEAF_STAMP();
-  // W = L^-1 by block forward substitution; W_ij (i > j) is built in the free upper block (j, i):
-  //   W_ij = -Winv_ii * sum_{k=j}^{i-1} L_ik W_kj
-  for (int d = 1; d < 4; ++d) {
-    const int j = warp, i = warp + d;
-    if (i < 4) {
-      double* dst = S + (j * LB) * S_LD + i * LB;
-      double acc[4][4][2];
-      warp_zero32(acc);
-      for (int k = j; k < i; ++k) {
-        const double* Lik = S + (i * LB) * S_LD + k * LB;
-        if (k == j) warp_gemm32<0>(acc, Lik, S_LD, Wd + j * LB * WD_LD, WD_LD, lane);
-        else warp_gemm32<0>(acc, Lik, S_LD, S + (j * LB) * S_LD + k * LB, S_LD, lane);
+
+  // finished block row `i` of L (zeros right of the diagonal block) -> global; one warp
+  auto store_L_row = [&](int i) {
+    for (int r = 0; r < LB; ++r) {
+      const int row = i * LB + r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 64 + lane * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if ((c >> 5) <= i) v = *reinterpret_cast<const double2*>(S + row * S_LD + c);
+        *reinterpret_cast<double2*>(A + (int64_t)row * lda + c) = v;
       }
-      warp_store32(acc, dst, S_LD, 1.0, 0.0, lane);
+    }
+  };
+  // finished block row `i` of W = L^-1 -> global; one warp
+  auto store_W_row = [&](int i) {
+    for (int r = 0; r < LB; ++r) {
+      const int row = i * LB + r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 64 + lane * 2;
+        const int bj = c >> 5;
+        double2 v = make_double2(0.0, 0.0);
+        if (bj == i) v = *reinterpret_cast<const double2*>(WDI(i) + r * WD_LD + (c & 31));
+        else if (bj < i) v = *reinterpret_cast<const double2*>(S + (bj * LB + r) * S_LD + i * LB + (c & 31));
+        *reinterpret_cast<double2*>(W + (int64_t)row * ldw + c) = v;
+      }
+    }
+  };
+  auto op_P = [&](int i, int k) {  // L_ik = A_ik Winv_kk^T, in place
+    double acc[4][4][2];
+    warp_zero32(acc);
+    warp_gemm32<1>(acc, SBLK(i, k), S_LD, WDI(k), WD_LD, lane);
+    __syncwarp();
+    warp_store32(acc, SBLK(i, k), S_LD, 1.0, 0.0, lane);
+  };
+  auto op_U = [&](int i, int j, int k) {  // A_ij -= L_ik L_jk^T
+    double acc[4][4][2];
+    warp_zero32(acc);
+    warp_gemm32<1>(acc, SBLK(i, k), S_LD, SBLK(j, k), S_LD, lane);
+    warp_store32(acc, SBLK(i, j), S_LD, -1.0, 1.0, lane);
+  };
+  // T_ij (+)= sum_{k=k0}^{k1} L_ik W_kj into the upper block (j, i); W_jj lives in Wd, W_kj (k > j) in block (j, k)
+  auto op_T = [&](int i, int j, int k0, int k1, bool accumulate) {
+    double acc[4][4][2];
+    if (accumulate) warp_load32(acc, SBLK(j, i), S_LD, lane);
+    else warp_zero32(acc);
+    for (int k = k0; k <= k1; ++k) {
+      if (k == j) warp_gemm32<0>(acc, SBLK(i, k), S_LD, WDI(j), WD_LD, lane);
+      else warp_gemm32<0>(acc, SBLK(i, k), S_LD, SBLK(j, k), S_LD, lane);
+    }
+    __syncwarp();
+    warp_store32(acc, SBLK(j, i), S_LD, 1.0, 0.0, lane);
+  };
+  auto op_F = [&](int i, int j) {  // W_ij = -Winv_ii T_ij, in place in block (j, i)
+    double acc[4][4][2];
+    warp_zero32(acc);
+    warp_gemm32<0>(acc, WDI(i), WD_LD, SBLK(j, i), S_LD, lane);
+    __syncwarp();
+    warp_store32(acc, SBLK(j, i), S_LD, -1.0, 0.0, lane);
+  };
+
+#pragma unroll 1
+  for (int kb = 0; kb < 4; ++kb) {
+    // ---- window kb: warp 0 runs D(kb); the other warps run the deferred work of step kb-1 ------------------
+    if (warp == 0) {
+      const int f = warp_potrf_trtri32(SBLK(kb, kb), S_LD, T, WDI(kb), lane);
+      if (lane == 0 && f >= 0 && failed < 0) failed = kb * LB + f;
+      if (kb == 0) asm volatile("cp.async.wait_group 0;\n" ::);
+    } else if (warp == 4) {
+      if (kb == 0) asm volatile("cp.async.wait_group 0;\n" ::);
+      if (kb >= 1) { store_L_row(kb - 1); }
+      if (kb == 1) store_W_row(0);
+      if (kb == 3) store_W_row(1);   // W row 1 was finished in window 2
+    } else {
+      if (kb == 0) {
+        asm volatile("cp.async.wait_group 0;\n" ::);
+      } else if (kb == 1) {
+        // P(2,0), P(3,0), T(1,0) first; then the five remaining updates of step 0
+        if (warp == 1) op_P(2, 0);
+        else if (warp == 2) op_P(3, 0);
+        else if (warp == 3) op_T(1, 0, 0, 0, false);
+        leaf_side_barrier();
+        if (warp == 1) op_U(2, 1, 0);
+        else if (warp == 2) op_U(3, 1, 0);
+        else if (warp == 3) op_U(2, 2, 0);
+        else if (warp == 5) op_U(3, 2, 0);
+        else if (warp == 6) op_U(3, 3, 0);
+        else if (warp == 7) op_T(2, 0, 0, 0, false);   // L20 W00 (P(2,0) is done)
+      } else if (kb == 2) {
+        if (warp == 1) op_P(3, 1);
+        else if (warp == 2) op_F(1, 0);
+        else if (warp == 3) op_T(2, 1, 1, 1, false);
+        else if (warp == 5) op_T(3, 0, 0, 0, false);   // L30 W00
+        leaf_side_barrier();
+        if (warp == 1) op_U(3, 2, 1);
+        else if (warp == 2) op_U(3, 3, 1);
+        else if (warp == 3) op_T(2, 0, 1, 1, true);    // + L21 W10
+        else if (warp == 5) op_T(3, 1, 1, 1, false);   // L31 W11
+        else if (warp == 6) op_T(3, 0, 1, 1, true);    // + L31 W10
+      } else {
+        if (warp == 1) op_F(2, 1);
+        else if (warp == 2) op_F(2, 0);
+        else if (warp == 3) op_T(3, 2, 2, 2, false);   // L32 W22
+        leaf_side_barrier();
+        if (warp == 1) op_T(3, 1, 2, 2, true);         // + L32 W21
+        else if (warp == 2) op_T(3, 0, 2, 2, true);    // + L32 W20
+        else if (warp == 5) store_W_row(2);
+      }
+    }
+    __syncthreads();
+    LEAF_STAMP();
+    if (kb == 3) break;
+    // ---- chain-critical slices: P(kb+1, kb) then U(kb+1, kb+1), 8 rows per warp on warps 0-3 -------------
+    if (warp < 4) {
+      double* C = SBLK(kb + 1, kb) + (8 * warp) * S_LD;
+      double acc[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+      warp_gemm8<1>(acc, C, S_LD, WDI(kb), WD_LD, lane);
       __syncwarp();
-      warp_zero32(acc);
-      warp_gemm32<0>(acc, Wd + i * LB * WD_LD, WD_LD, dst, S_LD, lane);
-      __syncwarp();
-      warp_store32(acc, dst, S_LD, -1.0, 0.0, lane);
+      warp_store8(acc, C, S_LD, 1.0, 0.0, lane);
+    }
+    __syncthreads();
+    if (warp < 4) {
+      double acc[4][2];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+      warp_gemm8<1>(acc, SBLK(kb + 1, kb) + (8 * warp) * S_LD, S_LD, SBLK(kb + 1, kb), S_LD, lane);
+      warp_store8(acc, SBLK(kb + 1, kb + 1) + (8 * warp) * S_LD, S_LD, -1.0, 1.0, lane);
     }
     __syncthreads();
     LEAF_STAMP();
   }
-#pragma unroll 8
-  for (int idx = tid; idx < NB * NB; idx += LEAF_THREADS) {
-    const int r = idx >> 7, c = idx & 127;
-    const int bi = r >> 5, bj = c >> 5;
-    double v = 0.0;
-    if (bi == bj) v = Wd[bi * LB * WD_LD + (r & 31) * WD_LD + (c & 31)];
-    else if (bi > bj) v = S[(bj * LB + (r & 31)) * S_LD + bi * LB + (c & 31)];
-    W[(int64_t)r * ldw + c] = v;
+  // ---- tail: last block row of the inverse, W_3j = -Winv_33 T_3j, then the last block rows go out ----------
+  if (warp >= 1 && warp <= 3) op_F(3, warp - 1);
+  else if (warp == 4) store_L_row(3);
+  __syncthreads();
+  LEAF_STAMP();
+  {
+    // W row 3: 32 rows x 128 columns over all 8 warps (4 rows per warp)
+    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
+      const int row = 3 * LB + r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 64 + lane * 2;
+        const int bj = c >> 5;
+        double2 v;
+        if (bj == 3) v = *reinterpret_cast<const double2*>(WDI(3) + r * WD_LD + (c & 31));
+        else v = *reinterpret_cast<const double2*>(S + (bj * LB + r) * S_LD + 3 * LB + (c & 31));
+        *reinterpret_cast<double2*>(W + (int64_t)row * ldw + c) = v;
+      }
+    }
   }
   LEAF_STAMP();
   if (tid == 0 && failed >= 0) atomicCAS(info, 0, pivot_base + failed + 1);

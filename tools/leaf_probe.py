@@ -11,7 +11,7 @@ for it in range(3):
     st.zero_()
     l.lfm_debug_leaf_profile(torch.cuda.current_stream().cuda_stream, A.data_ptr(), W.data_ptr(), info.data_ptr(), st.data_ptr())
     torch.cuda.synchronize()
-    s=st.cpu().numpy()[:16]
-    print("cycles:", np.diff(s)[:14], "total", s[14]-s[0], "diag phases [dot, shfl, rsqrt, store+sync, inverse]:", st.cpu().numpy()[16:21])
-names=["load","diag0","trail0","diag1","trail1","diag2","trail2","diag3","trail3","(stamp)","storeL?","inv1","inv2","inv3","storeW"]
+    s=st.cpu().numpy()[:11]
+    print("cycles:", np.diff(s), "total", s[10]-s[0])
+names=["load(0,0)","win0(D0)","PU0","win1(D1)","PU1","win2(D2)","PU2","win3(D3)","tailF","storeW3"]
 print(names)
