@@ -68,6 +68,16 @@ def reduce_best(local: np.ndarray, dist=None):
     return np.array([best, float(t2.item())])
 
 
+def reduce_best_gathered(allp: np.ndarray) -> np.ndarray:
+    """Rows [loss, id, ...] gathered from every rank -> [best_loss, id_of_best]: MIN on the loss, then the
+    smallest id among the rows that hold it (the same rule as `reduce_best`); NaN / inf never win."""
+    loss = np.where(np.isfinite(allp[:, 0]), allp[:, 0], np.inf)
+    best = float(loss.min()) if loss.size else float("inf")
+    if not np.isfinite(best):
+        return np.array([np.inf, -1.0])
+    return np.array([best, float(allp[loss == best, 1].min())])
+
+
 @dataclass
 class MultiStartResult:
     theta: np.ndarray        # (B_local, P) constrained results of this rank's shard
@@ -105,6 +115,8 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     Xd = ops._rows3(X, "x")
     yd = ops._dev(y).reshape(-1)
     st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters) if hi > lo else None
+    if st is not None and not isinstance(X, torch.Tensor):
+        st.unique_hint = ops.unique_rows(X)  # from the host copy: no device->host round trip
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
     ids = torch.arange(lo, hi, dtype=torch.float64, device=Xd.device)
@@ -131,23 +143,36 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
                 # MIN over the loss; the id is resolved after the loop (one more tiny all-reduce)
                 dist.all_reduce(trace[c, 0:1], op=dist.ReduceOp.MIN)
     main.wait_stream(side)
-    torch.cuda.synchronize()
-    if st is not None:
-        theta, hist, info = st.theta.cpu().numpy(), st.hist.cpu().numpy(), st.info.cpu().numpy()
-        local = pack_best(hist[:, -1] if num_iters > 0 else np.full(hi - lo, np.inf), np.arange(lo, hi))
+    # ---- global winner: ONE all-gather of [loss, id, theta(P)] per rank, ONE device->host copy --------------
+    packed = torch.full((P + 2,), float("inf"), dtype=torch.float64, device=Xd.device)
+    packed[1] = -1.0
+    if st is not None and num_iters > 0:
+        col = st.hist[:, num_iters - 1]
+        col = torch.where(torch.isfinite(col), col, torch.full_like(col, float("inf")))
+        k = torch.argmin(col)
+        packed[0] = col[k]
+        packed[1] = ids[k]
+        packed[2:] = st.theta[k]
+    if distributed and world > 1:
+        if dist.get_backend() == "nccl":
+            allp = torch.empty((world, P + 2), dtype=torch.float64, device=Xd.device)
+            dist.all_gather_into_tensor(allp, packed)
+            allp = allp.cpu().numpy()
+        else:  # gloo (CPU tests): gather on the host
+            buf = [torch.empty(P + 2, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(buf, packed.cpu())
+            allp = torch.stack(buf).numpy()
     else:
-        theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
-        local = np.array([np.inf, -1.0])
-    best = reduce_best(local, dist if distributed else None)
+        allp = packed.cpu().numpy()[None, :]
+    best = reduce_best_gathered(allp)
     best_id = int(best[1]) if np.isfinite(best[0]) else -1
     best_theta = None
     if best_id >= 0:
-        owner = next(r for r in range(world) if shard_bounds(B, r, world)[0] <= best_id < shard_bounds(B, r, world)[1])
-        bt = torch.zeros(P, dtype=torch.float64, device=Xd.device)
-        if owner == rank:
-            bt.copy_(torch.as_tensor(theta[best_id - lo]))
-        if distributed and world > 1:
-            dist.broadcast(bt, src=owner)
-        best_theta = bt.cpu().numpy()
+        owner = int(np.flatnonzero((allp[:, 0] == best[0]) & (allp[:, 1] == best[1]))[0])
+        best_theta = allp[owner, 2:].copy()
+    if st is not None:
+        theta, hist, info = st.theta.cpu().numpy(), st.hist.cpu().numpy(), st.info.cpu().numpy()
+    else:
+        theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
     return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
                             trace[:, 0].cpu().numpy())

@@ -417,11 +417,42 @@ static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ld
   return trsm_rec(st, m, n2, B + n1, ldb, L + n1 * ldl + n1, ldl, Wd + n1 * ldw + n1, ldw);
 }
 
-// Right-looking blocked Cholesky with 128-wide panels for small / medium n: every step is a leaf, one
-// in-place panel multiply by the inverted diagonal block and one fat trailing SYRK (3 launches per
-// block column instead of the O(log) tiny TRSM launches of the recursion).
-static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                               int64_t pivot_base) {
+// Right-looking blocked Cholesky with 128-wide panels and one step of look-ahead for small / medium n.
+// The dependent chain  leaf(k) -> L(k+1,k) = A(k+1,k) W_kk^T -> A(k+1,k+1) -= L(k+1,k) L(k+1,k)^T -> leaf(k+1)
+// runs on an internal HIGH-PRIORITY stream (its CTAs are placed before pending bulk CTAs whenever an SM
+// frees up; the two 128-row products run as 16 x 128 tiles over 8 CTAs each); the rest of the panel and of
+// the trailing update of step k stays on the caller's stream underneath leaf(k+1):
+//   bulk : wait leaf(k) | rows >= k+2 of the panel | wait L(k+1,k) | column k+1 of the update | square rest
+//   chain: wait bulk(k-1) before the panel of step k reads A(k+1, k)
+// Fork/join is by events only (no host synchronisation; legal under stream capture).
+struct LookAhead {
+  cudaStream_t chain = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
+  bool ok = false;
+  bool init() {
+    if (ok) return true;
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return false;
+    if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+    cudaEvent_t* all[] = {&fork, &join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1], &bulk_done[0],
+                          &bulk_done[1]};
+    for (cudaEvent_t* e : all)
+      if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
+    ok = true;
+    return true;
+  }
+};
+static thread_local LookAhead g_la_dev[16];  // per host thread and device
+
+static int lookahead_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LFM_LOOKAHEAD"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+static int potrf_right_looking_serial(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw,
+                                      int* info, int64_t pivot_base) {
   for (int64_t k = 0; k < n; k += NB) {
     double* Akk = A + k * lda + k;
     double* Wkk = W + k * ldw + k;
@@ -432,6 +463,58 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     LFM_TRY(lfm_dgemm(st, mk(0, 1, m, NB, NB, P, lda, Wkk, ldw, P, lda, 1.0, 0.0, 0, LFM_K_FULL)));
     LFM_TRY(lfm_dgemm(st, mk(0, 1, m, m, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 1, LFM_K_FULL)));
   }
+  return LFM_OK;
+}
+
+static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
+                               int64_t pivot_base) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
+  if (!lookahead_mode() || n < 4 * NB || dev < 0 || !g_la_dev[dev].init())
+    return potrf_right_looking_serial(st, n, A, lda, W, ldw, info, pivot_base);
+  LookAhead& la = g_la_dev[dev];
+  cudaStream_t ch = la.chain;
+  LFM_CUDA_OK(cudaEventRecord(la.fork, st));
+  LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.fork, 0));
+  int step = 0;
+  bool bulk_used = false;
+  for (int64_t k = 0; k < n; k += NB, ++step) {
+    const int e = step & 1;
+    double* Akk = A + k * lda + k;
+    double* Wkk = W + k * ldw + k;
+    LFM_TRY(leaf(ch, Akk, lda, Wkk, ldw, info, pivot_base + k));
+    const int64_t m = n - k - NB;
+    if (m <= 0) break;
+    double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
+    LFM_CUDA_OK(cudaEventRecord(la.leaf_done[e], ch));
+    // ---- chain: first 128 rows of the panel, then the next diagonal block
+    if (bulk_used) LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.bulk_done[e ^ 1], 0));
+    {
+      LfmGemm g = mk(0, 1, NB, NB, NB, P, lda, Wkk, ldw, P, lda, 1.0, 0.0, 0, LFM_K_FULL);
+      g.tile = 1;
+      LFM_TRY(lfm_dgemm(ch, g));
+      LfmGemm u = mk(0, 1, NB, NB, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 0, LFM_K_FULL);
+      u.tile = 1;
+      LFM_TRY(lfm_dgemm(ch, u));
+    }
+    if (m <= NB) continue;
+    LFM_CUDA_OK(cudaEventRecord(la.p1_done[e], ch));
+    // ---- bulk (caller's stream)
+    double* P2 = P + NB * lda;  // rows >= k+2 of the panel, (m - 128) x 128
+    const int64_t m2 = m - NB;
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.leaf_done[e], 0));
+    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.p1_done[e], 0));
+    // column k+1 of the trailing matrix: A(k+2:, k+1) -= L(k+2:, k) L(k+1, k)^T
+    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, NB, NB, P2, lda, P, lda, P2 + NB, lda, -1.0, 1.0, 0, LFM_K_FULL)));
+    // square rest: A(k+2:, k+2:) -= L(k+2:, k) L(k+2:, k)^T, lower tiles
+    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, m2, NB, P2, lda, P2, lda, P2 + 2 * NB, lda, -1.0, 1.0, 1, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], st));
+    bulk_used = true;
+  }
+  // join: everything after the factorisation is ordered behind the chain
+  LFM_CUDA_OK(cudaEventRecord(la.join, ch));
+  LFM_CUDA_OK(cudaStreamWaitEvent(st, la.join, 0));
   return LFM_OK;
 }
 

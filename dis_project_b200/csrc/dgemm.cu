@@ -35,8 +35,9 @@ template <int TRANS, int ROWS, int NT>
 __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ g, int64_t ld, int64_t row0,
                                           int64_t k0, int tid) {
 #pragma unroll
-  for (int i = 0; i < ROWS * 8 / NT; ++i) {
+  for (int i = 0; i < (ROWS * 8 + NT - 1) / NT; ++i) {
     const int id = tid + NT * i;
+    if (ROWS * 8 % NT != 0 && id >= ROWS * 8) break;
     if (TRANS == 0) {
       const int r = id >> 3, kc = id & 7;
       cp_async16(s + r * LDK + kc * 2, g + (row0 + r) * ld + k0 + kc * 2);
@@ -50,6 +51,7 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 // CTA tile (8 WM GM) x (8 WN 4): GM x 4 warps, each warp (8 WM) x (8 WN).
 //   <8,4,2> 128 x 128, 8 warps     <4,4,4> 128 x 128, 16 warps (4 per scheduler: better DMMA/LDS overlap)
 //   <4,4,2> 64 x 128 (in-place panel)       <4,2,2> 64 x 64 (small problems, 2 CTAs / SM)
+//   <1,4,2> 16 x 128 (one 128-row panel spread over 8 CTAs: the look-ahead chain of the factorisation)
 template <int TA, int TBN, int WM, int WN, int GM>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: K x N
 __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
   constexpr int BM = 8 * WM * GM, BN = 32 * WN, NT = 128 * GM;
@@ -179,9 +181,12 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
 struct GemmProf {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<char> is_chain;    // per pair: launched with the 16 x 128 latency tile (look-ahead chain)
   size_t used = 0;
-  double flops = 0.0;            // flops the launched tiles execute (tile-granular k-ranges)
-  long long launches = 0;
+  double flops = 0.0;            // flops the launched tiles execute (tile-granular k-ranges), bulk launches
+  double chain_flops = 0.0;
+  long long launches = 0, chain_launches = 0;
+  double chain_ms = 0.0;
 };
 static GemmProf g_prof;
 
@@ -208,21 +213,31 @@ static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
 
 extern "C" int lfm_debug_profile_begin(void) {
   g_prof.on = true; g_prof.used = 0; g_prof.flops = 0.0; g_prof.launches = 0;
+  g_prof.chain_flops = 0.0; g_prof.chain_launches = 0; g_prof.chain_ms = 0.0; g_prof.is_chain.clear();
   return LFM_OK;
 }
-// Synchronises the device; returns summed GEMM kernel time (ms), executed flops and launch count.
+// Synchronises the device; returns summed kernel time (ms), executed flops and launch count of the BULK
+// launches of lfm_dgemm_kernel.  The 16 x 128-tile launches of the look-ahead chain (a different template
+// instantiation, 8 CTAs, latency-bound by design) are accounted separately: lfm_debug_profile_chain.
 extern "C" int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches) {
   g_prof.on = false;
   LFM_CUDA_OK(cudaDeviceSynchronize());
-  double ms = 0.0;
+  double ms = 0.0, cms = 0.0;
   for (size_t i = 0; i + 1 < g_prof.used; i += 2) {
     float t = 0.f;
     LFM_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]));
-    ms += t;
+    if (g_prof.is_chain[i / 2]) cms += t; else ms += t;
   }
+  g_prof.chain_ms = cms;
   if (total_ms) *total_ms = ms;
   if (exec_flops) *exec_flops = g_prof.flops;
   if (launches) *launches = g_prof.launches;
+  return LFM_OK;
+}
+extern "C" int lfm_debug_profile_chain(double* total_ms, double* exec_flops, long long* launches) {
+  if (total_ms) *total_ms = g_prof.chain_ms;
+  if (exec_flops) *exec_flops = g_prof.chain_flops;
+  if (launches) *launches = g_prof.chain_launches;
   return LFM_OK;
 }
 static cudaEvent_t prof_event() {
@@ -250,8 +265,11 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   if (g_prof.on) {
     cudaEventRecord(prof_event(), st);
-    g_prof.flops += gemm_exec_flops(g, BM, BN) * (g.batch > 1 ? g.batch : 1);
-    g_prof.launches += 1;
+    const double f = gemm_exec_flops(g, BM, BN) * (g.batch > 1 ? g.batch : 1);
+    const bool chain = BM == 16;
+    g_prof.is_chain.push_back(chain ? 1 : 0);
+    if (chain) { g_prof.chain_flops += f; g_prof.chain_launches += 1; }
+    else { g_prof.flops += f; g_prof.launches += 1; }
   }
   const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
   lfm_dgemm_kernel<TA, TBN, WM, WN, GM><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
@@ -284,10 +302,19 @@ int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
   if (nb > 65535) return LFM_ERR_UNSUPPORTED;
   const int64_t t128 = nb * (g.lower_only ? (g.M / 128) * (g.M / 128 + 1) / 2 : (g.M / 128) * (g.N / 128));
   const bool inplace = (const double*)g.C == g.A;
+  if (g.tile == 1) {
+    if (g.N % 128 || g.lower_only) return LFM_ERR_INVALID;
+    return dispatch<1, 4, 2>(st, g);
+  }
   if (inplace) {
     if (g.N != 128) return LFM_ERR_INVALID;
     return (t128 >= 148) ? dispatch<8, 4, 2>(st, g) : dispatch<4, 4, 2>(st, g);
   }
+  static int force = -1;
+  if (force < 0) { const char* e = getenv("LFM_GEMM_FORCE"); force = e ? atoi(e) : 0; }
+  if (force == 1) return dispatch<4, 4, 4>(st, g);
+  if (force == 2) return dispatch<8, 4, 2>(st, g);
+  if (force == 3) return dispatch<4, 2, 2>(st, g);
   if (t128 >= 3 * 148) return big_variant() ? dispatch<4, 4, 4>(st, g) : dispatch<8, 4, 2>(st, g);
   return dispatch<4, 2, 2>(st, g);
 }

@@ -70,6 +70,7 @@ struct LfmGemm {
   int kmode;
   int batch;           // > 1: blockIdx.y-th problem uses A + y*strideA, B + y*strideB, C + y*strideC
   int64_t strideA, strideB, strideC;
+  int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain)
 };
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
 

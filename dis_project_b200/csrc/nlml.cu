@@ -359,6 +359,15 @@ extern "C" int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int
   g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
   return lfm_dgemm((cudaStream_t)stream, g);
 }
+// C(lower tiles, m x m, ldc) -= P P^T with P m x K (ldp): the trailing update of the blocked Cholesky
+extern "C" int lfm_debug_syrk(lfm_stream_t stream, int64_t m, int64_t K, const double* P, int64_t ldp, double* Cm,
+                              int64_t ldc) {
+  LfmGemm g;
+  g.transA = 0; g.transB = 1; g.M = m; g.N = m; g.K = K; g.A = P; g.lda = ldp; g.B = P; g.ldb = ldp;
+  g.C = Cm; g.ldc = ldc; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1; g.kmode = LFM_K_FULL;
+  g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
+  return lfm_dgemm((cudaStream_t)stream, g);
+}
 extern "C" int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv,
                                      int* info) {
   if (n <= 0 || n % LFM_NB || !A || !W || !info) return LFM_ERR_INVALID;

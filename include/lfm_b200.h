@@ -174,6 +174,8 @@ int lfm_debug_dgemm_nt(lfm_stream_t stream, int64_t M, int64_t N, int64_t K, con
  * call A holds L (lower), and if Sinv != NULL it receives Sigma^-1 (lower triangle valid).
  * W is an n x n scratch matrix. */
 int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv, int* info);
+/* C (lower tiles, m x m) -= P P^T, P m x K: the trailing update of the blocked Cholesky (roofline helper). */
+int lfm_debug_syrk(lfm_stream_t stream, int64_t m, int64_t K, const double* P, int64_t ldp, double* C, int64_t ldc);
 
 /* One 128 x 128 leaf factorisation with clock64() stamps at its phase boundaries (16 values). */
 int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info, long long* stamps);
@@ -184,6 +186,8 @@ unsigned long long lfm_debug_launch_count(void);
  * number of launches. */
 int lfm_debug_profile_begin(void);
 int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches);
+/* the 16 x 128-tile launches of the factorisation's look-ahead chain, accounted separately (call after _end) */
+int lfm_debug_profile_chain(double* total_ms, double* exec_flops, long long* launches);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,37 @@ def test_config3_full_size_properties(cuda):
     assert relerr((Si @ Kp).cpu().numpy(), probe.cpu().numpy()) < 1e-9
 
 
+def test_config5_full_size_posterior_properties(cuda):
+    """BASELINE config 5 (latent posterior at 102 400 test times from the N=32768 LFM): size-independent
+    properties -- the streamed chunks are independent of each other (a random subset evaluated in its own
+    call reproduces the same numbers), 0 < var <= prior variance 1 + 2 jitter, and at test times far
+    outside the data the posterior returns to the prior."""
+    from dis_project_b200 import ops
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs ~40 GB of HBM")
+    G, T, TS = 256, 128, 102400
+    x = o.make_inputs(G, T)
+    rng = np.random.default_rng(5)
+    y = rng.standard_normal(G * T)
+    var = rng.uniform(0.01, 0.1, G * T)
+    th = o.Params.reference_init(G).pack()
+    th[:G] = rng.uniform(0.3, 0.9, G)
+    ts = np.stack((np.linspace(0, 13, TS), -np.ones(TS), np.zeros(TS)), axis=1)
+    ts[-1, 0] = 60.0                                     # far from every observation
+    m, v, info = ops.latent_posterior(x, y, var, th, 1e-4, ts, G)
+    m, v = m.cpu().numpy(), v.cpu().numpy()
+    assert int(info.item()) == 0 and np.all(np.isfinite(m)) and np.all(np.isfinite(v))
+    assert np.all(v > 0) and np.all(v <= 1.0 + 2e-4 + 1e-12)
+    assert abs(m[-1]) < 1e-12 and abs(v[-1] - (1.0 + 2e-4)) < 1e-12
+    sub = np.sort(rng.choice(TS, 300, replace=False))
+    m2, v2, _ = ops.latent_posterior(x, y, var, th, 1e-4, ts[sub], G)
+    assert relerr(m2.cpu().numpy(), m[sub]) < 1e-12
+    assert relerr(v2.cpu().numpy(), v[sub]) < 1e-12
+    ops.release_workspaces()
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("G,T,R,Ts", [(5, 7, 1, 100), (5, 7, 3, 100), (6, 50, 1, 30)])
 def test_multi_gene_predict(cuda, G, T, R, Ts):
     """ExactLFM.multi_gene_predict (model.py:465-514) incl. the off-by-one gene

@@ -160,6 +160,10 @@ def test_restart_generation_and_sharding():
         assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
     assert np.array_equal(pack_best(np.array([3.0, np.nan, 1.5]), np.array([7, 8, 9])), [1.5, 9.0])
     assert pack_best(np.array([]), np.array([]))[1] == -1
+    from dis_project_b200.batched import reduce_best_gathered
+    rows = np.array([[2.0, 5.0, 0.0], [1.5, 9.0, 0.0], [np.nan, 1.0, 0.0], [1.5, 3.0, 0.0]])
+    assert np.array_equal(reduce_best_gathered(rows), [1.5, 3.0])
+    assert reduce_best_gathered(np.array([[np.inf, -1.0]]))[1] == -1
 
 
 def _gloo_worker(rank, world, port, q):
