@@ -48,6 +48,11 @@ SIGNATURES = {
     "lfm_nlml": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad_unc": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr, _ptr]),
+    "lfm_count_distinct_times": (_i64, [_i64, _ptr]),
+    "lfm_nlml_workspace_bytes_tg": (_sz, [_i64, _int, _i64]),
+    "lfm_nlml_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_unc_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
     "lfm_latent_posterior_workspace_bytes": (_sz, [_i64, _int, _i64]),
     "lfm_latent_posterior": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _ptr, _sz,
                                     _ptr, _ptr, _ptr]),

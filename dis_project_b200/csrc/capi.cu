@@ -94,7 +94,8 @@ extern "C" int lfm_nlml_grad_host(lfm_handle* h, int64_t N, int G, const double*
   const size_t P = 3 * (size_t)G + 2;
   const size_t nin = r2(3 * (size_t)N) + r2((size_t)N) + r2(P);
   const size_t nout = r2(1 + P);
-  LFM_TRY(ensure(&h->ws, &h->ws_bytes, lfm_nlml_workspace_bytes(N, G), false));
+  const int64_t tg = lfm_count_distinct_times(N, X);  // host copy at hand: O(N log T) per call
+  LFM_TRY(ensure(&h->ws, &h->ws_bytes, lfm_nlml_workspace_bytes_tg(N, G, tg), false));
   LFM_TRY(ensure((void**)&h->dbuf, &h->dbuf_bytes, (nin + nout) * 8, false));
   LFM_TRY(ensure((void**)&h->hpin, &h->hpin_bytes, (nin + nout) * 8, true));
   double* hp = h->hpin;
@@ -106,8 +107,9 @@ extern "C" int lfm_nlml_grad_host(lfm_handle* h, int64_t N, int G, const double*
   double* dy = dX + r2(3 * (size_t)N);
   double* dth = dy + r2((size_t)N);
   double* dout = h->dbuf + nin;
-  int st = unconstrained ? lfm_nlml_grad_unc(h->stream, N, G, dX, dy, dth, jitter, h->ws, h->ws_bytes, dout, h->dinfo)
-                         : lfm_nlml_grad(h->stream, N, G, dX, dy, dth, jitter, h->ws, h->ws_bytes, dout, h->dinfo);
+  int st = unconstrained
+               ? lfm_nlml_grad_unc_tg(h->stream, N, G, dX, dy, dth, jitter, tg, h->ws, h->ws_bytes, dout, h->dinfo)
+               : lfm_nlml_grad_tg(h->stream, N, G, dX, dy, dth, jitter, tg, h->ws, h->ws_bytes, dout, h->dinfo);
   if (st != LFM_OK) return st;
   LFM_CUDA_OK(cudaMemcpyAsync(hp + nin, dout, (1 + P) * 8, cudaMemcpyDeviceToHost, h->stream));
   int hinfo = 0;

@@ -11,42 +11,51 @@
 // Tile = 64 x 64 outputs per CTA of 256 threads (32 x 8): a thread owns two adjacent columns
 // (16-byte stores, 512 B contiguous per warp row) and 8 rows; the 64 row points and 64 column
 // points of the tile, with all per-point exp/erf terms, are staged once in shared memory.
+#include <cstring>
 #include "sim_math.cuh"
 
 #define GT 64  // tile edge
 
 __device__ __forceinline__ void lfm_stage_points(LfmPoint* sp, const double* __restrict__ X, int64_t n,
                                                  int64_t base, int G, const double* __restrict__ theta,
-                                                 double l, bool grad, int lane64) {
+                                                 double l, bool grad, int lane64, const int* __restrict__ tidx = nullptr) {
   // lane64 in [0,64): one point per thread
   const int64_t i = base + lane64;
   if (i < n) {
-    sp[lane64] = lfm_make_point(X + 3 * i, G, theta, theta + G, l, grad);
+    LfmPoint p = lfm_make_point(X + 3 * i, G, theta, theta + G, l, grad);
+    if (tidx) p.ti = tidx[i];
+    sp[lane64] = p;
   } else {
     LfmPoint p;
     p.t = 0; p.d = 1; p.s = 0; p.gam = 0; p.eg2 = 1; p.erfg = 0; p.e = 1; p.q = 0; p.g3 = 0; p.g4 = 0;
-    p.gene = 0; p.flag = 1;
+    p.gene = 0; p.flag = 1; p.ti = 0;
     sp[lane64] = p;
   }
 }
 
 // mode 0: general N x M block.  mode 1: symmetric training matrix, lower tiles only, padded.
-template <int MODE>
+template <int MODE, bool TAB>
 __global__ void __launch_bounds__(256) lfm_gram_tile_kernel(int64_t N, int64_t M, const double* __restrict__ X,
                                                           const double* __restrict__ Y, int G,
                                                           const double* __restrict__ theta,
                                                           double* __restrict__ out, int64_t ld,
                                                           const double* __restrict__ diag_vec,
-                                                          double diag_const, int add_sigma2, int64_t Npad) {
+                                                          double diag_const, int add_sigma2, int64_t Npad,
+                                                          LfmGrid grid) {
   __shared__ LfmPoint rowp[GT];
   __shared__ LfmPoint colp[GT];
   const int64_t tr = blockIdx.y, tc = blockIdx.x;
   if (MODE == 1 && tc > tr) return;
+  // time-grid tables (training matrix only): valid when the distinct times fit the caller's bound.  Both
+  // instantiations are launched; the one that does not apply exits here.
+  const bool tab = MODE == 1 && grid.Tu > 0 && *grid.count <= grid.Tu;
+  if (tab != TAB) return;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const double l = theta[3 * G];
   const double inv_l = 1.0 / l;
-  if (tid < 64) lfm_stage_points(rowp, X, N, tr * GT, G, theta, l, false, tid);
-  else if (tid < 128) lfm_stage_points(colp, Y, M, tc * GT, G, theta, l, false, tid - 64);
+  const int* tix = TAB ? grid.tidx : nullptr;
+  if (tid < 64) lfm_stage_points(rowp, X, N, tr * GT, G, theta, l, false, tid, tix);
+  else if (tid < 128) lfm_stage_points(colp, Y, M, tc * GT, G, theta, l, false, tid - 64, tix);
   __syncthreads();
   double dadd = diag_const;
   if (MODE == 1 && add_sigma2) {
@@ -77,8 +86,13 @@ __global__ void __launch_bounds__(256) lfm_gram_tile_kernel(int64_t N, int64_t M
     } else {
       // padded symmetric: inside [0,N)^2 the kernel value, identity outside
       if (i < N) {
-        v0 = (j0 < N) ? lfm_kxx(pr, pc0, l, inv_l) : 0.0;
-        v1 = (j0 + 1 < N) ? lfm_kxx(pr, pc1, l, inv_l) : 0.0;
+        if (TAB) {
+          v0 = (j0 < N) ? lfm_kxx_tab(grid, pr, pc0, l, inv_l) : 0.0;
+          v1 = (j0 + 1 < N) ? lfm_kxx_tab(grid, pr, pc1, l, inv_l) : 0.0;
+        } else {
+          v0 = (j0 < N) ? lfm_kxx(pr, pc0, l, inv_l) : 0.0;
+          v1 = (j0 + 1 < N) ? lfm_kxx(pr, pc1, l, inv_l) : 0.0;
+        }
         const double dv = dadd + (diag_vec ? diag_vec[i] : 0.0);
         if (i == j0) v0 += dv;
         if (i == j0 + 1) v1 += dv;
@@ -96,7 +110,9 @@ int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X,
   if (N <= 0 || M <= 0) return LFM_OK;
   dim3 grid((unsigned)((M + GT - 1) / GT), (unsigned)((N + GT - 1) / GT));
   if (grid.y > 65535) return LFM_ERR_UNSUPPORTED;
-  lfm_gram_tile_kernel<0><<<grid, dim3(32, 8), 0, st>>>(N, M, X, Y, G, theta, out, ld, nullptr, 0.0, 0, 0);
+  LfmGrid none;
+  memset(&none, 0, sizeof(none));
+  lfm_gram_tile_kernel<0, false><<<grid, dim3(32, 8), 0, st>>>(N, M, X, Y, G, theta, out, ld, nullptr, 0.0, 0, 0, none);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
@@ -105,11 +121,19 @@ int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X,
 // Sigma (lower tiles, padded to Npad) = k_xx(X, X) + diag(diag_vec) + (diag_const [+ sigma^2]) I
 int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G,
                            const double* theta, const double* diag_vec, double diag_const, int add_sigma2,
-                           double* out, int64_t ld) {
+                           double* out, int64_t ld, const LfmGrid* tg) {
   dim3 grid((unsigned)(Npad / GT), (unsigned)(Npad / GT));
-  lfm_gram_tile_kernel<1><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
-                                                       add_sigma2, Npad);
+  LfmGrid tgv;
+  memset(&tgv, 0, sizeof(tgv));
+  if (tg) tgv = *tg;
+  lfm_gram_tile_kernel<1, false><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
+                                                              add_sigma2, Npad, tgv);
   LFM_LAUNCHED(1);
+  if (tgv.Tu > 0) {
+    lfm_gram_tile_kernel<1, true><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
+                                                               add_sigma2, Npad, tgv);
+    LFM_LAUNCHED(1);
+  }
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
@@ -124,6 +148,7 @@ int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const doubl
 // ---------------------------------------------------------------------------------------------
 #define GC_TILES 16
 
+template <bool TAB>
 __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
                                                               const double* __restrict__ theta,
                                                               const double* __restrict__ Sinv, int64_t ld,
@@ -131,7 +156,7 @@ __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const
                                                               double* __restrict__ rowpart,  // [nchunk][Npad64][2]
                                                               double* __restrict__ colpart,  // [ntile][Npad64][2]
                                                               double* __restrict__ lpart,    // [ntile][nchunk]
-                                                              int64_t N64, int nchunk) {
+                                                              int64_t N64, int nchunk, LfmGrid grid) {
   __shared__ LfmPoint rowp[GT];
   __shared__ LfmPoint colp[GT];
   __shared__ double red[8][GT][2];
@@ -145,7 +170,10 @@ __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const
   const int jt1 = min(I, jt0 + GC_TILES - 1);
   const double l = theta[3 * G];
   const double inv_l = 1.0 / l;
-  if (tid < 64) lfm_stage_points(rowp, X, N, (int64_t)I * GT, G, theta, l, true, tid);
+  const bool tab = grid.Tu > 0 && *grid.count <= grid.Tu;
+  if (tab != TAB) return;   // both instantiations are launched; the one that does not apply exits here
+  const int* tix = TAB ? grid.tidx : nullptr;
+  if (tid < 64) lfm_stage_points(rowp, X, N, (int64_t)I * GT, G, theta, l, true, tid, tix);
   double racc_d[8], racc_k[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) { racc_d[r] = 0.0; racc_k[r] = 0.0; }
@@ -153,7 +181,7 @@ __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const
   const int c0 = lane * 2;
   for (int J = jt0; J <= jt1; ++J) {
     __syncthreads();
-    if (tid >= 64 && tid < 128) lfm_stage_points(colp, X, N, (int64_t)J * GT, G, theta, l, true, tid - 64);
+    if (tid >= 64 && tid < 128) lfm_stage_points(colp, X, N, (int64_t)J * GT, G, theta, l, true, tid - 64, tix);
     __syncthreads();
     const int64_t j0 = (int64_t)J * GT + c0;
     const LfmPoint pc0 = colp[c0];
@@ -172,7 +200,8 @@ __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const
       if (j0 <= i && j0 < N) {
         const double w = (j0 == i ? 0.5 : 1.0) * (sv.x - ai * a0);
         double k, dr, dc, dl;
-        lfm_kxx_grad(pr, pc0, l, inv_l, k, dr, dc, dl);
+        if (TAB) lfm_kxx_grad_tab(grid, pr, pc0, l, inv_l, k, dr, dc, dl);
+        else lfm_kxx_grad(pr, pc0, l, inv_l, k, dr, dc, dl);
         racc_d[rr] += w * dr; racc_k[rr] += w * k;
         cd0 += w * dc; ck0 += w * k;
         lacc += w * dl;
@@ -180,7 +209,8 @@ __global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const
       if (j0 + 1 <= i && j0 + 1 < N) {
         const double w = (j0 + 1 == i ? 0.5 : 1.0) * (sv.y - ai * a1);
         double k, dr, dc, dl;
-        lfm_kxx_grad(pr, pc1, l, inv_l, k, dr, dc, dl);
+        if (TAB) lfm_kxx_grad_tab(grid, pr, pc1, l, inv_l, k, dr, dc, dl);
+        else lfm_kxx_grad(pr, pc1, l, inv_l, k, dr, dc, dl);
         racc_d[rr] += w * dr; racc_k[rr] += w * k;
         cd1 += w * dc; ck1 += w * k;
         lacc += w * dl;
@@ -300,7 +330,10 @@ size_t lfm_grad_scratch_doubles(int64_t N) {
 
 int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G, const double* theta,
                              const double* Sinv, int64_t ld, const double* alpha, double* scratch,
-                             double* grad) {
+                             double* grad, const LfmGrid* tg) {
+  LfmGrid tgv;
+  memset(&tgv, 0, sizeof(tgv));
+  if (tg) tgv = *tg;
   const int64_t ntile = (N + GT - 1) / GT;
   const int64_t N64 = ntile * GT;
   const int64_t nchunk = (ntile + GC_TILES - 1) / GC_TILES;
@@ -311,8 +344,13 @@ int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G,
   // partial buffers are only sparsely written (lower triangle): clear them first
   LFM_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)(nchunk * N64 * 2 + ntile * N64 * 2 + ntile * nchunk), st));
   dim3 grid((unsigned)nchunk, (unsigned)ntile);
-  lfm_grad_contract_kernel<<<grid, dim3(32, 8), 0, st>>>(N, X, G, theta, Sinv, ld, alpha, rowpart, colpart, lpart,
-                                                        N64, (int)nchunk);
+  lfm_grad_contract_kernel<false><<<grid, dim3(32, 8), 0, st>>>(N, X, G, theta, Sinv, ld, alpha, rowpart, colpart,
+                                                               lpart, N64, (int)nchunk, tgv);
+  if (tgv.Tu > 0) {
+    lfm_grad_contract_kernel<true><<<grid, dim3(32, 8), 0, st>>>(N, X, G, theta, Sinv, ld, alpha, rowpart, colpart,
+                                                                lpart, N64, (int)nchunk, tgv);
+    LFM_LAUNCHED(1);
+  }
   LFM_CUDA_OK(cudaGetLastError());
   lfm_grad_point_kernel<<<(unsigned)((N * 2 + 255) / 256), 256, 0, st>>>(N, N64, (int)ntile, (int)nchunk, rowpart,
                                                                         colpart, pt);

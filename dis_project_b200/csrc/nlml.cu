@@ -3,15 +3,6 @@
 // W = L^-1, log-det / quadratic-form reductions (warp-shuffle), bijector chain.
 #include "sim_math.cuh"
 
-// provided by gram.cu / chol.cu
-int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G,
-                           const double* theta, const double* diag_vec, double diag_const, int add_sigma2,
-                           double* out, int64_t ld);
-size_t lfm_grad_scratch_doubles(int64_t N);
-int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G, const double* theta,
-                             const double* Sinv, int64_t ld, const double* alpha, double* scratch,
-                             double* grad);
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -223,13 +214,14 @@ int lfm_launch_alpha(cudaStream_t st, int64_t Np, const double* W, const double*
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct NlmlWs {
-  int64_t Np;
-  double *A, *W, *z, *w, *alpha, *theta, *part, *gscratch;
+  int64_t Np, Tu;
+  double *A, *W, *z, *w, *alpha, *theta, *part, *gscratch, *grid;
   size_t total_doubles;
 };
-static NlmlWs nlml_ws_layout(int64_t N, int G, void* base) {
+static NlmlWs nlml_ws_layout(int64_t N, int G, int64_t time_grid, void* base) {
   NlmlWs s;
   s.Np = lfm_round_up(N, LFM_NB);
+  s.Tu = lfm_grid_effective(N, G, time_grid);
   double* p = reinterpret_cast<double*>(base);
   size_t off = 0;
   auto take = [&](size_t n) { double* r = p ? p + off : nullptr; off += (n + 1) & ~(size_t)1; return r; };
@@ -241,76 +233,93 @@ static NlmlWs nlml_ws_layout(int64_t N, int G, void* base) {
   s.theta = take(3 * (size_t)G + 2);
   s.part = take(lfm_alpha_part_doubles(s.Np));
   s.gscratch = take(lfm_grad_scratch_doubles(N));
+  s.grid = take(lfm_grid_ws_doubles(N, G, s.Tu));
   s.total_doubles = off;
   return s;
 }
 
-extern "C" size_t lfm_nlml_workspace_bytes(int64_t N, int G) {
+extern "C" size_t lfm_nlml_workspace_bytes_tg(int64_t N, int G, int64_t time_grid) {
   if (N <= 0 || G <= 0) return 0;
-  return nlml_ws_layout(N, G, nullptr).total_doubles * sizeof(double);
+  return nlml_ws_layout(N, G, time_grid, nullptr).total_doubles * sizeof(double);
 }
+extern "C" size_t lfm_nlml_workspace_bytes(int64_t N, int G) { return lfm_nlml_workspace_bytes_tg(N, G, 0); }
 
-static int check_common(int64_t N, int G, const void* X, const void* y, const void* theta, void* ws, size_t ws_bytes,
-                        void* out, void* info) {
+static int check_common(int64_t N, int G, const void* X, const void* y, const void* theta, int64_t time_grid, void* ws,
+                        size_t ws_bytes, void* out, void* info) {
   if (N <= 0 || G <= 0 || !X || !y || !theta || !ws || !out || !info) return LFM_ERR_INVALID;
   if (N % G) return LFM_ERR_INVALID;  // mean_function's reshape would fail (model.py:145-149)
   if ((reinterpret_cast<uintptr_t>(ws) & 15) != 0) return LFM_ERR_INVALID;
-  if (ws_bytes < lfm_nlml_workspace_bytes(N, G)) return LFM_ERR_WORKSPACE;
+  if (time_grid < 0) return LFM_ERR_INVALID;
+  if (ws_bytes < lfm_nlml_workspace_bytes_tg(N, G, time_grid)) return LFM_ERR_WORKSPACE;
   return LFM_OK;
 }
 
-// Shared front half: z, Sigma, Cholesky.  Leaves L in ws.A and the inverted diagonal blocks in ws.W.
+// Shared front half: z, time-grid tables, Sigma, Cholesky.  Leaves L in ws.A and the inverted diagonal
+// blocks in ws.W; `grid` is the table view the gradient contraction reuses.
 static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* theta,
-                       double jitter, const NlmlWs& s, int* info) {
+                       double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info) {
   LFM_TRY(lfm_launch_residual(st, N, s.Np, X, y, G, theta, s.z, nullptr));
-  LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, nullptr, jitter, 1, s.A, s.Np));
+  LFM_TRY(lfm_grid_build(st, N, G, X, theta, s.Tu, grad, s.grid, grid));
+  LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, nullptr, jitter, 1, s.A, s.Np, grid));
   return lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
 }
 
-extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
-                        const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info) {
-  LFM_TRY(check_common(N, G, X, y, theta, ws, ws_bytes, out, info));
+extern "C" int lfm_nlml_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                           const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
+                           double* out, int* info) {
+  LFM_TRY(check_common(N, G, X, y, theta, time_grid, ws, ws_bytes, out, info));
   cudaStream_t st = (cudaStream_t)stream;
-  const NlmlWs s = nlml_ws_layout(N, G, ws);
-  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, info));
+  const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
+  LfmGrid grid;
+  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, false, &grid, info));
   LFM_TRY(trsv_rec(st, s.Np, s.A, s.Np, s.W, s.Np, s.z));  // z <- L^-1 z
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.z, info, out);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
+extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                        const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info) {
+  return lfm_nlml_tg(stream, N, G, X, y, theta, jitter, 0, ws, ws_bytes, out, info);
+}
 
 static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, const double* y,
                           const double* theta, double jitter, const NlmlWs& s, double* out, int* info) {
   const int P = 3 * G + 2;
-  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, info));
+  LfmGrid grid;
+  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, true, &grid, info));
   LFM_TRY(lfm_trtri(st, s.Np, s.A, s.Np, s.W, s.Np));
   LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
-  LFM_TRY(lfm_launch_grad_contract(st, N, X, G, theta, s.A, s.Np, s.alpha, s.gscratch, out + 1));
+  LFM_TRY(lfm_launch_grad_contract(st, N, X, G, theta, s.A, s.Np, s.alpha, s.gscratch, out + 1, &grid));
   lfm_poison_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, info, out + 1);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
 
+extern "C" int lfm_nlml_grad_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                                const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
+                                double* out, int* info) {
+  LFM_TRY(check_common(N, G, X, y, theta, time_grid, ws, ws_bytes, out, info));
+  const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
+  return nlml_grad_impl((cudaStream_t)stream, N, G, X, y, theta, jitter, s, out, info);
+}
 extern "C" int lfm_nlml_grad(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
                              const double* theta, double jitter, void* ws, size_t ws_bytes, double* out,
                              int* info) {
-  LFM_TRY(check_common(N, G, X, y, theta, ws, ws_bytes, out, info));
-  const NlmlWs s = nlml_ws_layout(N, G, ws);
-  return nlml_grad_impl((cudaStream_t)stream, N, G, X, y, theta, jitter, s, out, info);
+  return lfm_nlml_grad_tg(stream, N, G, X, y, theta, jitter, 0, ws, ws_bytes, out, info);
 }
 
-extern "C" int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
-                                 const double* theta_unc, double jitter, void* ws, size_t ws_bytes,
-                                 double* out, int* info) {
-  LFM_TRY(check_common(N, G, X, y, theta_unc, ws, ws_bytes, out, info));
+extern "C" int lfm_nlml_grad_unc_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                                    const double* theta_unc, double jitter, int64_t time_grid, void* ws,
+                                    size_t ws_bytes, double* out, int* info) {
+  LFM_TRY(check_common(N, G, X, y, theta_unc, time_grid, ws, ws_bytes, out, info));
   cudaStream_t st = (cudaStream_t)stream;
-  const NlmlWs s = nlml_ws_layout(N, G, ws);
+  const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
   const int P = 3 * G + 2;
   lfm_constrain_kernel<<<(P + 127) / 128, 128, 0, st>>>(1, G, theta_unc, s.theta);
   LFM_LAUNCHED(1);
@@ -320,6 +329,11 @@ extern "C" int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const do
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
+}
+extern "C" int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                                 const double* theta_unc, double jitter, void* ws, size_t ws_bytes,
+                                 double* out, int* info) {
+  return lfm_nlml_grad_unc_tg(stream, N, G, X, y, theta_unc, jitter, 0, ws, ws_bytes, out, info);
 }
 
 extern "C" int lfm_constrain(lfm_stream_t stream, int64_t B, int G, const double* theta_unc, double* theta) {

@@ -8,11 +8,6 @@
 // columns -- build the K_xf chunk, one triangular DMMA GEMM V = W K_xf, then column reductions.
 #include "sim_math.cuh"
 
-int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G,
-                           const double* theta, const double* diag_vec, double diag_const, int add_sigma2,
-                           double* out, int64_t ld);
-int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X, const double* Y, int G,
-                         const double* theta, double* out, int64_t ld);
 
 #define PC_COLS 2048
 #define PR_ROWS 1024

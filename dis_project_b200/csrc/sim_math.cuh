@@ -20,6 +20,7 @@ struct LfmPoint {
   double g4;    // 2/sqrt(pi) exp(-gamma_j^2)                   (gradient only)
   int gene;     // resolved gene index
   int flag;     // 1 gene expression, 0 latent force
+  int ti;       // index of t among the distinct times of X (time-grid tables only; else 0)
 };
 
 // jnp integer indexing semantics for the gene column (model.py:223-224): negative wraps, then clamp.
@@ -38,6 +39,7 @@ __device__ __forceinline__ LfmPoint lfm_make_point(const double* __restrict__ ro
   p.t = row3[0];
   p.gene = lfm_resolve_gene(row3[1], G);
   p.flag = ((int)row3[2]) != 0;
+  p.ti = 0;
   p.d = d[p.gene];
   p.s = s[p.gene];
   p.gam = p.d * l * 0.5;
@@ -73,24 +75,47 @@ __device__ __forceinline__ double lfm_erfsum(double a, double b) {
 // pa is the point (u, gene a), pb the point (v, gene b).
 //   H = E0 (A1 R1 - A2 R2),  E0 = exp(gam_b^2)/(d_a+d_b), A1 = exp(-d_b (v-u)),
 //   R1 = erf((v-u)/l - gam_b) + erf(u/l + gam_b), A2 = exp(-(d_b v + d_a u)) = e_a e_b, R2 = q_b.
+// The transcendental factors that depend on (gene b, u, v) only -- A1, A1 R1, g1 -- and on (gene b, u) only
+// -- g2 -- enter through lfm_h_core, so that they can come either from a direct evaluation (lfm_h) or
+// from the distinct-time tables of a gridded data set (LfmGrid, grid.cu): G T^2 evaluations instead of N^2.
+struct LfmPairTerms {
+  double inv;    // 1 / (d_a + d_b)
+  double A1;     // exp(-d_b (v - u))
+  double A1R1;   // A1 * [erf((v-u)/l - gam_b) + erf(u/l + gam_b)]
+  double g1;     // 2/sqrt(pi) exp(-((v-u)/l - gam_b)^2)    (gradient only)
+  double g2;     // 2/sqrt(pi) exp(-(u/l + gam_b)^2)        (gradient only)
+};
 template <bool GRAD>
-__device__ __forceinline__ void lfm_h(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
-                                      double& H, double& dH_da, double& dH_db, double& dH_dl) {
+__device__ __forceinline__ LfmPairTerms lfm_pair_terms(double ta, double tb, double d_b, double gam_b, double inv_l) {
+  LfmPairTerms r;
+  const double delta = tb - ta;
+  r.A1 = exp(-d_b * delta);
+  const double x1 = delta * inv_l - gam_b;
+  const double x2 = ta * inv_l + gam_b;
+  r.A1R1 = __dmul_rn(r.A1, lfm_erfsum(x1, x2));
+  if (GRAD) {
+    r.g1 = __dmul_rn(LFM_TWO_OVER_SQRT_PI, exp(-x1 * x1));
+    r.g2 = __dmul_rn(LFM_TWO_OVER_SQRT_PI, exp(-x2 * x2));
+  } else {
+    r.g1 = 0.0; r.g2 = 0.0;
+  }
+  r.inv = 0.0;
+  return r;
+}
+template <bool GRAD>
+__device__ __forceinline__ void lfm_h_core(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
+                                           const LfmPairTerms& pt, double& H, double& dH_da, double& dH_db,
+                                           double& dH_dl) {
   const double delta = pb.t - pa.t;
-  const double inv = 1.0 / (pa.d + pb.d);
+  const double inv = pt.inv;
   const double E0 = pb.eg2 * inv;
-  const double A1 = exp(-pb.d * delta);
-  const double x1 = delta * inv_l - pb.gam;
-  const double x2 = pa.t * inv_l + pb.gam;
-  const double R1 = lfm_erfsum(x1, x2);
+  const double A1 = pt.A1;
   const double A2 = pa.e * pb.e;
-  const double R2 = pb.q;
-  const double A1R1 = A1 * R1;
-  const double A2R2 = A2 * R2;
+  const double A1R1 = pt.A1R1;
+  const double A2R2 = __dmul_rn(A2, pb.q);
   H = E0 * (A1R1 - A2R2);
   if (GRAD) {
-    const double g1 = LFM_TWO_OVER_SQRT_PI * exp(-x1 * x1);
-    const double g2 = LFM_TWO_OVER_SQRT_PI * exp(-x2 * x2);
+    const double g1 = pt.g1, g2 = pt.g2;
     const double g3 = pb.g3, g4 = pb.g4;
     const double hl = 0.5 * l;
     const double hd = 0.5 * pb.d;
@@ -101,6 +126,70 @@ __device__ __forceinline__ void lfm_h(const LfmPoint& pa, const LfmPoint& pb, do
     dH_dl = H * pb.gam * pb.d + E0 * (A1 * (g1 * (-delta * il2 - hd) + g2 * (-pa.t * il2 + hd)) -
                                       A2 * (g3 * (-pb.t * il2 - hd) + g4 * hd));
   }
+}
+template <bool GRAD>
+__device__ __forceinline__ void lfm_h(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
+                                      double& H, double& dH_da, double& dH_db, double& dH_dl) {
+  LfmPairTerms pt = lfm_pair_terms<GRAD>(pa.t, pb.t, pb.d, pb.gam, inv_l);
+  pt.inv = 1.0 / (pa.d + pb.d);
+  lfm_h_core<GRAD>(pa, pb, l, inv_l, pt, H, dH_da, dH_db, dH_dl);
+}
+
+// ---- distinct-time tables ("time grid") -------------------------------------------------------------------
+// When the rows of X share a small set of distinct times (the reference's layout: every gene observed on the
+// same time grid, dataset.py:380-391), the pair terms above depend on (gene b, time index of a, time index
+// of b) only.  grid.cu finds the distinct times on the device, tabulates the terms once per evaluation
+// (G T^2 entries) and the tile kernels read them instead of evaluating exp / erf per matrix entry.
+// Layouts: X[b][ia][ib] with ib fastest; the *t arrays are the (ia, ib)-transposed copies so that both
+// h(col, row) and h(row, col) read consecutive addresses along a tile row.
+struct LfmGrid {
+  const int* tidx;     // [N] distinct-time index of every row of X
+  const int* count;    // device scalar: number of distinct times found; tables are valid iff *count <= Tu
+  int Tu;              // leading dimension of the tables (host-side upper bound on *count); 0: no tables
+  int G;
+  const double* A1R1;  const double* A1R1t;
+  const double* A1;    const double* A1t;    // gradient only
+  const double* g1;    const double* g1t;    // gradient only
+  const double* g2;                          // [G][Tu]: term of (gene b, time index of a); gradient only
+  const double* inv;                         // [G][G] 1 / (d_a + d_b)
+};
+// h(pa, pb) from the tables; `tr` selects the transposed copies (used for h(col, row), where the column
+// index runs along ia).
+template <bool GRAD>
+__device__ __forceinline__ void lfm_h_tab(const LfmGrid& g, const LfmPoint& pa, const LfmPoint& pb, bool tr, double l,
+                                          double inv_l, double& H, double& dH_da, double& dH_db, double& dH_dl) {
+  LfmPairTerms pt;
+  const size_t base = (size_t)pb.gene * g.Tu * g.Tu;
+  const size_t off = tr ? base + (size_t)pb.ti * g.Tu + pa.ti : base + (size_t)pa.ti * g.Tu + pb.ti;
+  pt.A1R1 = (tr ? g.A1R1t : g.A1R1)[off];
+  if (GRAD) {
+    pt.A1 = (tr ? g.A1t : g.A1)[off];
+    pt.g1 = (tr ? g.g1t : g.g1)[off];
+    pt.g2 = g.g2[(size_t)pb.gene * g.Tu + pa.ti];
+  } else {
+    pt.A1 = 0.0; pt.g1 = 0.0; pt.g2 = 0.0;
+  }
+  pt.inv = g.inv[(size_t)pa.gene * g.G + pb.gene];
+  lfm_h_core<GRAD>(pa, pb, l, inv_l, pt, H, dH_da, dH_db, dH_dl);
+}
+__device__ __forceinline__ double lfm_kxx_tab(const LfmGrid& g, const LfmPoint& pi, const LfmPoint& pj, double l,
+                                              double inv_l) {
+  double H1, H2, u0, u1, u2;
+  lfm_h_tab<false>(g, pj, pi, true, l, inv_l, H1, u0, u1, u2);
+  lfm_h_tab<false>(g, pi, pj, false, l, inv_l, H2, u0, u1, u2);
+  return pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l) * (H1 + H2);
+}
+__device__ __forceinline__ void lfm_kxx_grad_tab(const LfmGrid& g, const LfmPoint& pi, const LfmPoint& pj, double l,
+                                                 double inv_l, double& k, double& dk_drow, double& dk_dcol,
+                                                 double& dk_dl) {
+  double H1, dH1_da, dH1_db, dH1_dl, H2, dH2_da, dH2_db, dH2_dl;
+  lfm_h_tab<true>(g, pj, pi, true, l, inv_l, H1, dH1_da, dH1_db, dH1_dl);
+  lfm_h_tab<true>(g, pi, pj, false, l, inv_l, H2, dH2_da, dH2_db, dH2_dl);
+  const double mult = pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l);
+  k = mult * (H1 + H2);
+  dk_drow = mult * (dH1_db + dH2_da);
+  dk_dcol = mult * (dH1_da + dH2_db);
+  dk_dl = mult * (dH1_dl + dH2_dl) + k * inv_l;
 }
 
 // k_xx between gene point pi = (t, j) and gene point pj = (t', k)  (model.py:197-235):
@@ -137,6 +226,30 @@ __device__ __forceinline__ double lfm_kxf(const LfmPoint& pg, double t_latent, d
 __device__ __forceinline__ double lfm_kff(double t, double tp, double l) {
   const double dt = t - tp;
   return exp(-(dt * dt) / (2.0 * l));
+}
+
+// ---- host launchers shared between translation units (gram.cu / grid.cu) -------------------------------------
+// Sigma (lower tiles, padded to Npad) = k_xx(X, X) + diag(diag_vec) + (diag_const [+ sigma^2]) I
+int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G, const double* theta,
+                           const double* diag_vec, double diag_const, int add_sigma2, double* out, int64_t ld,
+                           const LfmGrid* tg = nullptr);
+size_t lfm_grad_scratch_doubles(int64_t N);
+int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G, const double* theta,
+                             const double* Sinv, int64_t ld, const double* alpha, double* scratch, double* grad,
+                             const LfmGrid* tg = nullptr);
+int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X, const double* Y, int G,
+                         const double* theta, double* out, int64_t ld);
+size_t lfm_grid_ws_doubles(int64_t N, int G, int64_t Tu);
+int lfm_grid_build(cudaStream_t st, int64_t N, int G, const double* X, const double* theta, int64_t Tu, bool grad,
+                   void* ws, LfmGrid* grid);
+// Effective table bound for a caller-supplied `time_grid`: 0 (direct evaluation) unless the tables are at
+// least 8x smaller than the matrix and fit 2 GB.
+static inline int64_t lfm_grid_effective(int64_t N, int G, int64_t time_grid) {
+  if (time_grid <= 0 || time_grid > 46000) return 0;
+  const double tab = (double)G * (double)time_grid * (double)time_grid;
+  if (tab * 8.0 > (double)N * (double)N) return 0;
+  if (tab * 6.0 * 8.0 > 2.0e9) return 0;
+  return time_grid;
 }
 
 // ExactLFM.kernel (model.py:152-195).  Only the branch the 0/1 switches select is evaluated;

@@ -122,7 +122,36 @@ def unconstrain(theta, G: int) -> torch.Tensor:
     return out
 
 
-def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int):
+_TG_CACHE: Dict[Tuple[int, int, int], int] = {}
+
+
+def distinct_times(X) -> int:
+    """Number of distinct times among the rows of X: the `time_grid` bound of the *_tg entry points.
+    Counted on a host copy; for a device tensor the answer is remembered per (storage, version, rows), so a
+    fit loop pays one device->host copy per data set, not per evaluation."""
+    import numpy as np
+
+    if isinstance(X, torch.Tensor):
+        if X.is_cuda:
+            key = (X.data_ptr(), X._version, X.shape[0])
+            if key not in _TG_CACHE:
+                if len(_TG_CACHE) > 64:
+                    _TG_CACHE.clear()
+                Xh = np.ascontiguousarray(X.detach().cpu().numpy(), dtype=np.float64)
+                _TG_CACHE[key] = int(_lib.lib().lfm_count_distinct_times(Xh.shape[0], Xh.ctypes.data))
+            return _TG_CACHE[key]
+        Xh = X.detach().numpy()
+    else:
+        Xh = np.asarray(X)
+    Xh = np.ascontiguousarray(Xh, dtype=np.float64)
+    if Xh.ndim != 2 or Xh.shape[1] != 3:
+        return 0
+    return int(_lib.lib().lfm_count_distinct_times(Xh.shape[0], Xh.ctypes.data))
+
+
+def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int, time_grid: Optional[int] = None):
+    if time_grid is None:
+        time_grid = distinct_times(X)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     theta = _theta(theta, G)
@@ -132,28 +161,30 @@ def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int):
     if N % G:
         raise ValueError(f"{N} rows is not divisible by num_genes={G} (model.py:145-149)")
     l = _lib.lib()
-    nbytes = l.lfm_nlml_workspace_bytes(N, G)
+    nbytes = l.lfm_nlml_workspace_bytes_tg(N, G, int(time_grid))
     ws = _workspace(nbytes, X.device, "nlml")
     out = torch.empty(nout, dtype=F64, device=X.device)
     info = torch.zeros(1, dtype=torch.int32, device=X.device)
     _lib.check(getattr(l, fn_name)(_stream(), N, G, X.data_ptr(), y.data_ptr(), theta.data_ptr(), float(jitter),
-                                   ws.data_ptr(), ws.numel(), out.data_ptr(), info.data_ptr()), fn_name)
+                                   int(time_grid), ws.data_ptr(), ws.numel(), out.data_ptr(), info.data_ptr()),
+               fn_name)
     return out, info
 
 
-def nlml(X, y, theta, jitter: float, G: int):
-    """CustomConjMLL(negative=True) value (reference src/objectives.py:21-78).  Returns (val[1], info[1])."""
-    return _nlml_call("lfm_nlml", X, y, theta, jitter, G, 1)
+def nlml(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None):
+    """CustomConjMLL(negative=True) value (reference src/objectives.py:21-78).  Returns (val[1], info[1]).
+    `time_grid`: bound on the distinct times of X (None: counted from X; 0: evaluate every entry directly)."""
+    return _nlml_call("lfm_nlml_tg", X, y, theta, jitter, G, 1, time_grid)
 
 
-def nlml_grad(X, y, theta, jitter: float, G: int):
+def nlml_grad(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None):
     """NLML and d NLML / d theta in constrained coordinates.  Returns (out[1+P], info[1])."""
-    return _nlml_call("lfm_nlml_grad", X, y, theta, jitter, G, 3 * G + 3)
+    return _nlml_call("lfm_nlml_grad_tg", X, y, theta, jitter, G, 3 * G + 3, time_grid)
 
 
-def nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
+def nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Optional[int] = None):
     """jax.value_and_grad(JaxTrainer.loss) w.r.t. the unconstrained leaves (reference src/trainer.py:126)."""
-    return _nlml_call("lfm_nlml_grad_unc", X, y, theta_unc, jitter, G, 3 * G + 3)
+    return _nlml_call("lfm_nlml_grad_unc_tg", X, y, theta_unc, jitter, G, 3 * G + 3, time_grid)
 
 
 def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):

@@ -95,6 +95,26 @@ int lfm_nlml_grad_unc(lfm_stream_t stream, int64_t N, int G, const double* X, co
                       const double* theta_unc, double jitter, void* ws, size_t ws_bytes, double* out,
                       int* info);
 
+/* ---- time-grid variants ----------------------------------------------------------------------
+ * `time_grid` is an upper bound on the number of DISTINCT times among the rows of X (0 = unknown;
+ * lfm_count_distinct_times gives it from a host copy).  The reference's layout observes every gene on
+ * the same few time points (src/dataset.py:380-391), and the exp/erf factors of h (src/model.py:315-365)
+ * depend on (gene, t, t') only: when the bound is small the library finds the distinct times on the
+ * device, tabulates those factors once per evaluation (G T^2 entries instead of N^2) and builds Sigma
+ * and the dK/dtheta contraction from the tables.  The tables hold the very values the direct path
+ * computes; results agree to rounding.  If X has more distinct times than the bound, the kernels
+ * detect it on the device and evaluate directly.  The plain entry points above are time_grid = 0. */
+int64_t lfm_count_distinct_times(int64_t N, const double* X_host);
+size_t lfm_nlml_workspace_bytes_tg(int64_t N, int G, int64_t time_grid);
+int lfm_nlml_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y, const double* theta,
+                double jitter, int64_t time_grid, void* ws, size_t ws_bytes, double* out, int* info);
+int lfm_nlml_grad_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                     const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
+                     double* out, int* info);
+int lfm_nlml_grad_unc_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                         const double* theta_unc, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
+                         double* out, int* info);
+
 /* ---- (d) latent posterior -------------------------------------------------------------------- */
 
 size_t lfm_latent_posterior_workspace_bytes(int64_t N, int G, int64_t Tstar);

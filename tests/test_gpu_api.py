@@ -277,3 +277,49 @@ def test_gene_expression_predictor(cuda):
     assert relerr(means[0], m_ref[:40]) < RTOL
     assert relerr(means[2], m_ref[120:160]) < RTOL  # blocks 3 and 4 swapped, as the reference does (utils.py:135-140)
     assert relerr(stds[4], np.sqrt(np.diag(c_ref))[160:]) < RTOL
+
+
+@pytest.mark.parametrize("G,T,R", [(5, 7, 1), (5, 7, 3), (6, 50, 1), (12, 40, 2)])
+def test_time_grid_tables_match_direct_evaluation(cuda, G, T, R):
+    """Time-grid tables (include/lfm_b200.h, *_tg): same NLML / gradient as evaluating every entry, against the
+    oracle too; a too-small bound falls back on the device; time_grid=0 is the direct path."""
+    from dis_project_b200 import ops
+    x, y, var, _ = o.synthetic_problem(G, T, R, seed=31)
+    rng = np.random.default_rng(32)
+    p = o.Params(d=rng.uniform(0.2, 1.0, G), s=rng.uniform(0.5, 1.5, G), b=rng.uniform(0.01, 0.1, G),
+                 l=float(rng.uniform(0.8, 3.2)), sigma=float(rng.uniform(0.6, 1.4)), jitter=1e-4)
+    assert ops.distinct_times(x) == T
+    v_ref, g_ref = o.nlml_and_grad(p, x, y)
+    direct, info0 = ops.nlml_grad(x, y, p.pack(), p.jitter, G, time_grid=0)
+    tab, info1 = ops.nlml_grad(x, y, p.pack(), p.jitter, G)                   # bound counted from X
+    small, info2 = ops.nlml_grad(x, y, p.pack(), p.jitter, G, time_grid=max(T - 2, 1))  # bound too small
+    loose, _ = ops.nlml_grad(x, y, p.pack(), p.jitter, G, time_grid=T + 5)
+    direct, tab, small, loose = (t.cpu().numpy() for t in (direct, tab, small, loose))
+    assert int(info0.item()) == 0 and int(info1.item()) == 0 and int(info2.item()) == 0
+    for out in (direct, tab, small, loose):
+        assert abs(out[0] - v_ref) <= RTOL * abs(v_ref)
+        assert np.max(np.abs(out[1:] - g_ref)) <= RTOL * np.max(np.abs(g_ref))
+    assert np.array_equal(small, direct)                    # the fallback IS the direct path
+    assert abs(tab[0] - direct[0]) <= 1e-13 * abs(direct[0])
+    assert np.max(np.abs(tab[1:] - direct[1:])) <= 1e-12 * np.max(np.abs(direct[1:]))
+    assert np.max(np.abs(loose - tab)) <= 1e-12 * np.max(np.abs(tab))
+    v, _ = ops.nlml(x, y, p.pack(), p.jitter, G)
+    assert abs(v.item() - v_ref) <= RTOL * abs(v_ref)
+
+
+def test_time_grid_irregular_times_use_direct_path(cuda):
+    """Every row its own time: the tables would be larger than the matrix, the library evaluates directly."""
+    from dis_project_b200 import ops
+    G, T = 4, 30
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=33)
+    x = x.copy()
+    x[:, 0] += np.random.default_rng(34).uniform(0, 0.05, x.shape[0])
+    p = o.Params.reference_init(G)
+    assert ops.distinct_times(x) == G * T
+    v_ref, g_ref = o.nlml_and_grad(p, x, y)
+    out, info = ops.nlml_grad(x, y, p.pack(), p.jitter, G)
+    out0, _ = ops.nlml_grad(x, y, p.pack(), p.jitter, G, time_grid=0)
+    assert np.array_equal(out.cpu().numpy(), out0.cpu().numpy())
+    out = out.cpu().numpy()
+    assert abs(out[0] - v_ref) <= RTOL * abs(v_ref)
+    assert np.max(np.abs(out[1:] - g_ref)) <= RTOL * np.max(np.abs(g_ref))

@@ -195,3 +195,16 @@ def test_best_objective_allreduce_gloo_world2():
         assert p.exitcode == 0
     assert [(r[1], r[2]) for r in res] == [(0, 6), (6, 11)]
     assert all(r[3] == 3.5 and r[4] == 3 for r in res)
+
+
+def test_count_distinct_times():
+    import ctypes as C
+    from dis_project_b200 import _lib
+    lib = _lib.lib()
+    x = np.stack((np.tile(np.linspace(0, 12, 7), 5), np.repeat(np.arange(5.0), 7), np.ones(35)), axis=1)
+    assert lib.lfm_count_distinct_times(35, x.ctypes.data) == 7
+    x2 = np.ascontiguousarray(np.concatenate([x, x + [[0.5, 0, 0]]]))
+    assert lib.lfm_count_distinct_times(70, x2.ctypes.data) == 14
+    assert lib.lfm_count_distinct_times(0, None) == 0
+    assert lib.lfm_nlml_workspace_bytes_tg(4000, 50, 80) > lib.lfm_nlml_workspace_bytes(4000, 50)
+    assert lib.lfm_nlml_workspace_bytes_tg(120, 4, 120) == lib.lfm_nlml_workspace_bytes(120, 4)  # tables not worthwhile
