@@ -90,20 +90,28 @@ __device__ __forceinline__ double leaf_rsqrt(double x) {
   return fma(t, y0 * e, y0);
 }
 __device__ __forceinline__ int warp_potrf_trtri32(double* __restrict__ D, int ldd, double* __restrict__ T,
-                                                  double* __restrict__ Winv, int lane) {
+                                                  double* __restrict__ Winv, int lane, long long* dbg = nullptr) {
   int fail = -1;
+  if (dbg && lane == 0) dbg[0] = clock64();
   double a[LB], y[LB];
 #pragma unroll
   for (int j = 0; j < LB; ++j) {
     a[j] = (j <= lane) ? D[lane * ldd + j] : 0.0;
     y[j] = (j == lane) ? 1.0 : 0.0;
   }
+  // The next pivot a_{k+1,k+1} - l_{k+1,k}^2 lives in lane k+1, which holds both operands in registers: it
+  // is broadcast from there, so the dependent chain per pivot is rsqrt -> scale -> one DFMA -> one
+  // shuffle and never waits for the shared-memory exchange.
+  double akk = __shfl_sync(0xffffffffu, a[0], 0);
+  if (dbg && lane == 0) dbg[1] = clock64();
 #pragma unroll
   for (int k = 0; k < LB; ++k) {
-    const double akk = __shfl_sync(0xffffffffu, a[k], k);
+    if (dbg && lane == 0 && (k == 8 || k == 16 || k == 24)) dbg[1 + k / 8] = clock64();
     if (!(akk > 0.0) && fail < 0) fail = k;
     const double rk = leaf_rsqrt(akk);
     const double lik = (lane == k) ? akk * rk : a[k] * rk;
+    double akk_next = 0.0;
+    if (k + 1 < LB) akk_next = __shfl_sync(0xffffffffu, fma(-lik, lik, a[k + 1]), k + 1);
     a[k] = lik;
     T[k * DP_LD + lane] = (lane >= k) ? lik : 0.0;
     const double wk = y[k] * rk;
@@ -124,12 +132,15 @@ __device__ __forceinline__ int warp_potrf_trtri32(double* __restrict__ D, int ld
         y[j + 1] = fma(-l2.y, wk, y[j + 1]);
       }
     }
+    akk = akk_next;
   }
+  if (dbg && lane == 0) dbg[5] = clock64();
 #pragma unroll
   for (int j = 0; j < LB; ++j) {
     D[lane * ldd + j] = (j <= lane) ? a[j] : 0.0;
     Winv[j * WD_LD + lane] = y[j];
   }
+  if (dbg && lane == 0) dbg[6] = clock64();
   return fail;
 }
 
@@ -287,14 +298,12 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
   for (int kb = 0; kb < 4; ++kb) {
     // ---- window kb: warp 0 runs D(kb); the other warps run the deferred work of step kb-1 ------------------
     if (warp == 0) {
-      const int f = warp_potrf_trtri32(SBLK(kb, kb), S_LD, T, WDI(kb), lane);
+      const int f = warp_potrf_trtri32(SBLK(kb, kb), S_LD, T, WDI(kb), lane, (stamps && kb == 0) ? stamps + 16 : nullptr);
       if (lane == 0 && f >= 0 && failed < 0) failed = kb * LB + f;
       if (kb == 0) asm volatile("cp.async.wait_group 0;\n" ::);
     } else if (warp == 4) {
+      // shares scheduler 0 with the chain warp: stays idle
       if (kb == 0) asm volatile("cp.async.wait_group 0;\n" ::);
-      if (kb >= 1) { store_L_row(kb - 1); }
-      if (kb == 1) store_W_row(0);
-      if (kb == 3) store_W_row(1);   // W row 1 was finished in window 2
     } else {
       if (kb == 0) {
         asm volatile("cp.async.wait_group 0;\n" ::);
@@ -310,6 +319,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
         else if (warp == 5) op_U(3, 2, 0);
         else if (warp == 6) op_U(3, 3, 0);
         else if (warp == 7) op_T(2, 0, 0, 0, false);   // L20 W00 (P(2,0) is done)
+        if (warp == 7) { store_L_row(0); store_W_row(0); }
       } else if (kb == 2) {
         if (warp == 1) op_P(3, 1);
         else if (warp == 2) op_F(1, 0);
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
         else if (warp == 3) op_T(2, 0, 1, 1, true);    // + L21 W10
         else if (warp == 5) op_T(3, 1, 1, 1, false);   // L31 W11
         else if (warp == 6) op_T(3, 0, 1, 1, true);    // + L31 W10
+        else if (warp == 7) store_L_row(1);
       } else {
         if (warp == 1) op_F(2, 1);
         else if (warp == 2) op_F(2, 0);
@@ -329,6 +340,8 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
         if (warp == 1) op_T(3, 1, 2, 2, true);         // + L32 W21
         else if (warp == 2) op_T(3, 0, 2, 2, true);    // + L32 W20
         else if (warp == 5) store_W_row(2);
+        else if (warp == 6) store_L_row(2);
+        else if (warp == 7) store_W_row(1);            // W row 1 was finished in window 2
       }
     }
     __syncthreads();
@@ -357,7 +370,17 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
   }
   // ---- tail: last block row of the inverse, W_3j = -Winv_33 T_3j, then the last block rows go out ----------
   if (warp >= 1 && warp <= 3) op_F(3, warp - 1);
-  else if (warp == 4) store_L_row(3);
+  else if (warp >= 4) {
+    // L row 3: 32 rows over warps 4-7
+    for (int r = (warp - 4) * 8; r < (warp - 4) * 8 + 8; ++r) {
+      const int row = 3 * LB + r;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = h * 64 + lane * 2;
+        *reinterpret_cast<double2*>(A + (int64_t)row * lda + c) = *reinterpret_cast<const double2*>(S + row * S_LD + c);
+      }
+    }
+  }
   __syncthreads();
   LEAF_STAMP();
   {
@@ -422,7 +445,7 @@ static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ld
 // runs on an internal HIGH-PRIORITY stream (its CTAs are placed before pending bulk CTAs whenever an SM
 // frees up; the two 128-row products run as 16 x 128 tiles over 8 CTAs each); the rest of the panel and of
 // the trailing update of step k stays on the caller's stream underneath leaf(k+1):
-//   bulk : wait leaf(k) | rows >= k+2 of the panel | wait L(k+1,k) | column k+1 of the update | square rest
+//   bulk : wait leaf(k) | rows >= k+2 of the panel | wait L(k+1,k) | trailing update minus block (k+1,k+1)
 //   chain: wait bulk(k-1) before the panel of step k reads A(k+1, k)
 // Fork/join is by events only (no host synchronisation; legal under stream capture).
 struct LookAhead {
@@ -505,10 +528,13 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.leaf_done[e], 0));
     LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.p1_done[e], 0));
-    // column k+1 of the trailing matrix: A(k+2:, k+1) -= L(k+2:, k) L(k+1, k)^T
-    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, NB, NB, P2, lda, P, lda, P2 + NB, lda, -1.0, 1.0, 0, LFM_K_FULL)));
-    // square rest: A(k+2:, k+2:) -= L(k+2:, k) L(k+2:, k)^T, lower tiles
-    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, m2, NB, P2, lda, P2, lda, P2 + 2 * NB, lda, -1.0, 1.0, 1, LFM_K_FULL)));
+    // trailing update A(k+1:, k+1:) -= L(k+1:, k) L(k+1:, k)^T on the lower tiles, minus the diagonal block
+    // (k+1, k+1) that the chain has already updated: one launch over a trapezoid of tiles
+    {
+      LfmGemm u = mk(0, 1, m, m, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 1, LFM_K_FULL);
+      u.tri_skip = NB;
+      LFM_TRY(lfm_dgemm(st, u));
+    }
     LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], st));
     bulk_used = true;
   }

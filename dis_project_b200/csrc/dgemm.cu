@@ -65,9 +65,12 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   if (g.lower_only) {
     // blockIdx.x enumerates lower-triangle tiles, longest k-range first: row tiles descending, except
     // when the k-range starts at the row tile
+    // (tiles of the first g.tri_skip rows, in units of BM, are not launched: skipped = s (s + 1) / 2)
+    const int64_t srows = g.tri_skip / BM;
+    const int64_t skipped = srows * (srows + 1) / 2;
     const int64_t total = (int64_t)gridDim.x;
     const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL);
-    const int64_t t = asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x;
+    const int64_t t = skipped + (asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x);
     int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
@@ -193,7 +196,7 @@ static GemmProf g_prof;
 static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
   const int64_t tm = g.M / BM, tn = g.N / BN;
   double f = 0.0;
-  for (int64_t i = 0; i < tm; ++i) {
+  for (int64_t i = (g.lower_only ? g.tri_skip / BM : 0); i < tm; ++i) {
     const int64_t jn = g.lower_only ? (i + 1) : tn;
     for (int64_t j = 0; j < jn; ++j) {
       int64_t kb = 0, ke = g.K;
@@ -261,6 +264,11 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   }
   const int64_t tm = g.M / BM, tn = g.N / BN;
   int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  if (g.lower_only && g.tri_skip > 0) {
+    if (BM != BN || g.tri_skip % BM) return LFM_ERR_INVALID;
+    const int64_t sr = g.tri_skip / BM;
+    tiles -= sr * (sr + 1) / 2;
+  }
   if (tiles <= 0) return LFM_OK;
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   if (g_prof.on) {
@@ -308,13 +316,15 @@ int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
   }
   if (inplace) {
     if (g.N != 128) return LFM_ERR_INVALID;
-    return (t128 >= 148) ? dispatch<8, 4, 2>(st, g) : dispatch<4, 4, 2>(st, g);
+    if (t128 >= 148) return dispatch<8, 4, 2>(st, g);
+    return (g.M / 64 >= 148) ? dispatch<4, 4, 2>(st, g) : dispatch<2, 4, 2>(st, g);  // 64- or 32-row tiles: fill the SMs
   }
   static int force = -1;
   if (force < 0) { const char* e = getenv("LFM_GEMM_FORCE"); force = e ? atoi(e) : 0; }
   if (force == 1) return dispatch<4, 4, 4>(st, g);
   if (force == 2) return dispatch<8, 4, 2>(st, g);
   if (force == 3) return dispatch<4, 2, 2>(st, g);
+  if (g.tri_skip > 0) return dispatch<4, 2, 2>(st, g);  // rank-128 trailing updates: 64 x 64 tiles measured fastest
   if (t128 >= 3 * 148) return big_variant() ? dispatch<4, 4, 4>(st, g) : dispatch<8, 4, 2>(st, g);
   return dispatch<4, 2, 2>(st, g);
 }

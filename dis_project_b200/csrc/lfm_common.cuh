@@ -71,6 +71,7 @@ struct LfmGemm {
   int batch;           // > 1: blockIdx.y-th problem uses A + y*strideA, B + y*strideB, C + y*strideC
   int64_t strideA, strideB, strideC;
   int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain)
+  int tri_skip = 0;    // lower_only: skip the output tiles of the first `tri_skip` rows of C (the look-ahead chain owns them)
 };
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
 

@@ -12,6 +12,6 @@ for it in range(3):
     l.lfm_debug_leaf_profile(torch.cuda.current_stream().cuda_stream, A.data_ptr(), W.data_ptr(), info.data_ptr(), st.data_ptr())
     torch.cuda.synchronize()
     s=st.cpu().numpy()[:11]
-    print("cycles:", np.diff(s), "total", s[10]-s[0])
+    print("cycles:", np.diff(s), "total", s[10]-s[0], "| D0: load, k0-7, k8-15, k16-23, k24-31, store:", np.diff(st.cpu().numpy()[16:23]))
 names=["load(0,0)","win0(D0)","PU0","win1(D1)","PU1","win2(D2)","PU2","win3(D3)","tailF","storeW3"]
 print(names)

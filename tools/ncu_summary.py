@@ -13,8 +13,8 @@ def launches(src, dst, note):
     lines = [l for l in open(src) if not l.startswith("==")]
     rows = [r for r in csv.DictReader(lines) if r.get("Metric Name") == "gpu__time_duration.sum"]
     names = [re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "") for r in rows]
-    # one evaluation = from one Sigma build (lfm_gram_tile_kernel<1>) to the next
-    idx = [i for i, n in enumerate(names) if "lfm_gram_tile_kernel<1>" in n]
+    # one evaluation = from one residual kernel (first launch of an NLML evaluation) to the next
+    idx = [i for i, n in enumerate(names) if "lfm_residual_kernel" in n]
     s, e = (idx[-2], idx[-1]) if len(idx) >= 2 else (0, len(rows))
     agg = collections.OrderedDict(); tot = 0.0
     for r, n in zip(rows[s:e], names[s:e]):
