@@ -117,6 +117,7 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters) if hi > lo else None
     if st is not None and not isinstance(X, torch.Tensor):
         st.unique_hint = ops.unique_rows(X)  # from the host copy: no device->host round trip
+        st.time_grid = ops.distinct_times(X)
     main = torch.cuda.current_stream()
     side = torch.cuda.Stream()
     ids = torch.arange(lo, hi, dtype=torch.float64, device=Xd.device)

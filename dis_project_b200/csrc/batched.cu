@@ -25,22 +25,7 @@
 #include "sim_math.cuh"
 
 
-struct BatchedArgs {
-  int64_t B;
-  int N, G;
-  const double* X;
-  const double* y;
-  double* u_io;       // B x P unconstrained (in/out)
-  double* adam;       // B x 2P (m, v) or NULL
-  double jitter, lr, b1, b2, eps;
-  int first_step, steps, total_steps, fix_params, steps_per_epoch;
-  double* hist; int64_t ld_hist;
-  double* theta_out;  // B x P constrained result written when the last step of the fit is reached (or NULL)
-  double* eval_val;   // eval-only mode: B
-  double* eval_grad;  // eval-only mode: B x P
-  int* info;
-  int max_unique;     // shared-memory matrix is sized for this many unique rows (N when unknown)
-};
+#include "batched.cuh"
 
 template <int BT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -407,12 +392,16 @@ static size_t batched_smem_bytes(int N, int G, int MU) {
   return d * 8 + (size_t)N * sizeof(LfmPoint) + 2 * (size_t)N * sizeof(int);
 }
 
-static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
+static int batched_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) {
   if (a.B <= 0 || a.N <= 0 || a.G <= 0 || !a.X || !a.y || !a.u_io) return LFM_ERR_INVALID;
   if (a.N % a.G) return LFM_ERR_INVALID;
   if (a.N > 128 || a.B > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   BatchedArgs b = a;
   if (b.max_unique <= 0 || b.max_unique > b.N) b.max_unique = b.N;
+  if (time_grid > 0) {  // one warp per LFM with shared-memory time-grid tables, when it fits
+    const int st2 = lfm_batched_warp_launch(st, b, time_grid);
+    if (st2 != LFM_ERR_UNSUPPORTED) return st2;
+  }
   const size_t smem = batched_smem_bytes(b.N, b.G, b.max_unique);
   if (smem > 227 * 1024) return LFM_ERR_UNSUPPORTED;
   const bool small = b.max_unique <= 64 && b.N <= 128 && 3 * b.G + 2 <= 128;
@@ -436,9 +425,10 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a) {
   return LFM_OK;
 }
 
-extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
-                                         const double* y, const double* theta_unc, double jitter,
-                                         int unique_rows_hint, double* out_val, double* out_grad, int* info) {
+extern "C" int lfm_batched_nlml_grad_unc_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                            const double* y, const double* theta_unc, double jitter,
+                                            int unique_rows_hint, int time_grid_hint, double* out_val,
+                                            double* out_grad, int* info) {
   if (!out_val || !out_grad) return LFM_ERR_INVALID;
   BatchedArgs a;
   memset(&a, 0, sizeof(a));
@@ -447,14 +437,20 @@ extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t
   a.jitter = jitter; a.steps = 1; a.total_steps = 1; a.steps_per_epoch = 1;
   a.eval_val = out_val; a.eval_grad = out_grad; a.info = info; a.max_unique = unique_rows_hint;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
-  return batched_launch((cudaStream_t)stream, a);
+  return batched_launch((cudaStream_t)stream, a, time_grid_hint);
+}
+extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                         const double* y, const double* theta_unc, double jitter,
+                                         int unique_rows_hint, double* out_val, double* out_grad, int* info) {
+  return lfm_batched_nlml_grad_unc_tg(stream, B, N, G, X, y, theta_unc, jitter, unique_rows_hint, 0, out_val, out_grad,
+                                      info);
 }
 
-extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
-                               double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
-                               double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
-                               int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
-                               double* out_theta, int* info) {
+extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                                  double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
+                                  double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
+                                  int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
+                                  int64_t ld_hist, double* out_theta, int* info) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
@@ -465,7 +461,16 @@ extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G,
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
   a.info = info; a.max_unique = unique_rows_hint;
-  return batched_launch((cudaStream_t)stream, a);
+  return batched_launch((cudaStream_t)stream, a, time_grid_hint);
+}
+extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                               double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
+                               double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
+                               int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
+                               double* out_theta, int* info) {
+  return lfm_batched_fit_tg(stream, B, N, G, X, y, theta_unc_io, adam_state, jitter, lr, b1, b2, eps, first_step, steps,
+                            total_steps, fix_params, steps_per_epoch, unique_rows_hint, 0, out_hist, ld_hist, out_theta,
+                            info);
 }
 
 // Number of distinct (time, gene, flag) rows of a HOST copy of X: the `unique_rows_hint` that lets the

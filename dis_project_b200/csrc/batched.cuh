@@ -1,0 +1,23 @@
+// Arguments shared by the two batched kernels (batched.cu: one CTA per LFM; batched_warp.cu: one warp per LFM).
+#pragma once
+#include "sim_math.cuh"
+
+struct BatchedArgs {
+  int64_t B;
+  int N, G;
+  const double* X;
+  const double* y;
+  double* u_io;       // B x P unconstrained (in/out)
+  double* adam;       // B x 2P (m, v) or NULL
+  double jitter, lr, b1, b2, eps;
+  int first_step, steps, total_steps, fix_params, steps_per_epoch;
+  double* hist; int64_t ld_hist;
+  double* theta_out;  // B x P constrained result written when the last step of the fit is reached (or NULL)
+  double* eval_val;   // eval-only mode: B
+  double* eval_grad;  // eval-only mode: B x P
+  int* info;
+  int max_unique;     // shared-memory matrix is sized for this many unique rows (N when unknown)
+};
+
+// batched_warp.cu: launches the warp-per-LFM kernel when the problem fits its limits, else LFM_ERR_UNSUPPORTED
+int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid);

@@ -247,9 +247,11 @@ def unique_rows(X) -> int:
     return int(_lib.lib().lfm_count_unique_rows(Xh.shape[0], Xh.ctypes.data))
 
 
-def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
-    """B independent value_and_grad evaluations.  theta_unc (B, P) -> (val[B], grad[B,P], info[B])."""
+def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Optional[int] = None):
+    """B independent value_and_grad evaluations.  theta_unc (B, P) -> (val[B], grad[B,P], info[B]).
+    `time_grid`: bound on the distinct times of X (None: counted from X; 0: one CTA per LFM, no tables)."""
     hint = unique_rows(X)
+    tg = distinct_times(X) if time_grid is None else int(time_grid)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     u = _dev(theta_unc)
@@ -262,10 +264,10 @@ def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int):
     info = torch.zeros(B, dtype=torch.int32, device=X.device)
     if B == 0:
         return val, grad, info
-    _lib.check(_lib.lib().lfm_batched_nlml_grad_unc(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), u.data_ptr(),
-                                                    float(jitter), hint, val.data_ptr(), grad.data_ptr(),
-                                                    info.data_ptr()),
-               "lfm_batched_nlml_grad_unc")
+    _lib.check(_lib.lib().lfm_batched_nlml_grad_unc_tg(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), u.data_ptr(),
+                                                       float(jitter), hint, tg, val.data_ptr(), grad.data_ptr(),
+                                                       info.data_ptr()),
+               "lfm_batched_nlml_grad_unc_tg")
     return val, grad, info
 
 
@@ -287,6 +289,7 @@ class BatchedFitState:
         self.info = torch.zeros(self.B, dtype=torch.int32, device=dev)
         self.step = 0
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
+        self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
 
 
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
@@ -295,17 +298,19 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
+    if state.time_grid is None:
+        state.time_grid = distinct_times(X)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     if state.B == 0 or steps <= 0:
         return
     steps = min(steps, state.total_steps - state.step)
-    _lib.check(_lib.lib().lfm_batched_fit(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
-                                          state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
-                                          state.step, steps, state.total_steps, int(bool(fix_params)),
-                                          int(steps_per_epoch), state.unique_hint, state.hist.data_ptr(),
-                                          state.hist.shape[1],
-                                          state.theta.data_ptr(), state.info.data_ptr()), "lfm_batched_fit")
+    _lib.check(_lib.lib().lfm_batched_fit_tg(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
+                                             state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
+                                             state.step, steps, state.total_steps, int(bool(fix_params)),
+                                             int(steps_per_epoch), state.unique_hint, int(state.time_grid),
+                                             state.hist.data_ptr(), state.hist.shape[1],
+                                             state.theta.data_ptr(), state.info.data_ptr()), "lfm_batched_fit_tg")
     state.step += steps
 
 

@@ -167,6 +167,20 @@ int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const doub
                     int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
                     double* out_theta, int* info);
 
+/* Time-grid variants of the two batched entry points: `time_grid_hint` is an upper bound on the number of
+ * DISTINCT times among the rows of X (lfm_count_distinct_times; 0 = unknown).  With both hints set and
+ * the problem inside the limits of the one-warp-per-LFM kernel (unique rows <= 64, G T^2 <= 2048), every
+ * LFM is fitted by a single warp with the exp/erf pair terms tabulated once per step in shared memory;
+ * otherwise the one-CTA-per-LFM kernel runs.  A hint smaller than the true count gives info = -2. */
+int lfm_batched_nlml_grad_unc_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                 const double* y, const double* theta_unc, double jitter, int unique_rows_hint,
+                                 int time_grid_hint, double* out_val, double* out_grad, int* info);
+int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                       double* theta_unc_io, double* adam_state, double jitter, double lr, double b1, double b2,
+                       double eps, int first_step, int steps, int total_steps, int fix_params,
+                       int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
+                       int64_t ld_hist, double* out_theta, int* info);
+
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */
 

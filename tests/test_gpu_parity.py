@@ -178,3 +178,35 @@ def test_batched_fit_matches_trainer(cuda, R, fix):
         # 150 chained optimiser steps amplify rounding differences; 1e-7 on the trajectory end point
         assert relerr(hist[b], h_ref) < 1e-8
         assert relerr(theta[b], th_ref) < 1e-7
+
+
+@pytest.mark.parametrize("G,T,R", [(5, 7, 1), (5, 7, 3), (3, 12, 2), (8, 8, 1), (2, 20, 3)])
+def test_batched_warp_kernel_matches_cta_kernel(cuda, G, T, R):
+    """One-warp-per-LFM kernel (time-grid tables in shared memory) against the one-CTA-per-LFM kernel
+    (time_grid=0) and the oracle: evaluation and a 40-step fit, unique rows 16..64 (both lane mappings)."""
+    from dis_project_b200 import ops
+    x, y, var, _ = o.synthetic_problem(G, T, R, seed=41)
+    rng = np.random.default_rng(42)
+    B = 5
+    u0 = o.unconstrain(o.Params.reference_init(G).pack())
+    U = u0[None, :] + 0.4 * rng.standard_normal((B, u0.shape[0]))
+    v1, g1, i1 = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G)
+    v0, g0, i0 = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G, time_grid=0)
+    assert not i1.cpu().numpy().any() and not i0.cpu().numpy().any()
+    v1, g1, v0, g0 = (t.cpu().numpy() for t in (v1, g1, v0, g0))
+    for b in range(B):
+        v, g = o.nlml_and_grad_unc(U[b], x, y, 1e-4)
+        assert abs(v1[b] - v) <= RTOL * abs(v) and relerr(g1[b], g) < RTOL
+        assert abs(v1[b] - v0[b]) <= 1e-11 * abs(v0[b]) and relerr(g1[b], g0[b]) < 1e-10
+    TH = o.constrain(U)
+    sa = ops.BatchedFitState(TH, G, 40)
+    sb = ops.BatchedFitState(TH, G, 40)
+    sb.time_grid = 0
+    for chunk in (7, 33):
+        ops.batched_fit_steps(sa, x, y, 1e-4, chunk)
+        ops.batched_fit_steps(sb, x, y, 1e-4, chunk)
+    assert relerr(sa.hist.cpu().numpy(), sb.hist.cpu().numpy()) < 1e-9
+    assert relerr(sa.theta.cpu().numpy(), sb.theta.cpu().numpy()) < 1e-8
+    # a time-grid bound that is too small is refused, not silently wrong
+    vv, gg, ii = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G, time_grid=T - 1)
+    assert np.all(ii.cpu().numpy() == -2) and np.all(np.isnan(vv.cpu().numpy()))
