@@ -13,7 +13,7 @@
 //     G T^2 evaluations instead of 2 U^2 (p53: 245 instead of 2520), one erf/erfc call per entry;
 //   * rows are mapped to lanes as {lane < U-32, (U-32) + lane}, so the triangular phases touch the
 //     U - 32 "extra" rows only while they are short.
-// Limits: N <= 128, U <= 64, 3G+2 <= 64, G T^2 <= 2048; anything else runs the CTA-per-LFM kernel.
+// Limits: N <= 128, U <= 40, 3G+2 <= 64, G T^2 <= 2048; anything else runs the CTA-per-LFM kernel.
 #include "batched.cuh"
 
 
@@ -37,9 +37,11 @@ __device__ __forceinline__ double w_rsqrt(double x) {
   return fma(t, y0 * e, y0);
 }
 
+#define WEX 8             // most "extra" rows beyond 32 the warp kernel takes (U <= 40)
+#define XLD (WEX + 1)
 struct WarpLayout {
   int ld;
-  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, w, beta, kb, wdiag, sdiag, dsum, th, u, gr, am, av, mu, ys;
+  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, w, beta, kb, wdiag, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, Msm, Xs, xdiag;
   size_t pts;       // byte offset
   size_t ints;      // byte offset: umap[N], urow[MU], rows_of[N], mflag[N]
   size_t bytes;
@@ -50,7 +52,7 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   L.ld = MU | 1;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 1) & ~(size_t)1; return r; };
-  L.S = take((size_t)MU * L.ld);
+  L.S = take((size_t)MU * L.ld > 32 * 33 ? (size_t)MU * L.ld : 32 * 33);  // also holds W22 as Wb[32][33]
   const size_t tab = (size_t)G * MT * MT;
   L.tA1R1 = take(tab); L.tA1 = take(tab); L.tG1 = take(tab);
   L.g2 = take((size_t)G * MT); L.inv = take((size_t)G * G); L.utime = take(MT);
@@ -59,11 +61,16 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   L.dsum = take(MU);
   L.th = take(P); L.u = take(P); L.gr = take(P); L.am = take(P); L.av = take(P); L.mu = take(G);
   L.ys = take(N);
+  L.ring = take(4 * 32);
+  L.Msm = take(WEX * 32);
+  L.Xs = take(WEX * XLD);
+  L.xdiag = take(WEX);
   L.pts = o * 8;
   size_t b = L.pts + (size_t)MU * sizeof(LfmPoint);
   b = (b + 15) & ~(size_t)15;
   L.ints = b;
   b += sizeof(int) * ((size_t)3 * N + MU);
+  b += sizeof(unsigned short) * ((size_t)MU * (MU + 1) / 2 + 2);  // pair table
   L.bytes = (b + 15) & ~(size_t)15;
   return L;
 }
@@ -83,12 +90,14 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   double* q = base + L.q; double* w = base + L.w; double* beta = base + L.beta; double* kb = base + L.kb;
   double* wdiag = base + L.wdiag; double* sdiag = base + L.sdiag; double* dsum = base + L.dsum;
   double* th = base + L.th; double* u = base + L.u; double* gr = base + L.gr; double* am = base + L.am;
-  double* av = base + L.av; double* mu = base + L.mu; double* ys = base + L.ys;
+  double* av = base + L.av; double* mu = base + L.mu; double* ys = base + L.ys; double* ring = base + L.ring;
+  double* Msm = base + L.Msm; double* Xs = base + L.Xs; double* xdiag = base + L.xdiag;
   LfmPoint* pts = reinterpret_cast<LfmPoint*>(smem_raw + L.pts);
   int* umap = reinterpret_cast<int*>(smem_raw + L.ints);  // row -> unique index       (N)
   int* urow = umap + N;                                   // unique index -> first row (MU)
   int* rows_of = urow + MU;                               // rows of class u: rows_of[u * R + r] (N)
   int* mflag = rows_of + N;                               // 2 * positional block + flag (N)
+  unsigned short* pairs = reinterpret_cast<unsigned short*>(mflag + N);  // lower-triangle pair p -> (r << 8) | c
 
   for (int p = lane; p < P; p += 32) {
     u[p] = a.u_io[bidx * P + p];
@@ -187,6 +196,12 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
 
   const int ld = U | 1;
   const int npairs = U * (U + 1) / 2;
+  for (int p = lane; p < npairs; p += 32) {
+    int r, cc;
+    wpair_decode(p, r, cc);
+    pairs[p] = (unsigned short)((r << 8) | cc);
+  }
+  __syncwarp();
   const bool eval_only = a.eval_val != nullptr;
   const int nsteps = eval_only ? 1 : a.steps;
   const double dR = (double)R;
@@ -268,8 +283,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     };
     // ---- D. M = c I + R K_u (lower + diagonal) -------------------------------------------------------
     for (int p = lane; p < npairs; p += 32) {
-      int r, cc;
-      wpair_decode(p, r, cc);
+      const int r = pairs[p] >> 8, cc = pairs[p] & 255;
       const LfmPoint pi = pts[r], pj = pts[cc];
       double H1, H2, u0, u1, u2;
       lfm_h_core<false>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, u0, u1, u2);
@@ -279,87 +293,195 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       S[r * ld + cc] = k;
     }
     __syncwarp();
-    // ---- E. Cholesky, left-looking, one lane per row ({lane < ex, ex + lane}) ---------------------------
-    for (int k = 0; k < U; ++k) {
-      const double* rk = S + k * ld;
-      double vA = 0.0, vB = 0.0;
-      const int rowA = lane, rowB = ex + lane;
-      const bool onA = k < ex && rowA >= k && rowA < ex;
-      const bool onB = rowB >= k && rowB < U;
-      if (k < ex) {  // warp-uniform: the extra rows are only live while k < ex
-        if (onA) {
-          const double* ri = S + rowA * ld;
-          double s0 = 0.0, s1 = 0.0;
-          int m = 0;
-          for (; m + 2 <= k; m += 2) { s0 = fma(ri[m], rk[m], s0); s1 = fma(ri[m + 1], rk[m + 1], s1); }
-          if (m < k) s0 = fma(ri[m], rk[m], s0);
-          vA = ri[k] - (s0 + s1);
+    // ---- E. M^-1 and log det M.  M = [[M11, M21^T], [M21, M22]] with M22 the trailing n2 = U - ex (<= 32) rows.
+    // M22 is factorised AND inverted in registers (lane i owns row i of M22 / L22 and column i of W22 = L22^-1; the
+    // pivot loop is fully unrolled; lanes >= n2 carry identity rows); the ex <= 8 leading rows enter through the
+    // Schur complement, every per-lane quantity in registers with compile-time indices:
+    //   B = M22^-1 M21,  S11 = M11 - M21^T B,  X11 = S11^-1,  Y = B X11,
+    //   M^-1 = [[X11, -Y^T], [-Y, M22^-1 + Y B^T]],   log det M = log det M22 + log det S11.
+    double logdetM;
+    {
+      const int n2 = U - ex;
+      double am[32], yw[32], m21[WEX];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        am[j] = (lane < n2) ? ((j <= lane) ? S[(ex + lane) * ld + ex + j] : 0.0) : ((j == lane) ? 1.0 : 0.0);
+        yw[j] = (j == lane) ? 1.0 : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < WEX; ++j) {
+        m21[j] = (j < ex && lane < n2) ? S[(ex + lane) * ld + j] : 0.0;
+        Msm[j * 32 + lane] = m21[j];                       // M21 transposed: Msm[j][c] = M21[c][j]
+      }
+      if (lane < ex)
+        for (int b1 = 0; b1 <= lane; ++b1) Xs[lane * XLD + b1] = S[lane * ld + b1];
+      __syncwarp();  // S is free from here on: it becomes Wb[32][33]
+      double my_rk = 1.0;
+      double akk = __shfl_sync(0xffffffffu, am[0], 0);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (!(akk > 0.0) && fail == 0) fail = ex + k + 1;
+        const double rk = w_rsqrt(akk);
+        const double lik = (lane == k) ? akk * rk : am[k] * rk;
+        double akk_next = 0.0;
+        if (k + 1 < 32) akk_next = __shfl_sync(0xffffffffu, fma(-lik, lik, am[k + 1]), k + 1);
+        if (lane == k) my_rk = rk;
+        am[k] = lik;
+        double* Tk = ring + (k & 3) * 32;
+        Tk[lane] = (lane >= k) ? lik : 0.0;
+        const double wk = yw[k] * rk;
+        yw[k] = wk;
+        __syncwarp();
+        if (k + 1 < 32) {
+          if ((k + 1) & 1) {
+            const double l1 = Tk[k + 1];
+            am[k + 1] = fma(-lik, l1, am[k + 1]);
+            yw[k + 1] = fma(-l1, wk, yw[k + 1]);
+          }
+#pragma unroll
+          for (int j = (k + 2) & ~1; j < 32; j += 2) {
+            const double2 l2 = *reinterpret_cast<const double2*>(Tk + j);
+            am[j] = fma(-lik, l2.x, am[j]);
+            am[j + 1] = fma(-lik, l2.y, am[j + 1]);
+            yw[j] = fma(-l2.x, wk, yw[j]);
+            yw[j + 1] = fma(-l2.y, wk, yw[j + 1]);
+          }
+        }
+        akk = akk_next;
+      }
+      double ld22 = (lane < n2) ? -log(my_rk) : 0.0;   // log L_kk = -log(1 / L_kk)
+      ld22 = 2.0 * wsum(ld22);
+      // W22 -> Wb[i][c] (constant stride 33; padded lanes carry exact zeros / identity)
+      double* Wb = S;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) Wb[i * 33 + lane] = yw[i];
+      __syncwarp();
+      // row `lane` of M22^-1 = W22^T W22 (complete row, both sides of the diagonal)
+      double mrow[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        double s0 = 0.0;
+#pragma unroll
+        for (int k = c; k < 32; ++k) s0 = fma(yw[k], Wb[k * 33 + c], s0);
+        mrow[c] = s0;
+      }
+      double ld11 = 0.0;
+      double yrow[WEX];
+#pragma unroll
+      for (int j = 0; j < WEX; ++j) yrow[j] = 0.0;
+      if (ex > 0) {
+        double bcol[WEX];
+#pragma unroll
+        for (int j = 0; j < WEX; ++j) {
+          double s0 = 0.0;
+          if (j < ex) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) s0 = fma(mrow[c], Msm[j * 32 + c], s0);
+          }
+          bcol[j] = s0;   // B[lane][j]
+        }
+        // S11 = M11 - M21^T B (lower), by lane 0 into Xs
+#pragma unroll
+        for (int a1 = 0; a1 < WEX; ++a1)
+#pragma unroll
+          for (int b1 = 0; b1 <= a1; ++b1)
+            if (a1 < ex) {
+              const double t = wsum(m21[a1] * bcol[b1]);
+              if (lane == 0) Xs[a1 * XLD + b1] -= t;
+            }
+        __syncwarp();
+        // S11 = L11 L11^T (left-looking, lane per row); W11 = L11^-1 in the upper triangle; X11 = W11^T W11
+        for (int k = 0; k < ex; ++k) {
+          double v = 0.0;
+          const bool on = lane >= k && lane < ex;
+          if (on) {
+            double s0 = 0.0;
+            for (int m = 0; m < k; ++m) s0 = fma(Xs[lane * XLD + m], Xs[k * XLD + m], s0);
+            v = Xs[lane * XLD + k] - s0;
+          }
+          const double piv = __shfl_sync(0xffffffffu, v, k);
+          if (!(piv > 0.0) && fail == 0) fail = k + 1;
+          const double rkk = w_rsqrt(piv);
+          if (on) Xs[lane * XLD + k] = (lane == k) ? piv * rkk : v * rkk;
+          if (lane == 0) { xdiag[k] = rkk; ld11 -= log(rkk); }
+          __syncwarp();
+        }
+        ld11 = 2.0 * __shfl_sync(0xffffffffu, ld11, 0);
+        if (lane < ex) {  // column `lane` of W11 into row `lane` of the upper triangle: Xs[c][i] = W11[i][c], i > c
+          const int cc = lane;
+          for (int i = cc + 1; i < ex; ++i) {
+            double s0 = Xs[i * XLD + cc] * xdiag[cc];
+            for (int k = cc + 1; k < i; ++k) s0 = fma(Xs[i * XLD + k], Xs[cc * XLD + k], s0);
+            Xs[cc * XLD + i] = -s0 * xdiag[i];
+          }
+        }
+        __syncwarp();
+        if (lane < ex) {  // row `lane` of X11 = W11^T W11 (lower + diagonal) -> registers, then in place
+          const int a1 = lane;
+          double xr[WEX];
+#pragma unroll
+          for (int b1 = 0; b1 < WEX; ++b1) {
+            double s0 = 0.0;
+            if (b1 <= a1) {
+              s0 = xdiag[a1] * ((a1 == b1) ? xdiag[a1] : Xs[b1 * XLD + a1]);
+              for (int k = a1 + 1; k < ex; ++k) s0 = fma(Xs[a1 * XLD + k], Xs[b1 * XLD + k], s0);
+            }
+            xr[b1] = s0;
+          }
+#pragma unroll
+          for (int b1 = 0; b1 < WEX; ++b1)
+            if (b1 <= a1) Xs[a1 * XLD + b1] = xr[b1];   // lower incl. diagonal; the upper triangle (W11) stays readable
+        }
+        __syncwarp();
+        // Y = B X11 (X11 symmetric, read from the lower triangle), B -> Msm for the rank-ex correction
+#pragma unroll
+        for (int a1 = 0; a1 < WEX; ++a1) {
+          double s0 = 0.0;
+          if (a1 < ex) {
+#pragma unroll
+            for (int b1 = 0; b1 < WEX; ++b1)
+              if (b1 < ex) s0 = fma(bcol[b1], (b1 <= a1) ? Xs[a1 * XLD + b1] : Xs[b1 * XLD + a1], s0);
+          }
+          yrow[a1] = s0;   // Y[lane][a1]
+        }
+#pragma unroll
+        for (int j = 0; j < WEX; ++j) Msm[j * 32 + lane] = bcol[j];
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          double s0 = mrow[c];
+#pragma unroll
+          for (int a1 = 0; a1 < WEX; ++a1)
+            if (a1 < ex) s0 = fma(yrow[a1], Msm[a1 * 32 + c], s0);   // + Y[lane][a] B[c][a]
+          mrow[c] = s0;
         }
       }
-      if (onB) {
-        const double* ri = S + rowB * ld;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int m = 0;
-        for (; m + 4 <= k; m += 4) {
-          s0 = fma(ri[m], rk[m], s0); s1 = fma(ri[m + 1], rk[m + 1], s1);
-          s2 = fma(ri[m + 2], rk[m + 2], s2); s3 = fma(ri[m + 3], rk[m + 3], s3);
+      __syncwarp();  // every lane is done with Wb: S receives M^-1 (lower triangle, runtime ld) and sdiag
+      if (lane < n2) {
+        double* row = S + (ex + lane) * ld;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c < lane) row[ex + c] = mrow[c];
+          else if (c == lane) sdiag[ex + lane] = mrow[c];
         }
-        for (; m < k; ++m) s0 = fma(ri[m], rk[m], s0);
-        vB = ri[k] - ((s0 + s1) + (s2 + s3));
+#pragma unroll
+        for (int a1 = 0; a1 < WEX; ++a1)
+          if (a1 < ex) row[a1] = -yrow[a1];               // M^-1_21 = -Y
       }
-      // pivot: row k lives in lane k (set A) while k < ex, else in lane k - ex (set B)
-      const double piv = (k < ex) ? __shfl_sync(0xffffffffu, vA, k) : __shfl_sync(0xffffffffu, vB, k - ex);
-      if (!(piv > 0.0) && fail == 0) fail = k + 1;
-      const double rkk = w_rsqrt(piv);
-      __syncwarp();
-      if (onA) S[rowA * ld + k] = (rowA == k) ? piv * rkk : vA * rkk;
-      if (onB) S[rowB * ld + k] = (rowB == k) ? piv * rkk : vB * rkk;
-      if (lane == 0) wdiag[k] = rkk;  // 1 / L_kk
-      __syncwarp();
-    }
-    // ---- F. log det M; W = L^-1 into the upper triangle (row c of S holds column c of W) -------------------
-    double logdet_part = 0.0;
-    for (int r = lane; r < U; r += 32) logdet_part += log(S[r * ld + r]);
-    const double logdetM = 2.0 * wsum(logdet_part);
-    // W[i][c] = -(sum_{k=c}^{i-1} L[i][k] W[k][c]) / L_ii, one lane per column c, rows ascending.
-    // columns {lane < ex} need all rows, columns ex + lane only rows > ex: the second pass is short.
-    for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 0 && ex == 0) continue;
-      const int cc = pass == 0 ? lane : ex + lane;
-      const bool on = pass == 0 ? (lane < ex) : (cc < U);
-      const int c0 = pass == 0 ? 0 : ex;           // smallest column of this pass
-      const double wcc = on ? wdiag[cc] : 0.0;
-      double* wc = S + (on ? cc : 0) * ld;         // wc[i] = W[i][cc] for i > cc
-      for (int i = c0 + 1; i < U; ++i) {
-        const double* li = S + i * ld;
-        double s0 = 0.0, s1 = 0.0;
-        int k = c0;
-        for (; k + 2 <= i; k += 2) {
-          const double w0 = (k == cc) ? wcc : wc[k];
-          const double w1 = (k + 1 == cc) ? wcc : wc[k + 1];
-          if (k >= cc) s0 = fma(li[k], w0, s0);
-          if (k + 1 >= cc) s1 = fma(li[k + 1], w1, s1);
-        }
-        if (k < i) {
-          const double w0 = (k == cc) ? wcc : wc[k];
-          if (k >= cc) s0 = fma(li[k], w0, s0);
-        }
-        if (on && i > cc) wc[i] = -(s0 + s1) * wdiag[i];
+      if (lane < ex) {
+        for (int b1 = 0; b1 < lane; ++b1) S[lane * ld + b1] = Xs[lane * XLD + b1];
+        sdiag[lane] = Xs[lane * XLD + lane];
       }
       __syncwarp();
+      logdetM = ld22 + ld11;
     }
-    // ---- G. w = W q, beta = W^T w, K_u beta = (q - c beta) / R ------------------------------------------
-    for (int r = lane; r < U; r += 32) {
-      double acc = wdiag[r] * q[r];
-      for (int k = 0; k < r; ++k) acc = fma(S[k * ld + r], q[k], acc);
-      w[r] = acc;
-    }
-    __syncwarp();
+    // ---- F. beta = M^-1 q (M^-1 symmetric: lower triangle + sdiag), K_u beta = (q - c beta) / R ---------------
     double qkb = 0.0, kbkb = 0.0;
     for (int r = lane; r < U; r += 32) {
-      double acc = wdiag[r] * w[r];
-      const double* uj = S + r * ld;
-      for (int i = r + 1; i < U; ++i) acc = fma(uj[i], w[i], acc);
+      double acc = sdiag[r] * q[r];
+      const double* rowr = S + r * ld;
+      for (int cc = 0; cc < r; ++cc) acc = fma(rowr[cc], q[cc], acc);
+      for (int cc = r + 1; cc < U; ++cc) acc = fma(S[cc * ld + r], q[cc], acc);
       beta[r] = acc;
       const double kbv = (q[r] - c * acc) / dR;
       kb[r] = kbv;
@@ -371,32 +493,12 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     const double quad = (zz - qkb) / c;
     const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
     __syncwarp();
-    // ---- H. M^-1 = W^T W into the lower triangle (+ sdiag), every entry independent --------------------
-    // Two sweeps: first all entries into registers-free order is impossible (L is dead but the lower triangle is
-    // the destination while the upper triangle is the source), so entries are written in place: entry (r, c)
-    // reads only the upper triangle and wdiag.
-    for (int p = lane; p < npairs; p += 32) {
-      int r, cc;
-      wpair_decode(p, r, cc);
-      const double* ur = S + r * ld;
-      const double* uc = S + cc * ld;
-      double s0 = wdiag[r] * ((r == cc) ? wdiag[r] : uc[r]);
-      double s1 = 0.0;
-      int k = r + 1;
-      for (; k + 2 <= U; k += 2) { s0 = fma(ur[k], uc[k], s0); s1 = fma(ur[k + 1], uc[k + 1], s1); }
-      if (k < U) s0 = fma(ur[k], uc[k], s0);
-      const double v = s0 + s1;
-      if (r == cc) sdiag[r] = v;
-      else S[r * ld + cc] = v;
-    }
-    __syncwarp();
     // ---- I. fused derivative contraction over the lower triangle of the unique pairs --------------------
     double dl_part = 0.0;
     for (int r = lane; r < U; r += 32) dsum[r] = 0.0;
     __syncwarp();
     for (int p = lane; p < npairs; p += 32) {
-      int r, cc;
-      wpair_decode(p, r, cc);
+      const int r = pairs[p] >> 8, cc = pairs[p] & 255;
       const double minv = (r == cc) ? sdiag[r] : S[r * ld + cc];
       const double wgt = ((r == cc) ? 0.5 : 1.0) * (dR * minv - beta[r] * beta[cc]);
       const LfmPoint pi = pts[r], pj = pts[cc];
@@ -514,7 +616,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
 int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) {
   const int P = 3 * a.G + 2;
   const int MU = a.max_unique;
-  if (time_grid <= 0 || MU <= 0 || MU > 64 || a.N > 128 || P > 64) return LFM_ERR_UNSUPPORTED;
+  if (time_grid <= 0 || MU <= 0 || MU > 32 + WEX || a.N > 128 || P > 64) return LFM_ERR_UNSUPPORTED;
   if ((long long)a.G * time_grid * time_grid > 2048 || a.G > 127) return LFM_ERR_UNSUPPORTED;
   const WarpLayout L = warp_layout(a.N, a.G, MU, time_grid);
   if (L.bytes > 100 * 1024) return LFM_ERR_UNSUPPORTED;
