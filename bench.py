@@ -33,6 +33,10 @@ G_C3, T_C3 = 256, 128        # config 3: N = 32768
 JITTER = 1e-4
 METRIC = "LFM NLML+grad evals/sec (fp64), N=4000 (50 genes x 80 time points)"
 UNIT = "evals/s"
+CONFIG = {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad at the reference's "
+                      "initial hyper-parameters", "N": 4000, "G": G_C2, "T": T_C2,
+          "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
+          "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2"}
 
 
 # synthetic inputs built here so that the product arm never imports oracle/
@@ -109,8 +113,7 @@ def run_reference(args):
             "steps": args.steps, "steps_executed": steps_exec, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / steps_exec, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad", "N": 4000,
-                       "G": G_C2, "T": T_C2},
+            "config": CONFIG,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{steps_exec} full NLML+grad evaluations at N=4000 (oracle/lfm_oracle.py, "
                                        "numpy+scipy+LAPACK, row chunks over all host threads)"},
@@ -363,10 +366,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad at the "
-                                       "reference's initial hyper-parameters", "N": N, "G": G_C2, "T": T_C2,
-                           "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
-                           "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2"},
+                "config": CONFIG,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int((4 * N + P) * 8),
                         "d2h_bytes_per_step": int((1 + P) * 8 + 4), "ms_per_step": 1e3 * e2e_s / args.steps,
                         "api": "lfm_nlml_grad_host (C-ABI, host buffers)"},

@@ -449,8 +449,8 @@ static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ld
 //   chain: wait bulk(k-1) before the panel of step k reads A(k+1, k)
 // Fork/join is by events only (no host synchronisation; legal under stream capture).
 struct LookAhead {
-  cudaStream_t chain = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t chain = nullptr, tri = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr;
   cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
   bool ok = false;
   bool init() {
@@ -458,7 +458,8 @@ struct LookAhead {
     int lo = 0, hi = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return false;
     if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
-    cudaEvent_t* all[] = {&fork, &join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1], &bulk_done[0],
+    if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
+    cudaEvent_t* all[] = {&fork, &join, &tri_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1], &bulk_done[0],
                           &bulk_done[1]};
     for (cudaEvent_t* e : all)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
@@ -489,16 +490,37 @@ static int potrf_right_looking_serial(cudaStream_t st, int64_t n, double* A, int
   return LFM_OK;
 }
 
+// With `with_trtri` (n / 128 a power of two, lda == ldw) the triangular inverse W = L^-1 is built DURING the
+// factorisation on a third, low-priority stream: the node of the trtri recursion tree that covers blocks
+// [o, o + 2 m) needs  T = W11^T-product with L21  as soon as its left half is inverted and the panels of its
+// columns are final, and  W21 = -W22 T  as soon as its right half is inverted; in the second half of the
+// factorisation, where the dependent chain leaves most SMs idle, these products are free.
 static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                               int64_t pivot_base) {
+                               int64_t pivot_base, bool with_trtri = false) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
-  if (!lookahead_mode() || n < 4 * NB || dev < 0 || !g_la_dev[dev].init())
-    return potrf_right_looking_serial(st, n, A, lda, W, ldw, info, pivot_base);
+  if (!lookahead_mode() || n < 4 * NB || dev < 0 || !g_la_dev[dev].init()) {
+    LFM_TRY(potrf_right_looking_serial(st, n, A, lda, W, ldw, info, pivot_base));
+    return with_trtri ? lfm_trtri(st, n, A, lda, W, ldw) : LFM_OK;
+  }
   LookAhead& la = g_la_dev[dev];
   cudaStream_t ch = la.chain;
+  cudaStream_t tr = la.tri;
   LFM_CUDA_OK(cudaEventRecord(la.fork, st));
   LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.fork, 0));
+  if (with_trtri) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.fork, 0));
+  const int64_t nb = n / NB;
+  // one product of the trtri node with half size mb blocks whose first block is ob (see trtri_levels)
+  auto tri_g1 = [&](int64_t ob, int64_t mb) {  // T^T = W11^T L21^T into the strictly upper block of W
+    const int64_t o = ob * NB, m = mb * NB;
+    return lfm_dgemm(tr, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
+                            1.0, 0.0, 0, LFM_K_GE_ROW));
+  };
+  auto tri_g2 = [&](int64_t ob, int64_t mb) {  // W21 = -W22 T
+    const int64_t o = ob * NB, m = mb * NB;
+    return lfm_dgemm(tr, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
+                            W + (o + m) * ldw + o, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW));
+  };
   int step = 0;
   bool bulk_used = false;
   for (int64_t k = 0; k < n; k += NB, ++step) {
@@ -507,9 +529,15 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     double* Wkk = W + k * ldw + k;
     LFM_TRY(leaf(ch, Akk, lda, Wkk, ldw, info, pivot_base + k));
     const int64_t m = n - k - NB;
+    LFM_CUDA_OK(cudaEventRecord(la.leaf_done[e], ch));
+    if (with_trtri) {
+      // nodes that END at block `step`: their right half is now inverted (lower levels first)
+      LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.leaf_done[e], 0));
+      for (int64_t mb = 1; 2 * mb <= nb; mb *= 2)
+        if ((step + 1) % (2 * mb) == 0) LFM_TRY(tri_g2(step + 1 - 2 * mb, mb));
+    }
     if (m <= 0) break;
     double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
-    LFM_CUDA_OK(cudaEventRecord(la.leaf_done[e], ch));
     // ---- chain: first 128 rows of the panel, then the next diagonal block
     if (bulk_used) LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.bulk_done[e ^ 1], 0));
     {
@@ -520,8 +548,17 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
       u.tile = 1;
       LFM_TRY(lfm_dgemm(ch, u));
     }
-    if (m <= NB) continue;
     LFM_CUDA_OK(cudaEventRecord(la.p1_done[e], ch));
+    // nodes whose LEFT half ends at block `step`: W11 is complete and, once this step's panel is final, so is L21
+    auto tri_front = [&](bool wait_bulk) -> int {
+      if (!with_trtri) return LFM_OK;
+      LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.p1_done[e], 0));
+      if (wait_bulk) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.bulk_done[e], 0));
+      for (int64_t mb = 1; 2 * mb <= nb; mb *= 2)
+        if ((step + 1) % (2 * mb) == mb) LFM_TRY(tri_g1(step + 1 - mb, mb));
+      return LFM_OK;
+    };
+    if (m <= NB) { LFM_TRY(tri_front(false)); continue; }
     // ---- bulk (caller's stream)
     double* P2 = P + NB * lda;  // rows >= k+2 of the panel, (m - 128) x 128
     const int64_t m2 = m - NB;
@@ -537,10 +574,15 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     }
     LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], st));
     bulk_used = true;
+    LFM_TRY(tri_front(true));
   }
-  // join: everything after the factorisation is ordered behind the chain
+  // join: everything after the factorisation is ordered behind the chain (and the inverse)
   LFM_CUDA_OK(cudaEventRecord(la.join, ch));
   LFM_CUDA_OK(cudaStreamWaitEvent(st, la.join, 0));
+  if (with_trtri) {
+    LFM_CUDA_OK(cudaEventRecord(la.tri_join, tr));
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.tri_join, 0));
+  }
   return LFM_OK;
 }
 
@@ -564,6 +606,21 @@ static int potrf_rec(cudaStream_t st, int64_t n, double* A, int64_t lda, double*
   LFM_TRY(trsm_rec(st, n2, n1, A21, lda, A, lda, W, ldw));
   LFM_TRY(lfm_dgemm(st, mk(0, 1, n2, n2, n1, A21, lda, A21, lda, A22, lda, -1.0, 1.0, 1, LFM_K_FULL)));
   return potrf_rec(st, n2, A22, lda, W + n1 * ldw + n1, ldw, info, pivot_base + n1);
+}
+
+// Cholesky and W = L^-1 together: for a single right-looking sweep (n <= threshold, power-of-two block count)
+// the inverse is interleaved with the factorisation, otherwise the two run back to back.
+int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {
+  if (n <= 0 || n % NB) return LFM_ERR_INVALID;
+  const int64_t nblk = n / NB;
+  static int fuse = -1;
+  if (fuse < 0) { const char* e = getenv("LFM_FUSE_TRTRI"); fuse = e ? atoi(e) : 1; }
+  if (fuse && nblk >= 4 && (nblk & (nblk - 1)) == 0 && lda == ldw && n <= rl_threshold()) {
+    LFM_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
+    return potrf_right_looking(st, n, A, lda, W, ldw, info, 0, true);
+  }
+  LFM_TRY(lfm_potrf(st, n, A, lda, W, ldw, info));
+  return lfm_trtri(st, n, A, lda, W, ldw);
 }
 
 int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {

@@ -149,7 +149,7 @@ int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const doubl
 #define GC_TILES 16
 
 template <bool TAB>
-__global__ void __launch_bounds__(256) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
+__global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
                                                               const double* __restrict__ theta,
                                                               const double* __restrict__ Sinv, int64_t ld,
                                                               const double* __restrict__ alpha,

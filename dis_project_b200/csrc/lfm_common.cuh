@@ -79,6 +79,8 @@ int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
 // (and, through the recursion, nothing else) into W's diagonal blocks.  info (device int) receives
 // 0 or the 1-based failing pivot.
 int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info);
+// lfm_potrf followed by lfm_trtri, interleaved on three streams when the matrix is a single right-looking sweep.
+int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info);
 // W = L^-1 (lower) given L and the inverse diagonal blocks already in W's diagonal.
 int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw);
 // S(lower) = W^T W, out of place.

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) lfm_trmv_lower_kernel(int64_t n, const do
 }
 
 // partial[chunk][j] = sum_{i in chunk, i >= j} W[i][j] w[i]; 128 columns per CTA, 512 rows per chunk.
-#define TC_ROWS 512
+#define TC_ROWS 128
 __global__ void __launch_bounds__(128) lfm_trmv_lowerT_kernel(int64_t n, const double* __restrict__ W, int64_t ldw,
                                                             const double* __restrict__ w,
                                                             double* __restrict__ partial) {
@@ -261,7 +261,8 @@ static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const
   LFM_TRY(lfm_launch_residual(st, N, s.Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_grid_build(st, N, G, X, theta, s.Tu, grad, s.grid, grid));
   LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, nullptr, jitter, 1, s.A, s.Np, grid));
-  return lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
+  // the gradient needs W = L^-1 as well: built together with the factorisation
+  return grad ? lfm_potrf_trtri(st, s.Np, s.A, s.Np, s.W, s.Np, info) : lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
 }
 
 extern "C" int lfm_nlml_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
@@ -288,7 +289,6 @@ static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, co
   const int P = 3 * G + 2;
   LfmGrid grid;
   LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, true, &grid, info));
-  LFM_TRY(lfm_trtri(st, s.Np, s.A, s.Np, s.W, s.Np));
   LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
   LFM_LAUNCHED(1);
@@ -386,10 +386,11 @@ extern "C" int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, 
                                      int* info) {
   if (n <= 0 || n % LFM_NB || !A || !W || !info) return LFM_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
-  LFM_TRY(lfm_potrf(st, n, A, n, W, n, info));
   if (Sinv) {
-    LFM_TRY(lfm_trtri(st, n, A, n, W, n));
+    LFM_TRY(lfm_potrf_trtri(st, n, A, n, W, n, info));
     LFM_TRY(lfm_lauum(st, n, W, n, Sinv, n));
+  } else {
+    LFM_TRY(lfm_potrf(st, n, A, n, W, n, info));
   }
   return LFM_OK;
 }

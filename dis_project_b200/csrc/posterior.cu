@@ -126,8 +126,7 @@ extern "C" int lfm_latent_posterior(lfm_stream_t stream, int64_t N, int G, const
   // factorisation of Sigma_p and alpha
   LFM_TRY(lfm_launch_residual(st, N, Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_launch_sigma_lower(st, N, Np, X, G, theta, variances, jitter, 0, s.A, Np));
-  LFM_TRY(lfm_potrf(st, Np, s.A, Np, s.W, Np, info));
-  LFM_TRY(lfm_trtri(st, Np, s.A, Np, s.W, Np));
+  LFM_TRY(lfm_potrf_trtri(st, Np, s.A, Np, s.W, Np, info));
   LFM_TRY(lfm_launch_alpha(st, Np, s.W, s.z, s.w, s.part, s.alpha));
   // stream the test inputs
   const int nrch = (int)((Np + PR_ROWS - 1) / PR_ROWS);
@@ -253,8 +252,7 @@ extern "C" int lfm_gene_posterior(lfm_stream_t stream, int64_t N, int G, const d
   const int64_t Np = s.Np, Tp = s.Tp;
   LFM_TRY(lfm_launch_residual(st, N, Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_launch_sigma_lower(st, N, Np, X, G, theta, variances, 0.0, 1, s.A, Np));
-  LFM_TRY(lfm_potrf(st, Np, s.A, Np, s.W, Np, info));
-  LFM_TRY(lfm_trtri(st, Np, s.A, Np, s.W, Np));
+  LFM_TRY(lfm_potrf_trtri(st, Np, s.A, Np, s.W, Np, info));
   LFM_TRY(lfm_launch_alpha(st, Np, s.W, s.z, s.w, s.part, s.alpha));
   LFM_CUDA_OK(cudaMemsetAsync(s.Kxt, 0, sizeof(double) * (size_t)Np * Tp, st));
   LFM_TRY(lfm_launch_cross_cov(st, N, Tstar, X, Xstar, G, theta, s.Kxt, Tp));
