@@ -141,6 +141,32 @@ def test_dense_factor_inverse(cuda):
     assert relerr(Cm, A @ B.T) < 1e-14
 
 
+@pytest.mark.parametrize("n", [512, 1024, 1536, 2048, 4096, 4608, 8192])
+def test_dense_driver_paths(cuda, n):
+    """Every driver of the blocked factorisation / inverse: look-ahead right-looking sweep with the triangular
+    inverse interleaved (power-of-two block counts up to 4096), the same sweep followed by the recursive inverse
+    (1536, 4608 blocks are not a power of two), and the recursive factorisation above 4096 -- against cuSOLVER /
+    cuBLAS through torch on the same device, and L L^T = S, S^-1 S = I on probe vectors."""
+    from dis_project_b200 import ops
+    g = torch.Generator(device="cuda")
+    g.manual_seed(n)
+    A = torch.randn(n, 192, dtype=torch.float64, device="cuda", generator=g)
+    S = A @ A.T
+    S.diagonal().add_(torch.linspace(1.0, 3.0, n, dtype=torch.float64, device="cuda"))
+    Lref = torch.linalg.cholesky(S)
+    probe = torch.randn(n, 3, dtype=torch.float64, device="cuda", generator=g)
+    Sp = S @ probe
+    L, Sinv, info = ops.debug_potrf_potri(S.clone())
+    assert int(info.item()) == 0
+    Lt = torch.tril(L)
+    assert float((Lt - Lref).abs().max() / Lref.abs().max()) < 1e-12
+    Si = torch.tril(Sinv) + torch.tril(Sinv, -1).T
+    assert float((Si @ Sp - probe).abs().max() / probe.abs().max()) < 1e-10
+    L2, none, info2 = ops.debug_potrf_potri(S.clone(), want_inverse=False)   # factorisation alone (value-only path)
+    assert none is None and int(info2.item()) == 0
+    assert torch.equal(torch.tril(L2), Lt)                                     # same arithmetic with / without the inverse
+
+
 @pytest.mark.parametrize("G,T,R", [(5, 7, 1), (5, 7, 3), (4, 32, 1)])
 def test_batched_eval(cuda, G, T, R):
     from dis_project_b200 import ops
