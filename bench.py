@@ -146,9 +146,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: ONE JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries ONE JSON line: NCCL prints its version banner to stdout while the communicator comes
+        # up (whenever NCCL_DEBUG >= VERSION), so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     from dis_project_b200 import _lib, ops
     from dis_project_b200.batched import make_restarts, multi_start_fit
     from dis_project_b200.dataset import JaxP53Data, dataset_3d

@@ -440,6 +440,127 @@ static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ld
   return trsm_rec(st, m, n2, B + n1, ldb, L + n1 * ldl + n1, ldl, Wd + n1 * ldw + n1, ldw);
 }
 
+// ---- chain step: L(k+1,k) = A(k+1,k) W_kk^T and A(k+1,k+1) -= L(k+1,k) L(k+1,k)^T in ONE launch -----------------
+// A cluster of 8 CTAs owns the 128 x 128 block row: CTA r computes rows [16 r, 16 r + 16) of the panel with all
+// of K = 128 resident in shared memory (one cp.async sweep in four k-quarters, no multi-stage refill), writes
+// them back in place, the cluster synchronises (release / acquire at cluster scope, so the rows every CTA wrote
+// are visible through L2), and CTA r then updates its 16 rows of the next diagonal block against the whole
+// panel.  Replaces two 16 x 128-tile GEMM launches on the dependent chain of the factorisation.
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+#define CS_LD 132
+#define CS_SMEM ((16 + NB) * CS_LD * 8)
+__global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1)
+    lfm_chain_step_kernel(double* __restrict__ P, int64_t ld, const double* __restrict__ Wkk, int64_t ldw,
+                          double* __restrict__ Cd) {
+  extern __shared__ __align__(16) double cs[];
+  double* sA = cs;                 // [16][CS_LD]
+  double* sB = cs + 16 * CS_LD;    // [128][CS_LD], stored [n][k]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int r0 = 16 * rank;
+  auto load_quarters = [&](const double* Bsrc, int64_t ldb, bool with_a) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (with_a) {
+        // A rows: 16 x 32 doubles of this quarter = 256 chunks of 16 bytes
+        const int r = tid >> 4, c = q * 32 + (tid & 15) * 2;
+        leaf_cp16(sA + r * CS_LD + c, P + (int64_t)(r0 + r) * ld + c);
+      }
+      // B: 128 x 32 doubles of this quarter = 2048 chunks
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int id = tid + 256 * i;
+        const int r = id >> 4, c = q * 32 + (id & 15) * 2;
+        leaf_cp16(sB + r * CS_LD + c, Bsrc + (int64_t)r * ldb + c);
+      }
+      asm volatile("cp.async.commit_group;\n" ::);
+    }
+  };
+  // one warp: rows [0,16) x columns [16 warp, 16 warp + 16); acc (+)= sgn * sA sB^T over the resident K = 128
+  auto sweep = [&](double (&acc)[2][2][2], double sgn) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (q == 0) asm volatile("cp.async.wait_group 3;\n" ::);
+      else if (q == 1) asm volatile("cp.async.wait_group 2;\n" ::);
+      else if (q == 2) asm volatile("cp.async.wait_group 1;\n" ::);
+      else asm volatile("cp.async.wait_group 0;\n" ::);
+      __syncthreads();
+#pragma unroll
+      for (int k4 = q * 32; k4 < q * 32 + 32; k4 += 4) {
+        const double a0 = sgn * sA[fr * CS_LD + k4 + fc];
+        const double a1 = sgn * sA[(8 + fr) * CS_LD + k4 + fc];
+        const double b0 = sB[(16 * warp + fr) * CS_LD + k4 + fc];
+        const double b1 = sB[(16 * warp + 8 + fr) * CS_LD + k4 + fc];
+        leaf_dmma(acc[0][0][0], acc[0][0][1], a0, b0);
+        leaf_dmma(acc[0][1][0], acc[0][1][1], a0, b1);
+        leaf_dmma(acc[1][0][0], acc[1][0][1], a1, b0);
+        leaf_dmma(acc[1][1][0], acc[1][1][1], a1, b1);
+      }
+    }
+  };
+  // ---- phase 1: panel rows
+  load_quarters(Wkk, ldw, true);
+  double acc[2][2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+  sweep(acc, 1.0);
+  __syncthreads();  // every warp is done reading sA / sB
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 8 * i + fr, c = 16 * warp + 8 * j + 2 * fc;
+      const double2 v = make_double2(acc[i][j][0], acc[i][j][1]);
+      *reinterpret_cast<double2*>(P + (int64_t)(r0 + r) * ld + c) = v;   // L(k+1,k) rows, in place
+      *reinterpret_cast<double2*>(sA + r * CS_LD + c) = v;               // and as the A operand of phase 2
+    }
+  __threadfence();
+  cluster.sync();
+  // ---- phase 2: rows of the next diagonal block (lower part only: columns <= last row of this CTA)
+  load_quarters(P, ld, false);
+  const bool live = 16 * warp <= r0 + 15;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int r = 8 * i + fr, c = 16 * warp + 8 * j + 2 * fc;
+      double2 v = make_double2(0.0, 0.0);
+      if (live) v = *reinterpret_cast<const double2*>(Cd + (int64_t)(r0 + r) * ld + c);
+      acc[i][j][0] = v.x; acc[i][j][1] = v.y;
+    }
+  sweep(acc, -1.0);
+  if (live) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = 8 * i + fr, c = 16 * warp + 8 * j + 2 * fc;
+        *reinterpret_cast<double2*>(Cd + (int64_t)(r0 + r) * ld + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+      }
+  }
+}
+static int chain_step(cudaStream_t st, double* P, int64_t ld, const double* Wkk, int64_t ldw, double* Cd) {
+  static bool configured = false;
+  if (!configured) {
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
+    configured = true;
+  }
+  lfm_chain_step_kernel<<<8, 256, CS_SMEM, st>>>(P, ld, Wkk, ldw, Cd);
+  LFM_LAUNCHED(1);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
+static int chain_fused_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LFM_CHAIN_FUSED"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 // Right-looking blocked Cholesky with 128-wide panels and one step of look-ahead for small / medium n.
 // The dependent chain  leaf(k) -> L(k+1,k) = A(k+1,k) W_kk^T -> A(k+1,k+1) -= L(k+1,k) L(k+1,k)^T -> leaf(k+1)
 // runs on an internal HIGH-PRIORITY stream (its CTAs are placed before pending bulk CTAs whenever an SM
@@ -540,7 +661,9 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
     // ---- chain: first 128 rows of the panel, then the next diagonal block
     if (bulk_used) LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.bulk_done[e ^ 1], 0));
-    {
+    if (chain_fused_mode()) {
+      LFM_TRY(chain_step(ch, P, lda, Wkk, ldw, P + NB));
+    } else {
       LfmGemm g = mk(0, 1, NB, NB, NB, P, lda, Wkk, ldw, P, lda, 1.0, 0.0, 0, LFM_K_FULL);
       g.tile = 1;
       LFM_TRY(lfm_dgemm(ch, g));
