@@ -35,6 +35,7 @@ METRIC = "LFM NLML+grad evals/sec (fp64), N=4000 (50 genes x 80 time points)"
 UNIT = "evals/s"
 CONFIG = {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000), NLML+grad at the reference's "
                       "initial hyper-parameters", "N": 4000, "G": G_C2, "T": T_C2,
+          "launch": "one CUDA-graph replay per evaluation (ops.NlmlGradPlan / lfm_plan_launch); e2e: lfm_nlml_grad_host",
           "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
           "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2"}
 
@@ -185,8 +186,12 @@ def main():
     X, y, th = (torch.as_tensor(a).to(dev) for a in (Xh, yh, thh))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    # the public API for repeated evaluations at fixed (X, y): a CUDA-graph evaluation plan (what JaxTrainer's
+    # objective uses); every step writes theta into the bound buffer and replays ~140 kernel launches
+    plan = ops.NlmlGradPlan(X, y, G_C2, JITTER)
+
     def step():
-        return ops.nlml_grad(X, y, th, JITTER, G_C2)
+        return plan(th)
 
     # ---- FP64 roofline denominator: cuBLAS Dgemm, measured here (MEASURED_PEAKS.json has no FP64 entry) ----
     peak_tf = None
@@ -261,7 +266,7 @@ def main():
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
         for _ in range(args.steps):
-            step()
+            ops.nlml_grad(X, y, th, JITTER, G_C2)   # stream launches: per-launch events cannot be taken inside a graph
         pe1.record()
         ms, fl, nl = C.c_double(0), C.c_double(0), C.c_longlong(0)
         _lib.check(lib.lfm_debug_profile_end(C.byref(ms), C.byref(fl), C.byref(nl)), "profile_end")
@@ -289,9 +294,12 @@ def main():
                 "executed_flops_per_eval": fl.value / args.steps,
                 "launches_per_eval": nl.value / args.steps, "kernel_s_per_eval": gemm_s,
                 "kernel_share_of_step": gemm_s / prof_step_s,
-                "note": "launches on the factorisation's two streams overlap, so summed kernel time can exceed its "
-                        "share of the step's wall time",
-                "chain_tile_launches": {"kernel": "lfm_dgemm_kernel<.,.,1,4,2> (16 x 128 tiles, 8 CTAs per launch)",
+                "kernel_s_per_eval_summed": lib.lfm_debug_profile_sum_ms() * 1e-3 / args.steps,
+                "note": "the factorisation launches on three streams and launches overlap: kernel_s_per_eval is the "
+                        "length of the union of the launch intervals (CUDA-event timestamps), the plain sum is beside it",
+                "chain_tile_launches": {"kernel": "lfm_dgemm_kernel<.,.,1,4,2> (16 x 128 tiles; only with LFM_CHAIN_FUSED=0 -- by "
+                                                  "default the chain step is lfm_chain_step_kernel, one 8-CTA cluster "
+                                                  "launch per 128 columns, outside this accounting)",
                                         "launches_per_eval": cnl.value / args.steps,
                                         "kernel_s_per_eval": cms.value * 1e-3 / args.steps,
                                         "executed_flops_per_eval": cfl.value / args.steps},

@@ -49,6 +49,10 @@ SIGNATURES = {
     "lfm_nlml_grad": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad_unc": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _ptr, _sz, _ptr, _ptr]),
     "lfm_count_distinct_times": (_i64, [_i64, _ptr]),
+    "lfm_nlml_grad_plan_create": (_int, [C.POINTER(C.c_void_p), _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _int, _ptr, _sz,
+                                         _ptr, _ptr]),
+    "lfm_plan_launch": (_int, [_ptr, _ptr]),
+    "lfm_plan_destroy": (_int, [_ptr]),
     "lfm_nlml_workspace_bytes_tg": (_sz, [_i64, _int, _i64]),
     "lfm_nlml_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
@@ -77,6 +81,7 @@ SIGNATURES = {
     "lfm_debug_launch_count": (C.c_ulonglong, []),
     "lfm_debug_profile_begin": (_int, []),
     "lfm_debug_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    "lfm_debug_profile_sum_ms": (C.c_double, []),
     "lfm_debug_profile_chain": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "lfm_debug_dgemm_nt": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "lfm_debug_potrf_potri": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr]),

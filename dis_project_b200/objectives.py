@@ -23,6 +23,8 @@ class CustomConjMLL:
     def __init__(self, negative: bool = False):
         self.negative = bool(negative)
         self.constant = -1.0 if negative else 1.0  # gpjax AbstractObjective.constant
+        self._plan = None       # CUDA-graph evaluation plan of the last (data set, jitter) seen by value_and_grad
+        self._plan_key = None
 
     def __call__(self, model: ExactLFM, train_data: Dataset) -> float:
         return self.step(model, train_data)
@@ -36,8 +38,20 @@ class CustomConjMLL:
     def value_and_grad(self, model_unconstrained: ExactLFM, train_data: Dataset) -> Tuple[float, np.ndarray]:
         """Loss and gradient w.r.t. the UNCONSTRAINED leaves [d, s, b, l, obs_stddev]:
         jax.value_and_grad(lambda m: objective(m.constrain(), data)) (reference trainer.py:86-103,126)."""
-        out, info = ops.nlml_grad_unc(train_data.X, train_data.y, model_unconstrained.pack(),
-                                      model_unconstrained.jitter, model_unconstrained.num_genes)
+        n = train_data.n
+        if n <= 8192:
+            # launch-bound sizes: the evaluation is captured once per data set as a CUDA graph and replayed per step
+            key = (id(train_data), float(model_unconstrained.jitter), model_unconstrained.num_genes)
+            if self._plan_key != key:
+                if self._plan is not None:
+                    self._plan.close()
+                self._plan = ops.NlmlGradPlan(train_data.X, train_data.y, model_unconstrained.num_genes,
+                                              model_unconstrained.jitter, unconstrained=True)
+                self._plan_key = key
+            out, info = self._plan(model_unconstrained.pack())
+        else:
+            out, info = ops.nlml_grad_unc(train_data.X, train_data.y, model_unconstrained.pack(),
+                                          model_unconstrained.jitter, model_unconstrained.num_genes)
         out = out.cpu().numpy()
         s = -self.constant
         return s * float(out[0]), s * out[1:]

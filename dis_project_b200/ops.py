@@ -171,6 +171,63 @@ def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int, time
     return out, info
 
 
+class NlmlGradPlan:
+    """One NLML+grad evaluation over fixed device buffers, captured once as a CUDA graph and replayed per call
+    (include/lfm_b200.h, "evaluation plans").  What a fit loop wants: (X, y) stay, theta changes.
+
+        plan = NlmlGradPlan(X, y, G, jitter)          # or unconstrained=True for trainer.py:126 semantics
+        out, info = plan(theta)                        # out[0] = NLML, out[1:] = gradient; buffers are reused
+
+    `out` / `info` are the plan's own buffers: copy them if they must survive the next call."""
+
+    def __init__(self, X, y, G: int, jitter: float, unconstrained: bool = False, time_grid: Optional[int] = None):
+        import ctypes as C
+
+        if time_grid is None:
+            time_grid = distinct_times(X)
+        self.X = _rows3(X, "x")
+        self.y = _dev(y).reshape(-1)
+        self.G, self.P = int(G), 3 * int(G) + 2
+        N = self.X.shape[0]
+        if self.y.numel() != N:
+            raise ValueError(f"y has {self.y.numel()} values for {N} input rows")
+        if N % G:
+            raise ValueError(f"{N} rows is not divisible by num_genes={G} (model.py:145-149)")
+        dev = self.X.device
+        l = _lib.lib()
+        self.theta = torch.ones(self.P, dtype=F64, device=dev)  # a valid point for the warm-up evaluation
+        if not unconstrained:
+            self.theta[3 * G] = 2.5
+        self.out = torch.empty(self.P + 1, dtype=F64, device=dev)
+        self.info = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ws = torch.empty(int(l.lfm_nlml_workspace_bytes_tg(N, G, int(time_grid))), dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize(dev)
+        self._plan = C.c_void_p()
+        _lib.check(l.lfm_nlml_grad_plan_create(C.byref(self._plan), N, G, self.X.data_ptr(), self.y.data_ptr(),
+                                               self.theta.data_ptr(), float(jitter), int(time_grid),
+                                               int(bool(unconstrained)), self.ws.data_ptr(), self.ws.numel(),
+                                               self.out.data_ptr(), self.info.data_ptr()), "lfm_nlml_grad_plan_create")
+
+    def __call__(self, theta):
+        t = theta if isinstance(theta, torch.Tensor) else torch.as_tensor(theta, dtype=F64)
+        if t.numel() != self.P:
+            raise ValueError(f"theta must hold 3G+2={self.P} values [d,s,b,l,sigma], got {t.numel()}")
+        self.theta.copy_(t.reshape(-1), non_blocking=True)
+        _lib.check(_lib.lib().lfm_plan_launch(self._plan, _stream()), "lfm_plan_launch")
+        return self.out, self.info
+
+    def close(self) -> None:
+        if getattr(self, "_plan", None):
+            _lib.lib().lfm_plan_destroy(self._plan)
+            self._plan = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def nlml(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None):
     """CustomConjMLL(negative=True) value (reference src/objectives.py:21-78).  Returns (val[1], info[1]).
     `time_grid`: bound on the distinct times of X (None: counted from X; 0: evaluate every entry directly)."""

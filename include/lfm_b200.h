@@ -184,6 +184,19 @@ int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const d
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */
 
+/* ---- evaluation plans -------------------------------------------------------------------------
+ * One lfm_nlml_grad[_unc]_tg evaluation over FIXED device buffers, captured once as a CUDA graph (the ~140
+ * launches and ~70 cross-stream event edges of an N = 4000 evaluation replay with ~1 us between dependent
+ * kernels).  A fit loop writes the next theta into the bound `theta` buffer and launches the plan again
+ * (src/trainer.py:201-216 evaluates the same (X, y) at every step).  create runs the evaluation once eagerly
+ * (validation, lazy initialisation) and synchronises; launch is stream-ordered and never synchronises. */
+typedef struct lfm_plan lfm_plan;
+int lfm_nlml_grad_plan_create(lfm_plan** out_plan, int64_t N, int G, const double* X, const double* y,
+                              const double* theta, double jitter, int64_t time_grid, int unconstrained, void* ws,
+                              size_t ws_bytes, double* out, int* info);
+int lfm_plan_launch(lfm_plan* plan, lfm_stream_t stream);
+int lfm_plan_destroy(lfm_plan* plan);
+
 typedef struct lfm_handle lfm_handle;
 int lfm_handle_create(lfm_handle** out);
 int lfm_handle_destroy(lfm_handle* h);
@@ -216,10 +229,12 @@ int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info,
 /* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long lfm_debug_launch_count(void);
 /* Bracket every DMMA GEMM launch with CUDA events on its stream between begin and end; end
- * synchronises the device and reports the summed kernel time, the flops the tiles executed and the
- * number of launches. */
+ * synchronises the device and reports the kernel time, the flops the tiles executed and the number of
+ * launches.  Launches on the factorisation's streams overlap: the time is the length of the UNION of the
+ * launch intervals (lfm_debug_profile_sum_ms gives the plain sum). */
 int lfm_debug_profile_begin(void);
 int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches);
+double lfm_debug_profile_sum_ms(void);
 /* the 16 x 128-tile launches of the factorisation's look-ahead chain, accounted separately (call after _end) */
 int lfm_debug_profile_chain(double* total_ms, double* exec_flops, long long* launches);
 

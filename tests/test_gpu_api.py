@@ -323,3 +323,42 @@ def test_time_grid_irregular_times_use_direct_path(cuda):
     out = out.cpu().numpy()
     assert abs(out[0] - v_ref) <= RTOL * abs(v_ref)
     assert np.max(np.abs(out[1:] - g_ref)) <= RTOL * np.max(np.abs(g_ref))
+
+
+def test_evaluation_plan_replays_the_eager_path(cuda):
+    """CUDA-graph evaluation plans (include/lfm_b200.h): bit-identical to the stream-launched evaluation, at several
+    theta values written into the bound buffer, constrained and unconstrained; also through CustomConjMLL."""
+    from dis_project_b200 import ops
+    for (G, T, R) in ((5, 7, 3), (12, 50, 1)):
+        x, y, var, _ = o.synthetic_problem(G, T, R, seed=51)
+        rng = np.random.default_rng(52)
+        plan = ops.NlmlGradPlan(x, y, G, 1e-4)
+        plan_u = ops.NlmlGradPlan(x, y, G, 1e-4, unconstrained=True)
+        for _ in range(3):
+            p = o.Params(d=rng.uniform(0.2, 1.0, G), s=rng.uniform(0.5, 1.5, G), b=rng.uniform(0.01, 0.1, G),
+                         l=float(rng.uniform(0.8, 3.2)), sigma=float(rng.uniform(0.6, 1.4)), jitter=1e-4)
+            out, info = plan(p.pack())
+            ref, _ = ops.nlml_grad(x, y, p.pack(), 1e-4, G)
+            assert int(info.item()) == 0 and torch.equal(out, ref)
+            v_ref, g_ref = o.nlml_and_grad(p, x, y)
+            assert abs(out[0].item() - v_ref) <= RTOL * abs(v_ref)
+            u = o.unconstrain(p.pack())
+            out_u, _ = plan_u(u)
+            ref_u, _ = ops.nlml_grad_unc(x, y, u, 1e-4, G)
+            assert torch.equal(out_u, ref_u)
+        plan.close(); plan_u.close()
+    # the trainer's eager loop (N > 128) goes through the plan held by the objective
+    from dis_project_b200 import gpx_compat as gpx
+    from dis_project_b200.model import ExactLFM
+    from dis_project_b200.objectives import CustomConjMLL
+    from dis_project_b200.trainer import JaxTrainer
+    from dis_project_b200.dataset import JaxP53Data
+    G, T = 6, 30
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=53)
+    data = gpx.Dataset(x, y.reshape(-1, 1))
+    model = ExactLFM(jitter=1e-4, num_genes=G)
+    tr = JaxTrainer(model, CustomConjMLL(negative=True), data, gpx.adam(0.01), None, 5)
+    assert not tr._device_scan_ok()     # N = 180 > 128: the host loop with one plan replay per step
+    m2, hist = tr.fit()
+    _, h_ref = o.fit(model.pack(), x, y, 1e-4, num_iters=5)
+    assert relerr(hist, h_ref) < 1e-9
