@@ -36,6 +36,9 @@ def make_restarts(theta_init: np.ndarray, B: int, scale: float = 0.5, seed: int 
     return TH
 
 
+LAST_TIMING = None
+
+
 def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous restart range [lo, hi) of `rank`; sizes differ by at most one."""
     base, rem = divmod(B, world)
@@ -105,6 +108,16 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
 
     from . import ops
 
+    import os
+    import time
+    timing = os.environ.get("LFM_MSF_TIMING") == "1"   # debug: synchronising phase timers (tools/batched_probe3.py)
+    tmarks = [time.perf_counter()]
+
+    def mark():
+        if timing:
+            torch.cuda.synchronize()
+            tmarks.append(time.perf_counter())
+
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank() if distributed else 0
     world = dist.get_world_size() if distributed else 1
@@ -122,27 +135,24 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     side = torch.cuda.Stream()
     ids = torch.arange(lo, hi, dtype=torch.float64, device=Xd.device)
     nchunks = (num_iters + chunk - 1) // chunk
-    trace = torch.full((max(nchunks, 1), 2), float("inf"), dtype=torch.float64, device=Xd.device)
+    # per chunk ONE device word: the fit kernel atomic-mins the order-preserving integer image of every loss into
+    # it, the side stream MIN-all-reduces it across ranks -- no extra kernels, nothing the fit ever waits for
+    keys = torch.full((max(nchunks, 1),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=Xd.device)
     done = 0
+    mark()
     for c in range(nchunks):
         steps = min(chunk, num_iters - done)
         if st is not None:
             ops.batched_fit_steps(st, Xd, yd, jitter, steps, lr=lr, b1=b1, b2=b2, eps=eps, fix_params=fix_params,
-                                  steps_per_epoch=num_steps_per_epoch)
+                                  steps_per_epoch=num_steps_per_epoch, best_key=keys[c:c + 1])
         done += steps
-        ev = torch.cuda.Event()
-        ev.record(main)
-        with torch.cuda.stream(side):
-            side.wait_event(ev)
-            if st is not None:
-                col = st.hist[:, done - 1]
-                col = torch.where(torch.isfinite(col), col, torch.full_like(col, float("inf")))
-                k = torch.argmin(col)
-                trace[c, 0] = col[k]
-                trace[c, 1] = ids[k]
-            if distributed and world > 1:
-                # MIN over the loss; the id is resolved after the loop (one more tiny all-reduce)
-                dist.all_reduce(trace[c, 0:1], op=dist.ReduceOp.MIN)
+        if distributed and world > 1:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                dist.all_reduce(keys[c:c + 1], op=dist.ReduceOp.MIN)
+    mark()
     main.wait_stream(side)
     # ---- global winner: ONE all-gather of [loss, id, theta(P)] per rank, ONE device->host copy --------------
     packed = torch.full((P + 2,), float("inf"), dtype=torch.float64, device=Xd.device)
@@ -175,5 +185,9 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
         theta, hist, info = st.theta.cpu().numpy(), st.hist.cpu().numpy(), st.info.cpu().numpy()
     else:
         theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
+    mark()
+    if timing:
+        global LAST_TIMING
+        LAST_TIMING = [round(1e3 * (b - a), 3) for a, b in zip(tmarks[:-1], tmarks[1:])]
     return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
-                            trace[:, 0].cpu().numpy())
+                            ops.loss_key_to_float(keys.cpu().numpy()))

@@ -383,6 +383,10 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
     if (a.first_step == 0 || eval_only) a.info[bidx] = fail;
     else if (fail) a.info[bidx] = fail;
   }
+  if (tid == 0 && a.best_key && !eval_only && a.hist && a.steps > 0) {
+    const double v = a.hist[bidx * a.ld_hist + a.first_step + a.steps - 1];
+    if (v == v) atomicMin(a.best_key, lfm_loss_key(v));
+  }
 }
 
 static size_t batched_smem_bytes(int N, int G, int MU) {
@@ -450,7 +454,7 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
                                   double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                                   double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
                                   int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
-                                  int64_t ld_hist, double* out_theta, int* info) {
+                                  int64_t ld_hist, double* out_theta, int* info, long long* best_key) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
@@ -460,7 +464,7 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
   a.jitter = jitter; a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
-  a.info = info; a.max_unique = unique_rows_hint;
+  a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key;
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
@@ -470,7 +474,7 @@ extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G,
                                double* out_theta, int* info) {
   return lfm_batched_fit_tg(stream, B, N, G, X, y, theta_unc_io, adam_state, jitter, lr, b1, b2, eps, first_step, steps,
                             total_steps, fix_params, steps_per_epoch, unique_rows_hint, 0, out_hist, ld_hist, out_theta,
-                            info);
+                            info, nullptr);
 }
 
 // Number of distinct (time, gene, flag) rows of a HOST copy of X: the `unique_rows_hint` that lets the

@@ -1,5 +1,6 @@
 // Arguments shared by the two batched kernels (batched.cu: one CTA per LFM; batched_warp.cu: one warp per LFM).
 #pragma once
+#include <cstring>
 #include "sim_math.cuh"
 
 struct BatchedArgs {
@@ -16,8 +17,21 @@ struct BatchedArgs {
   double* eval_val;   // eval-only mode: B
   double* eval_grad;  // eval-only mode: B x P
   int* info;
-  int max_unique;     // shared-memory matrix is sized for this many unique rows (N when unknown)
+  int max_unique;
+  long long* best_key; // NULL or one device word: atomicMin of lfm_loss_key(loss after the launch's last step) over the batch     // shared-memory matrix is sized for this many unique rows (N when unknown)
 };
+
+// Order-preserving map double -> signed 64-bit integer (finite values and infinities; NaN never enters): the
+// best objective of a chunk is one atomicMin per LFM and one integer MIN all-reduce across ranks.
+__host__ __device__ inline long long lfm_loss_key(double v) {
+  long long i;
+#ifdef __CUDA_ARCH__
+  i = __double_as_longlong(v);
+#else
+  memcpy(&i, &v, sizeof(i));
+#endif
+  return i >= 0 ? i : (i ^ 0x7fffffffffffffffLL);
+}
 
 // batched_warp.cu: launches the warp-per-LFM kernel when the problem fits its limits, else LFM_ERR_UNSUPPORTED
 int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid);

@@ -609,6 +609,10 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     if (a.first_step == 0 || eval_only) a.info[bidx] = fail;
     else if (fail) a.info[bidx] = fail;
   }
+  if (lane == 0 && a.best_key && !eval_only && a.hist && a.steps > 0) {
+    const double v = a.hist[bidx * a.ld_hist + a.first_step + a.steps - 1];
+    if (v == v) atomicMin(a.best_key, lfm_loss_key(v));
+  }
 }
 
 // Launch the warp-per-LFM kernel if the problem fits its limits; returns LFM_ERR_UNSUPPORTED otherwise

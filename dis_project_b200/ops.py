@@ -349,9 +349,20 @@ class BatchedFitState:
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
 
 
+def loss_key_to_float(keys):
+    """Inverse of the order-preserving double -> int64 map of include/lfm_b200.h (best_key); INT64_MAX -> inf."""
+    import numpy as np
+
+    k = np.asarray(keys, dtype=np.int64)
+    bits = np.where(k >= 0, k, k ^ np.int64(0x7FFFFFFFFFFFFFFF))
+    out = bits.view(np.float64).copy()
+    out[k == np.iinfo(np.int64).max] = np.inf
+    return out
+
+
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
                       b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
-                      steps_per_epoch: int = 1000) -> None:
+                      steps_per_epoch: int = 1000, best_key: Optional[torch.Tensor] = None) -> None:
     """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
@@ -367,7 +378,9 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
                                              state.step, steps, state.total_steps, int(bool(fix_params)),
                                              int(steps_per_epoch), state.unique_hint, int(state.time_grid),
                                              state.hist.data_ptr(), state.hist.shape[1],
-                                             state.theta.data_ptr(), state.info.data_ptr()), "lfm_batched_fit_tg")
+                                             state.theta.data_ptr(), state.info.data_ptr(),
+                                             best_key.data_ptr() if best_key is not None else None),
+               "lfm_batched_fit_tg")
     state.step += steps
 
 

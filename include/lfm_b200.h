@@ -179,7 +179,12 @@ int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const d
                        double* theta_unc_io, double* adam_state, double jitter, double lr, double b1, double b2,
                        double eps, int first_step, int steps, int total_steps, int fix_params,
                        int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
-                       int64_t ld_hist, double* out_theta, int* info);
+                       int64_t ld_hist, double* out_theta, int* info, long long* best_key);
+/* best_key (may be NULL): one device word that receives atomicMin over the batch of the order-preserving integer
+ * image of each LFM's loss after the last step of this call (finite losses only; initialise it to INT64_MAX).
+ * key(v) = bits(v) for v >= 0, bits(v) ^ 0x7fff...f otherwise -- monotone in v, so the global best objective of a
+ * chunk of steps is ONE integer MIN all-reduce of that word across ranks (north_star: "one NCCL allreduce of
+ * best-objective ... state per step"). */
 
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */

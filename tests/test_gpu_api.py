@@ -153,6 +153,7 @@ def test_multi_start_single_rank(cuda):
     t_ref, h_ref = o.fit(TH[5], x, y, 1e-4, num_iters=40)
     assert relerr(res.history[5], h_ref) < 1e-9
     assert np.all(np.diff(res.best_trace) <= 1e-9)  # best objective after each chunk never increases much
+    assert res.best_trace[-1] == res.best_loss      # the atomicMin key of the last chunk IS the winner's loss, bit for bit
 
 
 def test_config2_full_size_parity(cuda):

@@ -208,3 +208,15 @@ def test_count_distinct_times():
     assert lib.lfm_count_distinct_times(0, None) == 0
     assert lib.lfm_nlml_workspace_bytes_tg(4000, 50, 80) > lib.lfm_nlml_workspace_bytes(4000, 50)
     assert lib.lfm_nlml_workspace_bytes_tg(120, 4, 120) == lib.lfm_nlml_workspace_bytes(120, 4)  # tables not worthwhile
+
+
+def test_loss_key_is_order_preserving():
+    """include/lfm_b200.h best_key: double -> int64 map used for the atomicMin / MIN all-reduce of the best objective."""
+    from dis_project_b200.ops import loss_key_to_float
+    v = np.array([-np.inf, -1e300, -104.74, -1.0, -1e-300, -0.0, 0.0, 1e-300, 3.5, 1e300, np.inf])
+    bits = v.view(np.int64)
+    keys = np.where(bits >= 0, bits, bits ^ np.int64(0x7FFFFFFFFFFFFFFF))
+    assert np.all(np.diff(keys) >= 0) and np.all(np.diff(keys)[[0, 1, 2, 3, 6, 7, 8, 9]] > 0)
+    back = loss_key_to_float(keys)
+    assert np.array_equal(back, v)
+    assert loss_key_to_float(np.array([np.iinfo(np.int64).max]))[0] == np.inf
