@@ -195,3 +195,94 @@ def test_oracle_reproduces_golden(path):
     assert np.allclose(m, g["posterior_mean"], rtol=1e-10, atol=1e-12)
     assert np.allclose(pv, g["posterior_var"], rtol=1e-10, atol=1e-12)
     assert G == p.num_genes
+
+
+# ---- whole-path anchor in 50-digit arithmetic (independent of numpy / LAPACK) ------------------------------------
+def _mp_nlml(theta, x, y, jitter, G):
+    """objectives.py:64-78 over model.py:124-149,197-235 literally: mean, Sigma = K + (jitter + sigma^2) I, mpmath
+    Cholesky, -log N(y; mu, Sigma)."""
+    th = [mp.mpf(v) for v in theta]
+    d, s, b, l, sigma = th[:G], th[G:2 * G], th[2 * G:3 * G], th[3 * G], th[3 * G + 1]
+
+    class P:  # the attributes mp_kxx reads
+        pass
+    P.d, P.s, P.l = d, s, l
+    N = x.shape[0]
+    block = N // G
+    mu = [b[min(i // block, G - 1)] / d[min(i // block, G - 1)] * int(x[i, 2]) for i in range(N)]
+    K = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(i + 1):
+            v = mp_kxx_mp(P, mp.mpf(float(x[i, 0])), int(x[i, 1]), mp.mpf(float(x[j, 0])), int(x[j, 1]))
+            K[i, j] = v
+            K[j, i] = v
+        K[i, i] += mp.mpf(jitter) + sigma**2
+    L = mp.cholesky(K)
+    z = mp.matrix([mp.mpf(float(y[i])) - mu[i] for i in range(N)])
+    w = mp.lu_solve(L, z)  # exact triangular solve at 50 digits
+    logdet = 2 * sum(mp.log(L[i, i]) for i in range(N))
+    return (N * mp.log(2 * mp.pi) + logdet + sum(w[i] ** 2 for i in range(N))) / 2
+
+
+def mp_h_mp(d, l, j, k, t1, t2):
+    t_dist = t2 - t1
+    gk = d[k] * l / 2
+    multiplier = mp.e ** (gk**2) / (d[j] + d[k])
+    first = mp.e ** (-d[k] * t_dist) * (mp.erf(t_dist / l - gk) + mp.erf(t1 / l + gk))
+    second = mp.e ** (-(d[k] * t2 + d[j] * t1)) * (mp.erf(t2 / l - gk) + mp.erf(gk))
+    return multiplier * (first - second)
+
+
+def mp_kxx_mp(P, t, j, tp, k):
+    mult = P.s[j] * P.s[k] * P.l * mp.sqrt(mp.pi) / 2
+    return mult * (mp_h_mp(P.d, P.l, k, j, tp, t) + mp_h_mp(P.d, P.l, j, k, t, tp))
+
+
+def test_nlml_and_gradient_against_mpmath_end_to_end():
+    """NLML and its gradient (central differences at 50 digits, h = 1e-20) for a 3-gene x 4-time problem: pins the
+    oracle's composition -- positional mean, jitter + sigma^2 on the diagonal, Cholesky log-det, quadratic form and
+    every closed-form derivative -- on arithmetic that shares no code with it."""
+    G, T = 3, 4
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=61)
+    p = rand_params(G, 62)
+    p.sigma = 0.8
+    theta = p.pack()
+    v, g = o.nlml_and_grad(p, x, y)
+    ref = _mp_nlml([float(t) for t in theta], x, y, p.jitter, G)
+    assert abs(float(mp.mpf(float(v)) - ref)) <= 1e-12 * abs(float(ref))
+    h = mp.mpf(10) ** -20
+    for idx in range(theta.shape[0]):
+        tp = [mp.mpf(float(t)) for t in theta]; tm = list(tp)
+        tp[idx] += h; tm[idx] -= h
+        gref = (_mp_nlml(tp, x, y, p.jitter, G) - _mp_nlml(tm, x, y, p.jitter, G)) / (2 * h)
+        assert abs(float(mp.mpf(float(g[idx])) - gref)) <= 1e-10 * max(1.0, abs(float(gref))), (idx, g[idx], gref)
+
+
+def test_latent_posterior_against_mpmath_end_to_end():
+    """model.py:420-463 at 50 digits: Sigma_p = K + diag(variances) + jitter I, mean = K_fx Sigma_p^-1 (y - mu),
+    var = k_ff(t*, t*) + 2 jitter - k^T Sigma_p^-1 k (jitter enters twice)."""
+    G, T = 3, 4
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=63)
+    p = rand_params(G, 64)
+    ts = np.array([[0.7, -1.0, 0.0], [5.2, -1.0, 0.0], [11.0, -1.0, 0.0]])
+    m, v = o.latent_predict(p, ts, x, y, var)
+
+    class P:
+        pass
+    P.d = [mp.mpf(float(t)) for t in p.d]; P.s = [mp.mpf(float(t)) for t in p.s]; P.l = mp.mpf(float(p.l))
+    b = [mp.mpf(float(t)) for t in p.b]
+    N = x.shape[0]
+    block = N // G
+    K = mp.matrix(N, N)
+    for i in range(N):
+        for j in range(N):
+            K[i, j] = mp_kxx_mp(P, mp.mpf(float(x[i, 0])), int(x[i, 1]), mp.mpf(float(x[j, 0])), int(x[j, 1]))
+        K[i, i] += mp.mpf(float(var[i])) + mp.mpf(p.jitter)
+    z = mp.matrix([mp.mpf(float(y[i])) - b[min(i // block, G - 1)] / P.d[min(i // block, G - 1)] for i in range(N)])
+    Kinv = K ** -1
+    for q in range(ts.shape[0]):
+        k = mp.matrix([mp_kxf(p, x[i, 0], int(x[i, 1]), ts[q, 0]) for i in range(N)])
+        mean = (k.T * Kinv * z)[0]
+        vv = 1 + 2 * mp.mpf(p.jitter) - (k.T * Kinv * k)[0]
+        assert abs(float(mp.mpf(float(m[q])) - mean)) <= 1e-11 * max(1.0, abs(float(mean)))
+        assert abs(float(mp.mpf(float(v[q])) - vv)) <= 1e-11 * max(1.0, abs(float(vv)))
