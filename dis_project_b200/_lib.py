@@ -79,6 +79,8 @@ SIGNATURES = {
                                     _int, _int, _int, _ptr, _ptr, _ptr]),
     "lfm_debug_leaf_profile": (_int, [_ptr, _ptr, _ptr, _ptr, _ptr]),
     "lfm_debug_launch_count": (C.c_ulonglong, []),
+    "lfm_debug_batched_stamps": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _int, _int, _int, _ptr, _ptr,
+                                        _ptr]),
     "lfm_debug_profile_begin": (_int, []),
     "lfm_debug_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "lfm_debug_profile_sum_ms": (C.c_double, []),

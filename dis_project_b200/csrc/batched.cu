@@ -467,6 +467,21 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
   a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key;
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
+// Debug: one launch of `steps` >= 2 steps with clock64 stamps at the phase boundaries of the SECOND step of LFM 0
+// (warp-per-LFM kernel only): A B C D E[load] E[routine] E[W^T W] E[Schur] E[store] F I J K end.
+extern "C" int lfm_debug_batched_stamps(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                        const double* y, double* theta_unc_io, double* adam_state, double jitter,
+                                        int steps, int unique_rows_hint, int time_grid_hint, double* out_hist,
+                                        int* info, long long* stamps) {
+  BatchedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y; a.u_io = theta_unc_io; a.adam = adam_state;
+  a.jitter = jitter; a.lr = 0.01; a.b1 = 0.9; a.b2 = 0.999; a.eps = 1e-8;
+  a.first_step = 0; a.steps = steps; a.total_steps = steps; a.fix_params = 1; a.steps_per_epoch = 1000;
+  a.hist = out_hist; a.ld_hist = steps; a.info = info; a.max_unique = unique_rows_hint; a.stamps = stamps;
+  return batched_launch((cudaStream_t)stream, a, time_grid_hint);
+}
+
 extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
                                double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                                double b2, double eps, int first_step, int steps, int total_steps, int fix_params,

@@ -18,6 +18,7 @@ struct BatchedArgs {
   double* eval_grad;  // eval-only mode: B x P
   int* info;
   int max_unique;
+  long long* stamps;   // debug (lfm_debug_batched_stamps): clock64 at the phase boundaries of the first step of LFM 0
   long long* best_key; // NULL or one device word: atomicMin of lfm_loss_key(loss after the launch's last step) over the batch     // shared-memory matrix is sized for this many unique rows (N when unknown)
 };
 

@@ -13,7 +13,7 @@
 //     G T^2 evaluations instead of 2 U^2 (p53: 245 instead of 2520), one erf/erfc call per entry;
 //   * rows are mapped to lanes as {lane < U-32, (U-32) + lane}, so the triangular phases touch the
 //     U - 32 "extra" rows only while they are short.
-// Limits: N <= 128, U <= 40, 3G+2 <= 64, G T^2 <= 2048; anything else runs the CTA-per-LFM kernel.
+// Limits: N <= 128, U <= 36, 3G+2 <= 64, G T^2 <= 2048; anything else runs the CTA-per-LFM kernel.
 #include "batched.cuh"
 
 
@@ -37,11 +37,36 @@ __device__ __forceinline__ double w_rsqrt(double x) {
   return fma(t, y0 * e, y0);
 }
 
-#define WEX 8             // most "extra" rows beyond 32 the warp kernel takes (U <= 40)
+#define WEX 4             // most "extra" rows beyond 32 the warp kernel takes (U <= 36)
 #define XLD (WEX + 1)
+// lfm_h_core (sim_math.cuh) with the Gaussian factors entering pre-multiplied by A1: pt.g1 = A1 g1, pt.g2 = A1 g2
+template <bool GRAD>
+__device__ __forceinline__ void w_h_core(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
+                                         const LfmPairTerms& pt, double& H, double& dH_da, double& dH_db,
+                                         double& dH_dl) {
+  const double delta = pb.t - pa.t;
+  const double inv = pt.inv;
+  const double E0 = pb.eg2 * inv;
+  const double A2 = pa.e * pb.e;
+  const double A1R1 = pt.A1R1;
+  const double A2R2 = A2 * pb.q;
+  H = E0 * (A1R1 - A2R2);
+  if (GRAD) {
+    const double A1g1 = pt.g1, A1g2 = pt.g2;
+    const double g3 = pb.g3, g4 = pb.g4;
+    const double hl = 0.5 * l;
+    const double hd = 0.5 * pb.d;
+    const double il2 = inv_l * inv_l;
+    dH_da = -H * inv + E0 * pa.t * A2R2;
+    dH_db = H * (pb.gam * l - inv) + E0 * (-delta * A1R1 + hl * (A1g2 - A1g1) + pb.t * A2R2 - A2 * hl * (g4 - g3));
+    dH_dl = H * pb.gam * pb.d + E0 * ((A1g1 * (-delta * il2 - hd) + A1g2 * (-pa.t * il2 + hd)) -
+                                      A2 * (g3 * (-pb.t * il2 - hd) + g4 * hd));
+  }
+}
+
 struct WarpLayout {
   int ld;
-  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, w, beta, kb, wdiag, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, Msm, Xs, xdiag;
+  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
   size_t pts;       // byte offset
   size_t ints;      // byte offset: umap[N], urow[MU], rows_of[N], mflag[N]
   size_t bytes;
@@ -52,25 +77,38 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   L.ld = MU | 1;
   size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 1) & ~(size_t)1; return r; };
-  L.S = take((size_t)MU * L.ld > 32 * 33 ? (size_t)MU * L.ld : 32 * 33);  // also holds W22 as Wb[32][33]
+  // S also holds W22 as Wb[32][33] (phase E) and, in phases B / C, the per-step factor tables (aliased below)
+  const size_t scratch = 6 * (((size_t)G * MT + 1) & ~(size_t)1) + (((size_t)MT + 1) & ~(size_t)1) +
+                         (((size_t)MT * MT + 1) & ~(size_t)1) + (((size_t)G * MT * MT + 1) & ~(size_t)1);
+  size_t s_doubles = (size_t)MU * L.ld > 32 * 33 ? (size_t)MU * L.ld : 32 * 33;
+  if (scratch > s_doubles) s_doubles = scratch;
+  L.S = take(s_doubles);
   const size_t tab = (size_t)G * MT * MT;
   L.tA1R1 = take(tab); L.tA1 = take(tab); L.tG1 = take(tab);
   L.g2 = take((size_t)G * MT); L.inv = take((size_t)G * G); L.utime = take(MT);
-  L.e2 = take((size_t)G * MT); L.c2 = take((size_t)G * MT);
-  L.q = take(MU); L.w = take(MU); L.beta = take(MU); L.kb = take(MU); L.wdiag = take(MU); L.sdiag = take(MU);
+  L.q = take(MU); L.beta = take(MU); L.kb = take(MU); L.sdiag = take(MU);
   L.dsum = take(MU);
   L.th = take(P); L.u = take(P); L.gr = take(P); L.am = take(P); L.av = take(P); L.mu = take(G);
   L.ys = take(N);
   L.ring = take(4 * 32);
+  L.gterm = take(4 * (size_t)G);
+  L.dval = take((size_t)MT * MT);
+  {  // aliases inside S
+    size_t so = L.S;
+    auto sub = [&](size_t n) { size_t r = so; so += (n + 1) & ~(size_t)1; return r; };
+    L.Em = sub((size_t)G * MT); L.Ep = sub((size_t)G * MT); L.e3 = sub((size_t)G * MT); L.g3t = sub((size_t)G * MT);
+    L.e2 = sub((size_t)G * MT); L.c2 = sub((size_t)G * MT);
+    L.Gt = sub(MT); L.Gd = sub((size_t)MT * MT); L.er1 = sub((size_t)G * MT * MT);
+  }
   L.Msm = take(WEX * 32);
   L.Xs = take(WEX * XLD);
-  L.xdiag = take(WEX);
   L.pts = o * 8;
   size_t b = L.pts + (size_t)MU * sizeof(LfmPoint);
   b = (b + 15) & ~(size_t)15;
   L.ints = b;
-  b += sizeof(int) * ((size_t)3 * N + MU);
+  b += sizeof(int) * ((size_t)3 * N + 2 * MU);
   b += sizeof(unsigned short) * ((size_t)MU * (MU + 1) / 2 + 2);  // pair table
+  b += sizeof(unsigned short) * ((size_t)MT * MT + 2);             // distinct time-difference index of every time pair
   L.bytes = (b + 15) & ~(size_t)15;
   return L;
 }
@@ -87,17 +125,21 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   double* tA1R1 = base + L.tA1R1; double* tA1 = base + L.tA1; double* tG1 = base + L.tG1;
   double* g2 = base + L.g2; double* inv = base + L.inv; double* utime = base + L.utime;
   double* e2 = base + L.e2; double* c2 = base + L.c2;
-  double* q = base + L.q; double* w = base + L.w; double* beta = base + L.beta; double* kb = base + L.kb;
-  double* wdiag = base + L.wdiag; double* sdiag = base + L.sdiag; double* dsum = base + L.dsum;
+  double* q = base + L.q; double* beta = base + L.beta; double* kb = base + L.kb;
+  double* sdiag = base + L.sdiag; double* dsum = base + L.dsum;
   double* th = base + L.th; double* u = base + L.u; double* gr = base + L.gr; double* am = base + L.am;
   double* av = base + L.av; double* mu = base + L.mu; double* ys = base + L.ys; double* ring = base + L.ring;
-  double* Msm = base + L.Msm; double* Xs = base + L.Xs; double* xdiag = base + L.xdiag;
+  double* Msm = base + L.Msm; double* Xs = base + L.Xs;
+  double* gterm = base + L.gterm;
+  double* Em = base + L.Em; double* Ep = base + L.Ep; double* e3 = base + L.e3; double* g3t = base + L.g3t;
+  double* Gt = base + L.Gt; double* Gd = base + L.Gd; double* er1 = base + L.er1; double* dval = base + L.dval;
   LfmPoint* pts = reinterpret_cast<LfmPoint*>(smem_raw + L.pts);
   int* umap = reinterpret_cast<int*>(smem_raw + L.ints);  // row -> unique index       (N)
   int* urow = umap + N;                                   // unique index -> first row (MU)
   int* rows_of = urow + MU;                               // rows of class u: rows_of[u * R + r] (N)
   int* mflag = rows_of + N;                               // 2 * positional block + flag (N)
-  unsigned short* pairs = reinterpret_cast<unsigned short*>(mflag + N);  // lower-triangle pair p -> (r << 8) | c
+  int* pgene = mflag + N;                                 // gene of every unique row (MU)
+  unsigned short* pairs = reinterpret_cast<unsigned short*>(pgene + MU);  // lower-triangle pair p -> (r << 8) | c
 
   for (int p = lane; p < P; p += 32) {
     u[p] = a.u_io[bidx * P + p];
@@ -108,11 +150,14 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   int fail = 0;
   const int blk = N / G;  // rows per positional mean block (model.py:145)
   // ---- once per launch: duplicate rows (class representative = first identical row), multiplicity ---------
+  double* Xsm = S;   // X (N x 3) staged in shared memory for the O(N^2) scans below (S is not in use yet)
+  for (int i = lane; i < 3 * N; i += 32) Xsm[i] = a.X[i];
+  __syncwarp();
   for (int i = lane; i < N; i += 32) {
     int rep = i;
-    const double t0 = a.X[3 * i], g0 = a.X[3 * i + 1], f0 = a.X[3 * i + 2];
+    const double t0 = Xsm[3 * i], g0 = Xsm[3 * i + 1], f0 = Xsm[3 * i + 2];
     for (int j = 0; j < i; ++j)
-      if (a.X[3 * j] == t0 && a.X[3 * j + 1] == g0 && a.X[3 * j + 2] == f0) { rep = j; break; }
+      if (Xsm[3 * j] == t0 && Xsm[3 * j + 1] == g0 && Xsm[3 * j + 2] == f0) { rep = j; break; }
     umap[i] = rep;
     ys[i] = a.y[i];
     int m = i / blk;
@@ -170,9 +215,9 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   if (fail == 0) {
     int nfirst = 0;
     for (int r = lane; r < U; r += 32) {
-      const double t = a.X[3 * urow[r]];
+      const double t = Xsm[3 * urow[r]];
       int first = 1;
-      for (int j = 0; j < r; ++j) if (a.X[3 * urow[j]] == t) { first = 0; break; }
+      for (int j = 0; j < r; ++j) if (Xsm[3 * urow[j]] == t) { first = 0; break; }
       nfirst += first;
       pts[r].flag = first;  // temporary marker
     }
@@ -182,9 +227,9 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     if (Tu > MT) { fail = -2; }  // caller's time-grid bound was wrong: refuse (info = -2)
     else {
       for (int r = lane; r < U; r += 32) {
-        const double t = a.X[3 * urow[r]];
+        const double t = Xsm[3 * urow[r]];
         int idx = 0, rep = r;
-        for (int j = 0; j < r; ++j) if (a.X[3 * urow[j]] == t) { rep = j; break; }
+        for (int j = 0; j < r; ++j) if (Xsm[3 * urow[j]] == t) { rep = j; break; }
         for (int j = 0; j < rep; ++j) idx += pts[j].flag;
         pts[r].ti = idx;
         if (rep == r) utime[idx] = t;
@@ -201,6 +246,35 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     wpair_decode(p, r, cc);
     pairs[p] = (unsigned short)((r << 8) | cc);
   }
+  // distinct time differences: the erf / erfc factor of a pair term depends on (gene, t_ib - t_ia) only, and a
+  // regular grid has 2 T - 1 distinct differences, not T^2 (compared bit for bit; an irregular grid keeps T^2)
+  unsigned short* didx = pairs + ((size_t)MU * (MU + 1) / 2 + 2);
+  int nD = 0;
+  {
+    const int TTp = Tu * Tu;
+    for (int p = lane; p < TTp; p += 32) {
+      const double dv = utime[p % Tu] - utime[p / Tu];   // pair p = ia * Tu + ib
+      int first = p;
+      for (int j = 0; j < p; ++j)
+        if (utime[j % Tu] - utime[j / Tu] == dv) { first = j; break; }
+      didx[p] = (unsigned short)first;  // temporarily the representative pair
+    }
+    __syncwarp();
+    for (int p = lane; p < TTp; p += 32) {
+      const int rep = didx[p];
+      int idx = 0;
+      for (int j = 0; j < rep; ++j) idx += (didx[j] == j);
+      if (rep == p) dval[idx] = utime[p % Tu] - utime[p / Tu];
+      Gd[p] = (double)idx;  // park the compact index (Gd is rebuilt every step)
+    }
+    __syncwarp();
+    int cnt = 0;
+    for (int p = lane; p < TTp; p += 32) cnt += (didx[p] == p);
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    nD = cnt;
+    __syncwarp();
+    for (int p = lane; p < TTp; p += 32) didx[p] = (unsigned short)(int)Gd[p];
+  }
   __syncwarp();
   const bool eval_only = a.eval_val != nullptr;
   const int nsteps = eval_only ? 1 : a.steps;
@@ -208,20 +282,85 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   const int ex = U > 32 ? U - 32 : 0;  // rows [0, ex) are the "extra" rows: lane -> rows {lane < ex, ex + lane}
   const int TT = Tu * Tu;
 
+  int nstamp = 0;
+  // Adam bias corrections b^(step+1), carried multiplicatively (pow once per launch, not twice per step per leaf)
+  double b1t = pow(a.b1, (double)a.first_step), b2t = pow(a.b2, (double)a.first_step);
+#define WSTAMP() do { if (a.stamps && bidx == 0 && sidx == 1 && lane == 0) a.stamps[nstamp++] = clock64(); } while (0)
   for (int sidx = 0; sidx < nsteps; ++sidx) {
     const int step = a.first_step + sidx;
+    WSTAMP();
     // ---- A. constrain -----------------------------------------------------------------------
     for (int p = lane; p < P; p += 32) th[p] = (p == 3 * G) ? lfm_l_forward(u[p]) : lfm_softplus(u[p]);
     __syncwarp();
     const double l = th[3 * G], inv_l = 1.0 / l, sigma = th[3 * G + 1];
     const double c = a.jitter + sigma * sigma;
+    WSTAMP();
     // ---- B. unique points, q = P^T z, z^T z ------------------------------------------------------
-    for (int m = lane; m < G; m += 32) mu[m] = th[2 * G + m] / th[m];
+    // Transcendentals, factored so that each is evaluated once per distinct argument:
+    //   per gene b          : gamma_b, exp(gamma_b^2), erf(gamma_b), g4_b = 2/sqrt(pi) exp(-gamma_b^2)
+    //   per time i          : Gt_i = exp(-t_i^2 / l^2)
+    //   per (b, i)          : Em = exp(-d_b t_i), Ep = 1 / Em, erf / erfc of t_i/l + gamma_b, erf(t_i/l - gamma_b),
+    //                         g2 = g4_b Gt_i Em, g3 = g4_b Gt_i Ep           (2 gamma_b / l = d_b)
+    //   per time pair       : Gd = exp(-(t_ib - t_ia)^2 / l^2)
+    //   per (b, difference) : erf or erfc of (t_ib - t_ia)/l - gamma_b
+    // and per table entry (b, ia, ib) only products remain: A1 = Em[ib] Ep[ia], A1 g1 = g4_b Gd.
+    // |d_b t_i| > 600 (Ep would overflow) switches the whole warp to direct evaluation of A1 and g1.
+    int slow = 0;
+    for (int m = lane; m < G; m += 32) {
+      mu[m] = th[2 * G + m] / th[m];
+      const double gam = th[m] * l * 0.5;
+      gterm[4 * m + 0] = gam;
+      gterm[4 * m + 1] = exp(gam * gam);
+      gterm[4 * m + 2] = erf(gam);
+      gterm[4 * m + 3] = LFM_TWO_OVER_SQRT_PI * exp(-gam * gam);
+    }
+    for (int i = lane; i < Tu; i += 32) { const double tl = utime[i] * inv_l; Gt[i] = exp(-tl * tl); }
+    for (int p = lane; p < TT; p += 32) {
+      const double dl = (utime[p % Tu] - utime[p / Tu]) * inv_l;
+      Gd[p] = exp(-dl * dl);
+    }
+    __syncwarp();
+    for (int e = lane; e < G * Tu; e += 32) {
+      const int b = e / Tu, i = e % Tu;
+      const double t = utime[i], d_b = th[b], gam = gterm[4 * b], g4b = gterm[4 * b + 3];
+      if (fabs(d_b * t) > 600.0) slow = 1;
+      const double em = exp(-d_b * t), ep = 1.0 / em;
+      Em[b * MT + i] = em;
+      Ep[b * MT + i] = ep;
+      const double x2 = t * inv_l + gam, x3 = t * inv_l - gam;
+      e2[b * MT + i] = erf(x2);
+      c2[b * MT + i] = erfc(fabs(x2));
+      e3[b * MT + i] = erf(x3);
+      g2[b * MT + i] = g4b * Gt[i] * em;
+      g3t[b * MT + i] = g4b * Gt[i] * ep;
+    }
+    for (int e = lane; e < G * G; e += 32) inv[e] = 1.0 / (th[e / G] + th[e % G]);
+    slow = __any_sync(0xffffffffu, slow);
+    // erf-family factor per (gene, distinct difference): erfc(|x1|) beyond 0.5, erf(x1) inside
+    for (int e = lane; e < G * nD; e += 32) {
+      const int b = e / nD, k = e % nD;
+      const double x1 = dval[k] * inv_l - gterm[4 * b];
+      er1[b * MT * MT + k] = (fabs(x1) > 0.5) ? erfc(fabs(x1)) : erf(x1);
+    }
+    __syncwarp();
     for (int r = lane; r < U; r += 32) {
-      const int ti = pts[r].ti;
-      LfmPoint p = lfm_make_point(a.X + 3 * urow[r], G, th, th + G, l, true);
-      p.ti = ti;
+      const double* row3 = a.X + 3 * urow[r];
+      LfmPoint p;
+      p.t = row3[0];
+      p.gene = lfm_resolve_gene(row3[1], G);
+      p.flag = ((int)row3[2]) != 0;
+      p.ti = pts[r].ti;
+      p.d = th[p.gene];
+      p.s = th[G + p.gene];
+      p.gam = gterm[4 * p.gene + 0];
+      p.eg2 = gterm[4 * p.gene + 1];
+      p.erfg = gterm[4 * p.gene + 2];
+      p.g4 = gterm[4 * p.gene + 3];
+      p.e = Em[p.gene * MT + p.ti];
+      p.q = e3[p.gene * MT + p.ti] + p.erfg;
+      p.g3 = slow ? LFM_TWO_OVER_SQRT_PI * exp(-(p.t * inv_l - p.gam) * (p.t * inv_l - p.gam)) : g3t[p.gene * MT + p.ti];
       pts[r] = p;
+      pgene[r] = p.gene;
     }
     __syncwarp();
     double zz = 0.0;
@@ -238,64 +377,64 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
       q[r] = acc;
     }
-    // ---- C. time-grid tables: per (gene b, time ia) the x2 terms, per (b, ia, ib) the pair terms -------------
-    for (int e = lane; e < G * Tu; e += 32) {
-      const int b = e / Tu, ia = e % Tu;
-      const double gam = th[b] * l * 0.5;
-      const double x2 = utime[ia] * inv_l + gam;
-      e2[b * MT + ia] = erf(x2);
-      c2[b * MT + ia] = erfc(fabs(x2));
-      g2[b * MT + ia] = __dmul_rn(LFM_TWO_OVER_SQRT_PI, exp(-x2 * x2));
-    }
-    for (int e = lane; e < G * G; e += 32) inv[e] = 1.0 / (th[e / G] + th[e % G]);
-    __syncwarp();
+    WSTAMP();
+    // ---- C. time-grid tables: per (b, ia, ib) products of the factors above (tG1 holds A1 * g1) -----------------
     for (int e = lane; e < G * TT; e += 32) {
       const int b = e / TT, r2 = e % TT, ia = r2 / Tu, ib = r2 % Tu;
-      const double d_b = th[b];
-      const double gam = d_b * l * 0.5;
-      const double ta = utime[ia], tb = utime[ib];
-      const double delta = tb - ta;
-      const double A1 = exp(-d_b * delta);
+      const double gam = gterm[4 * b];
+      const double delta = utime[ib] - utime[ia];
       const double x1 = delta * inv_l - gam;
-      const double x2 = ta * inv_l + gam;
-      // lfm_erfsum(x1, x2) with the x2 half read from the (b, ia) tables: identical values, half the calls
+      const double x2 = utime[ia] * inv_l + gam;
+      const double ev = er1[b * MT * MT + didx[r2]];
+      const bool big1 = fabs(x1) > 0.5;
+      // lfm_erfsum(x1, x2): erfc(-n) - erfc(p) for opposite signs beyond 0.5, erf(x1) + erf(x2) otherwise
       double R1;
-      if (x1 * x2 < 0.0 && fmin(fabs(x1), fabs(x2)) > 0.5) {
-        const double cx1 = erfc(fabs(x1));
-        R1 = (x1 < x2) ? (cx1 - c2[b * MT + ia]) : (c2[b * MT + ia] - cx1);  // erfc(-n) - erfc(p)
+      if (x1 * x2 < 0.0 && big1 && fabs(x2) > 0.5) {
+        R1 = (x1 < x2) ? (ev - c2[b * MT + ia]) : (c2[b * MT + ia] - ev);
       } else {
-        R1 = erf(x1) + e2[b * MT + ia];
+        const double erf1 = big1 ? copysign(1.0 - ev, x1) : ev;
+        R1 = erf1 + e2[b * MT + ia];
+      }
+      double A1, A1g1;
+      if (slow) {
+        A1 = exp(-th[b] * delta);
+        A1g1 = A1 * (LFM_TWO_OVER_SQRT_PI * exp(-x1 * x1));
+      } else {
+        A1 = Em[b * MT + ib] * Ep[b * MT + ia];
+        A1g1 = gterm[4 * b + 3] * Gd[r2];
       }
       const size_t o = (size_t)b * MT * MT + (size_t)ia * MT + ib;
       tA1[o] = A1;
-      tA1R1[o] = __dmul_rn(A1, R1);
-      tG1[o] = __dmul_rn(LFM_TWO_OVER_SQRT_PI, exp(-x1 * x1));
+      tA1R1[o] = A1 * R1;
+      tG1[o] = A1g1;
     }
     __syncwarp();
     // h(pa, pb) from the shared-memory tables
     auto pair_terms = [&](const LfmPoint& pa, const LfmPoint& pb) {
       LfmPairTerms pt;
       const size_t o = (size_t)pb.gene * MT * MT + (size_t)pa.ti * MT + pb.ti;
-      pt.A1 = tA1[o]; pt.A1R1 = tA1R1[o]; pt.g1 = tG1[o];
-      pt.g2 = g2[pb.gene * MT + pa.ti];
+      pt.A1 = tA1[o]; pt.A1R1 = tA1R1[o]; pt.g1 = tG1[o];              // g1 slot: A1 * g1
+      pt.g2 = pt.A1 * g2[pb.gene * MT + pa.ti];                           // g2 slot: A1 * g2
       pt.inv = inv[pa.gene * G + pb.gene];
       return pt;
     };
+    WSTAMP();
     // ---- D. M = c I + R K_u (lower + diagonal) -------------------------------------------------------
     for (int p = lane; p < npairs; p += 32) {
       const int r = pairs[p] >> 8, cc = pairs[p] & 255;
       const LfmPoint pi = pts[r], pj = pts[cc];
       double H1, H2, u0, u1, u2;
-      lfm_h_core<false>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, u0, u1, u2);
-      lfm_h_core<false>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, u0, u1, u2);
+      w_h_core<false>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, u0, u1, u2);
+      w_h_core<false>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, u0, u1, u2);
       double k = dR * (pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l) * (H1 + H2));
       if (r == cc) k += c;
       S[r * ld + cc] = k;
     }
     __syncwarp();
+    WSTAMP();
     // ---- E. M^-1 and log det M.  M = [[M11, M21^T], [M21, M22]] with M22 the trailing n2 = U - ex (<= 32) rows.
     // M22 is factorised AND inverted in registers (lane i owns row i of M22 / L22 and column i of W22 = L22^-1; the
-    // pivot loop is fully unrolled; lanes >= n2 carry identity rows); the ex <= 8 leading rows enter through the
+    // pivot loop is fully unrolled; lanes >= n2 carry identity rows); the ex <= 4 leading rows enter through the
     // Schur complement, every per-lane quantity in registers with compile-time indices:
     //   B = M22^-1 M21,  S11 = M11 - M21^T B,  X11 = S11^-1,  Y = B X11,
     //   M^-1 = [[X11, -Y^T], [-Y, M22^-1 + Y B^T]],   log det M = log det M22 + log det S11.
@@ -316,6 +455,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       if (lane < ex)
         for (int b1 = 0; b1 <= lane; ++b1) Xs[lane * XLD + b1] = S[lane * ld + b1];
       __syncwarp();  // S is free from here on: it becomes Wb[32][33]
+      WSTAMP();
       double my_rk = 1.0;
       double akk = __shfl_sync(0xffffffffu, am[0], 0);
 #pragma unroll
@@ -349,6 +489,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         }
         akk = akk_next;
       }
+      WSTAMP();
       double ld22 = (lane < n2) ? -log(my_rk) : 0.0;   // log L_kk = -log(1 / L_kk)
       ld22 = 2.0 * wsum(ld22);
       // W22 -> Wb[i][c] (constant stride 33; padded lanes carry exact zeros / identity)
@@ -365,6 +506,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         for (int k = c; k < 32; ++k) s0 = fma(yw[k], Wb[k * 33 + c], s0);
         mrow[c] = s0;
       }
+      WSTAMP();
       double ld11 = 0.0;
       double yrow[WEX];
 #pragma unroll
@@ -380,69 +522,82 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
           }
           bcol[j] = s0;   // B[lane][j]
         }
-        // S11 = M11 - M21^T B (lower), by lane 0 into Xs
+        // S11 = M11 - M21^T B: the ex (ex + 1) / 2 lane sums are reduced together (independent butterfly chains
+        // interleave), every lane ends up with all of S11 in registers ...
+        double s11[WEX][WEX];
 #pragma unroll
         for (int a1 = 0; a1 < WEX; ++a1)
 #pragma unroll
-          for (int b1 = 0; b1 <= a1; ++b1)
-            if (a1 < ex) {
-              const double t = wsum(m21[a1] * bcol[b1]);
-              if (lane == 0) Xs[a1 * XLD + b1] -= t;
-            }
-        __syncwarp();
-        // S11 = L11 L11^T (left-looking, lane per row); W11 = L11^-1 in the upper triangle; X11 = W11^T W11
-        for (int k = 0; k < ex; ++k) {
-          double v = 0.0;
-          const bool on = lane >= k && lane < ex;
-          if (on) {
-            double s0 = 0.0;
-            for (int m = 0; m < k; ++m) s0 = fma(Xs[lane * XLD + m], Xs[k * XLD + m], s0);
-            v = Xs[lane * XLD + k] - s0;
-          }
-          const double piv = __shfl_sync(0xffffffffu, v, k);
-          if (!(piv > 0.0) && fail == 0) fail = k + 1;
+          for (int b1 = 0; b1 <= a1; ++b1) s11[a1][b1] = (a1 < ex) ? m21[a1] * bcol[b1] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int a1 = 0; a1 < WEX; ++a1)
+#pragma unroll
+            for (int b1 = 0; b1 <= a1; ++b1)
+              if (a1 < ex) s11[a1][b1] += __shfl_xor_sync(0xffffffffu, s11[a1][b1], o);
+#pragma unroll
+        for (int a1 = 0; a1 < WEX; ++a1)
+#pragma unroll
+          for (int b1 = 0; b1 <= a1; ++b1) s11[a1][b1] = (a1 < ex) ? Xs[a1 * XLD + b1] - s11[a1][b1] : ((a1 == b1) ? 1.0 : 0.0);
+        // ... and factorises / inverts it redundantly with compile-time indices (identity padding beyond ex):
+        // L11 (in place), W11 = L11^-1, X11 = W11^T W11
+        double rprod = 1.0;
+        double rd[WEX];
+#pragma unroll
+        for (int k = 0; k < WEX; ++k) {
+          const double piv = s11[k][k];
+          if (k < ex && !(piv > 0.0) && fail == 0) fail = k + 1;
           const double rkk = w_rsqrt(piv);
-          if (on) Xs[lane * XLD + k] = (lane == k) ? piv * rkk : v * rkk;
-          if (lane == 0) { xdiag[k] = rkk; ld11 -= log(rkk); }
-          __syncwarp();
-        }
-        ld11 = 2.0 * __shfl_sync(0xffffffffu, ld11, 0);
-        if (lane < ex) {  // column `lane` of W11 into row `lane` of the upper triangle: Xs[c][i] = W11[i][c], i > c
-          const int cc = lane;
-          for (int i = cc + 1; i < ex; ++i) {
-            double s0 = Xs[i * XLD + cc] * xdiag[cc];
-            for (int k = cc + 1; k < i; ++k) s0 = fma(Xs[i * XLD + k], Xs[cc * XLD + k], s0);
-            Xs[cc * XLD + i] = -s0 * xdiag[i];
-          }
-        }
-        __syncwarp();
-        if (lane < ex) {  // row `lane` of X11 = W11^T W11 (lower + diagonal) -> registers, then in place
-          const int a1 = lane;
-          double xr[WEX];
+          rd[k] = rkk;
+          if (k < ex) rprod *= rkk;
+          s11[k][k] = piv * rkk;
 #pragma unroll
-          for (int b1 = 0; b1 < WEX; ++b1) {
+          for (int i = k + 1; i < WEX; ++i) s11[i][k] *= rkk;
+#pragma unroll
+          for (int i = k + 1; i < WEX; ++i)
+#pragma unroll
+            for (int j = k + 1; j <= i; ++j) s11[i][j] = fma(-s11[i][k], s11[j][k], s11[i][j]);
+        }
+        ld11 = -2.0 * log(rprod);   // log det S11 = 2 sum log L_kk = -2 log prod (1 / L_kk)
+        double w11[WEX][WEX];      // lower: W11 = L11^-1
+#pragma unroll
+        for (int cc = 0; cc < WEX; ++cc) {
+          w11[cc][cc] = rd[cc];
+#pragma unroll
+          for (int i = cc + 1; i < WEX; ++i) {
             double s0 = 0.0;
-            if (b1 <= a1) {
-              s0 = xdiag[a1] * ((a1 == b1) ? xdiag[a1] : Xs[b1 * XLD + a1]);
-              for (int k = a1 + 1; k < ex; ++k) s0 = fma(Xs[a1 * XLD + k], Xs[b1 * XLD + k], s0);
-            }
-            xr[b1] = s0;
-          }
 #pragma unroll
-          for (int b1 = 0; b1 < WEX; ++b1)
-            if (b1 <= a1) Xs[a1 * XLD + b1] = xr[b1];   // lower incl. diagonal; the upper triangle (W11) stays readable
+            for (int k = cc; k < i; ++k) s0 = fma(s11[i][k], w11[k][cc], s0);
+            w11[i][cc] = -s0 * rd[i];
+          }
         }
-        __syncwarp();
-        // Y = B X11 (X11 symmetric, read from the lower triangle), B -> Msm for the rank-ex correction
+        double x11[WEX][WEX];      // full symmetric X11 = W11^T W11
+#pragma unroll
+        for (int a1 = 0; a1 < WEX; ++a1)
+#pragma unroll
+          for (int b1 = 0; b1 <= a1; ++b1) {
+            double s0 = 0.0;
+#pragma unroll
+            for (int k = a1; k < WEX; ++k) s0 = fma(w11[k][a1], w11[k][b1], s0);
+            x11[a1][b1] = s0;
+            x11[b1][a1] = s0;
+          }
+        if (lane == 0) {
+#pragma unroll
+          for (int a1 = 0; a1 < WEX; ++a1)
+#pragma unroll
+            for (int b1 = 0; b1 <= a1; ++b1)
+              if (a1 < ex) Xs[a1 * XLD + b1] = x11[a1][b1];   // for the final store of M^-1_11
+        }
+        // Y = B X11
 #pragma unroll
         for (int a1 = 0; a1 < WEX; ++a1) {
           double s0 = 0.0;
-          if (a1 < ex) {
 #pragma unroll
-            for (int b1 = 0; b1 < WEX; ++b1)
-              if (b1 < ex) s0 = fma(bcol[b1], (b1 <= a1) ? Xs[a1 * XLD + b1] : Xs[b1 * XLD + a1], s0);
-          }
-          yrow[a1] = s0;   // Y[lane][a1]
+          for (int b1 = 0; b1 < WEX; ++b1)
+            if (b1 < ex) s0 = fma(bcol[b1], x11[b1][a1], s0);
+          yrow[a1] = (a1 < ex) ? s0 : 0.0;   // Y[lane][a1]
         }
 #pragma unroll
         for (int j = 0; j < WEX; ++j) Msm[j * 32 + lane] = bcol[j];
@@ -456,6 +611,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
           mrow[c] = s0;
         }
       }
+      WSTAMP();
       __syncwarp();  // every lane is done with Wb: S receives M^-1 (lower triangle, runtime ld) and sdiag
       if (lane < n2) {
         double* row = S + (ex + lane) * ld;
@@ -475,6 +631,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       __syncwarp();
       logdetM = ld22 + ld11;
     }
+    WSTAMP();
     // ---- F. beta = M^-1 q (M^-1 symmetric: lower triangle + sdiag), K_u beta = (q - c beta) / R ---------------
     double qkb = 0.0, kbkb = 0.0;
     for (int r = lane; r < U; r += 32) {
@@ -493,6 +650,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     const double quad = (zz - qkb) / c;
     const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
     __syncwarp();
+    WSTAMP();
     // ---- I. fused derivative contraction over the lower triangle of the unique pairs --------------------
     double dl_part = 0.0;
     for (int r = lane; r < U; r += 32) dsum[r] = 0.0;
@@ -503,8 +661,8 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       const double wgt = ((r == cc) ? 0.5 : 1.0) * (dR * minv - beta[r] * beta[cc]);
       const LfmPoint pi = pts[r], pj = pts[cc];
       double H1, dH1_da, dH1_db, dH1_dl, H2, dH2_da, dH2_db, dH2_dl;
-      lfm_h_core<true>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, dH1_da, dH1_db, dH1_dl);
-      lfm_h_core<true>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, dH2_da, dH2_db, dH2_dl);
+      w_h_core<true>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, dH1_da, dH1_db, dH1_dl);
+      w_h_core<true>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, dH2_da, dH2_db, dH2_dl);
       const double mult = pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l);
       const double k = mult * (H1 + H2);
       const double dr = mult * (dH1_db + dH2_da);
@@ -528,25 +686,24 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       dsum[r] = s0 + s1;
     }
     __syncwarp();
+    WSTAMP();
     // ---- J. fold by gene; mean-function terms; sigma ---------------------------------------------
-    for (int m = 0; m < G; ++m) {
+    for (int m = lane; m < G; m += 32) {   // one lane per gene: fixed summation order, no shuffles
       double gd = 0.0, gs = 0.0, asum = 0.0;
-      for (int i = lane; i < U; i += 32) {
-        if (pts[i].gene == m) {
+      for (int i = 0; i < U; ++i) {
+        if (pgene[i] == m) {
           gd += dsum[i];
           gs += 1.0 - c * sdiag[i] - beta[i] * kb[i];
         }
       }
       // asum_m = sum_{i in positional block m} alpha_i,  alpha_i = (z_i - (K_u beta)_{u(i)}) / c
-      for (int i = m * blk + lane; i < (m + 1) * blk; i += 32)
+      for (int i = m * blk; i < (m + 1) * blk; ++i)
         asum += ys[i] - mu[m] * (double)(mflag[i] & 1) - kb[umap[i]];
-      gd = wsum(gd); gs = wsum(gs); asum = wsum(asum) / c;
-      if (lane == 0) {
-        const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
-        gr[m] = gd + asum * Bm / (D * D);
-        gr[G + m] = gs / Sm;
-        gr[2 * G + m] = -asum / D;
-      }
+      asum /= c;
+      const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
+      gr[m] = gd + asum * Bm / (D * D);
+      gr[G + m] = gs / Sm;
+      gr[2 * G + m] = -asum / D;
     }
     {
       double tr = 0.0;
@@ -560,8 +717,10 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
     }
     __syncwarp();
+    WSTAMP();
     // ---- K. chain rule, Adam, hook ----------------------------------------------------------------
     const bool bad = fail != 0;
+    b1t *= a.b1; b2t *= a.b2;
     for (int p = lane; p < P; p += 32) {
       const double sg = lfm_sigmoid(u[p]);
       const double jac = (p == 3 * G) ? (LFM_L_HIGH - LFM_L_LOW) * sg * (1.0 - sg) : sg;
@@ -573,8 +732,8 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         const double m1 = a.b1 * am[p] + (1.0 - a.b1) * g;
         const double v1 = a.b2 * av[p] + (1.0 - a.b2) * g * g;
         am[p] = m1; av[p] = v1;
-        const double mhat = m1 / (1.0 - pow(a.b1, (double)(step + 1)));
-        const double vhat = v1 / (1.0 - pow(a.b2, (double)(step + 1)));
+        const double mhat = m1 / (1.0 - b1t);
+        const double vhat = v1 / (1.0 - b2t);
         double un = u[p] - a.lr * mhat / (sqrt(vhat) + a.eps);
         if (a.fix_params && (step % a.steps_per_epoch) == 0 && G > 3) {
           if (p == G + 3) un = 1.0;  // true_s[3]  (trainer.py:152, unconstrained space: SURVEY Q5)
@@ -583,6 +742,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         u[p] = un;
       }
     }
+    WSTAMP();
     if (lane == 0) {
       const double v = bad ? nan("") : nlml;
       if (eval_only) a.eval_val[bidx] = v;

@@ -169,7 +169,7 @@ int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const doub
 
 /* Time-grid variants of the two batched entry points: `time_grid_hint` is an upper bound on the number of
  * DISTINCT times among the rows of X (lfm_count_distinct_times; 0 = unknown).  With both hints set and
- * the problem inside the limits of the one-warp-per-LFM kernel (unique rows <= 64, G T^2 <= 2048), every
+ * the problem inside the limits of the one-warp-per-LFM kernel (unique rows <= 36, G T^2 <= 2048), every
  * LFM is fitted by a single warp with the exp/erf pair terms tabulated once per step in shared memory;
  * otherwise the one-CTA-per-LFM kernel runs.  A hint smaller than the true count gives info = -2. */
 int lfm_batched_nlml_grad_unc_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
@@ -231,6 +231,10 @@ int lfm_debug_syrk(lfm_stream_t stream, int64_t m, int64_t K, const double* P, i
 
 /* One 128 x 128 leaf factorisation with clock64() stamps at its phase boundaries (16 values). */
 int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info, long long* stamps);
+/* clock64 stamps at the phase boundaries of the second optimiser step of LFM 0 (warp-per-LFM kernel; tools/). */
+int lfm_debug_batched_stamps(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                             double* theta_unc_io, double* adam_state, double jitter, int steps, int unique_rows_hint,
+                             int time_grid_hint, double* out_hist, int* info, long long* stamps);
 /* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
 unsigned long long lfm_debug_launch_count(void);
 /* Bracket every DMMA GEMM launch with CUDA events on its stream between begin and end; end
