@@ -454,7 +454,8 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
                                   double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                                   double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
                                   int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
-                                  int64_t ld_hist, double* out_theta, int* info, long long* best_key) {
+                                  int64_t ld_hist, double* out_theta, int* info, long long* best_key,
+                                  void* structure_cache) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
@@ -465,6 +466,7 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
   a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key;
+  a.struct_cache = structure_cache;
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 // Debug: one launch of `steps` >= 2 steps with clock64 stamps at the phase boundaries of the SECOND step of LFM 0
@@ -482,6 +484,13 @@ extern "C" int lfm_debug_batched_stamps(lfm_stream_t stream, int64_t B, int64_t 
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 
+extern "C" size_t lfm_batched_structure_bytes(int64_t N, int G, int unique_rows_hint, int time_grid_hint) {
+  if (N <= 0 || N > 128 || G <= 0) return 0;
+  int MU = unique_rows_hint;
+  if (MU <= 0 || MU > N) MU = (int)N;
+  return lfm_batched_warp_structure_bytes((int)N, G, MU, time_grid_hint);
+}
+
 extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
                                double* theta_unc_io, double* adam_state, double jitter, double lr, double b1,
                                double b2, double eps, int first_step, int steps, int total_steps, int fix_params,
@@ -489,7 +498,7 @@ extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G,
                                double* out_theta, int* info) {
   return lfm_batched_fit_tg(stream, B, N, G, X, y, theta_unc_io, adam_state, jitter, lr, b1, b2, eps, first_step, steps,
                             total_steps, fix_params, steps_per_epoch, unique_rows_hint, 0, out_hist, ld_hist, out_theta,
-                            info, nullptr);
+                            info, nullptr, nullptr);
 }
 
 // Number of distinct (time, gene, flag) rows of a HOST copy of X: the `unique_rows_hint` that lets the

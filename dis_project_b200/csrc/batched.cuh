@@ -19,6 +19,7 @@ struct BatchedArgs {
   int* info;
   int max_unique;
   long long* stamps;   // debug (lfm_debug_batched_stamps): clock64 at the phase boundaries of the first step of LFM 0
+  void* struct_cache;  // NULL or lfm_batched_structure_bytes() device bytes kept by the caller between the launches of a fit
   long long* best_key; // NULL or one device word: atomicMin of lfm_loss_key(loss after the launch's last step) over the batch     // shared-memory matrix is sized for this many unique rows (N when unknown)
 };
 
@@ -36,3 +37,4 @@ __host__ __device__ inline long long lfm_loss_key(double v) {
 
 // batched_warp.cu: launches the warp-per-LFM kernel when the problem fits its limits, else LFM_ERR_UNSUPPORTED
 int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid);
+size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT);

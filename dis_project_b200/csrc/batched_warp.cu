@@ -106,7 +106,7 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   size_t b = L.pts + (size_t)MU * sizeof(LfmPoint);
   b = (b + 15) & ~(size_t)15;
   L.ints = b;
-  b += sizeof(int) * ((size_t)3 * N + 2 * MU);
+  b += sizeof(int) * ((size_t)3 * N + 3 * MU);
   b += sizeof(unsigned short) * ((size_t)MU * (MU + 1) / 2 + 2);  // pair table
   b += sizeof(unsigned short) * ((size_t)MT * MT + 2);             // distinct time-difference index of every time pair
   L.bytes = (b + 15) & ~(size_t)15;
@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   int* rows_of = urow + MU;                               // rows of class u: rows_of[u * R + r] (N)
   int* mflag = rows_of + N;                               // 2 * positional block + flag (N)
   int* pgene = mflag + N;                                 // gene of every unique row (MU)
-  unsigned short* pairs = reinterpret_cast<unsigned short*>(pgene + MU);  // lower-triangle pair p -> (r << 8) | c
+  int* tiarr = pgene + MU;                                // distinct-time index of every unique row (MU)
+  unsigned short* pairs = reinterpret_cast<unsigned short*>(tiarr + MU);  // lower-triangle pair p -> (r << 8) | c
 
   for (int p = lane; p < P; p += 32) {
     u[p] = a.u_io[bidx * P + p];
@@ -149,6 +150,26 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   }
   int fail = 0;
   const int blk = N / G;  // rows per positional mean block (model.py:145)
+  // ---- structure of X (duplicate rows, distinct times, distinct time differences, pair table): identical for every
+  // LFM and every launch of a fit, so the first launch (first_step == 0) stores LFM 0's copy in a.struct_cache and
+  // later launches load it instead of repeating the O(N^2) scans
+  int U = 0, R = 0, Tu = 0, nD = 0, ld = 1, npairs = 0;
+  unsigned short* didx = pairs + ((size_t)MU * (MU + 1) / 2 + 2);
+  int* const cache_i = reinterpret_cast<int*>(a.struct_cache);
+  const size_t int_bytes = L.bytes - L.ints;
+  if (cache_i && a.first_step > 0 && a.eval_val == nullptr) {
+    U = cache_i[0]; R = cache_i[1]; Tu = cache_i[2]; nD = cache_i[3]; fail = cache_i[4];
+    const int* src = cache_i + 8;
+    int* dst = reinterpret_cast<int*>(smem_raw + L.ints);
+    for (size_t i = lane; i < int_bytes / 4; i += 32) dst[i] = src[i];
+    const double* srcd = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(src) + int_bytes);
+    for (int i = lane; i < MT; i += 32) utime[i] = srcd[i];
+    for (int i = lane; i < MT * MT; i += 32) dval[i] = srcd[MT + i];
+    for (int i = lane; i < N; i += 32) ys[i] = a.y[i];
+    ld = U | 1;
+    npairs = U * (U + 1) / 2;
+    __syncwarp();
+  } else {
   // ---- once per launch: duplicate rows (class representative = first identical row), multiplicity ---------
   double* Xsm = S;   // X (N x 3) staged in shared memory for the O(N^2) scans below (S is not in use yet)
   for (int i = lane; i < 3 * N; i += 32) Xsm[i] = a.X[i];
@@ -165,7 +186,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     mflag[i] = 2 * m + (((int)f0) != 0 ? 1 : 0);
   }
   __syncwarp();
-  int U = 0, R = 0, uniform = 1;
+  int uniform = 1;
   {
     int nrep = 0, cnt0 = 0;
     for (int i = lane; i < N; i += 32) {
@@ -211,7 +232,6 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     __syncwarp();
   }
   // ---- distinct times of the unique rows -> pts[].ti, utime[] ------------------------------------------------
-  int Tu = 0;
   if (fail == 0) {
     int nfirst = 0;
     for (int r = lane; r < U; r += 32) {
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         int idx = 0, rep = r;
         for (int j = 0; j < r; ++j) if (Xsm[3 * urow[j]] == t) { rep = j; break; }
         for (int j = 0; j < rep; ++j) idx += pts[j].flag;
-        pts[r].ti = idx;
+        tiarr[r] = idx;
         if (rep == r) utime[idx] = t;
       }
     }
@@ -239,8 +259,8 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   }
   if (fail != 0) { U = 0; Tu = 0; }
 
-  const int ld = U | 1;
-  const int npairs = U * (U + 1) / 2;
+  ld = U | 1;
+  npairs = U * (U + 1) / 2;
   for (int p = lane; p < npairs; p += 32) {
     int r, cc;
     wpair_decode(p, r, cc);
@@ -248,8 +268,6 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   }
   // distinct time differences: the erf / erfc factor of a pair term depends on (gene, t_ib - t_ia) only, and a
   // regular grid has 2 T - 1 distinct differences, not T^2 (compared bit for bit; an irregular grid keeps T^2)
-  unsigned short* didx = pairs + ((size_t)MU * (MU + 1) / 2 + 2);
-  int nD = 0;
   {
     const int TTp = Tu * Tu;
     for (int p = lane; p < TTp; p += 32) {
@@ -276,6 +294,17 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     for (int p = lane; p < TTp; p += 32) didx[p] = (unsigned short)(int)Gd[p];
   }
   __syncwarp();
+  if (cache_i && a.first_step == 0 && a.eval_val == nullptr && bidx == 0) {
+    __syncwarp();
+    if (lane == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; }
+    int* dst = cache_i + 8;
+    const int* src = reinterpret_cast<const int*>(smem_raw + L.ints);
+    for (size_t i = lane; i < int_bytes / 4; i += 32) dst[i] = src[i];
+    double* dstd = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dst) + int_bytes);
+    for (int i = lane; i < MT; i += 32) dstd[i] = utime[i];
+    for (int i = lane; i < MT * MT; i += 32) dstd[MT + i] = dval[i];
+  }
+  }
   const bool eval_only = a.eval_val != nullptr;
   const int nsteps = eval_only ? 1 : a.steps;
   const double dR = (double)R;
@@ -349,7 +378,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       p.t = row3[0];
       p.gene = lfm_resolve_gene(row3[1], G);
       p.flag = ((int)row3[2]) != 0;
-      p.ti = pts[r].ti;
+      p.ti = tiarr[r];
       p.d = th[p.gene];
       p.s = th[G + p.gene];
       p.gam = gterm[4 * p.gene + 0];
@@ -420,15 +449,25 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     };
     WSTAMP();
     // ---- D. M = c I + R K_u (lower + diagonal) -------------------------------------------------------
-    for (int p = lane; p < npairs; p += 32) {
-      const int r = pairs[p] >> 8, cc = pairs[p] & 255;
+    // two pairs per lane and iteration: the two evaluations are independent straight-line code (loads first,
+    // stores last), so their dependent chains interleave
+    auto kxx_pair = [&](int p, int& r, int& cc) {
+      r = pairs[p] >> 8; cc = pairs[p] & 255;
       const LfmPoint pi = pts[r], pj = pts[cc];
       double H1, H2, u0, u1, u2;
       w_h_core<false>(pj, pi, l, inv_l, pair_terms(pj, pi), H1, u0, u1, u2);
       w_h_core<false>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, u0, u1, u2);
       double k = dR * (pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l) * (H1 + H2));
       if (r == cc) k += c;
-      S[r * ld + cc] = k;
+      return k;
+    };
+    for (int p = lane; p < npairs; p += 64) {
+      const bool two = p + 32 < npairs;
+      int r0, c0, r1, c1;
+      const double k0 = kxx_pair(p, r0, c0);
+      const double k1 = kxx_pair(two ? p + 32 : p, r1, c1);
+      S[r0 * ld + c0] = k0;
+      if (two) S[r1 * ld + c1] = k1;
     }
     __syncwarp();
     WSTAMP();
@@ -655,8 +694,11 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     double dl_part = 0.0;
     for (int r = lane; r < U; r += 32) dsum[r] = 0.0;
     __syncwarp();
-    for (int p = lane; p < npairs; p += 32) {
-      const int r = pairs[p] >> 8, cc = pairs[p] & 255;
+    struct GradPair { int r, cc; double wr, wc, wl; };
+    auto grad_pair = [&](int p) {
+      GradPair g;
+      g.r = pairs[p] >> 8; g.cc = pairs[p] & 255;
+      const int r = g.r, cc = g.cc;
       const double minv = (r == cc) ? sdiag[r] : S[r * ld + cc];
       const double wgt = ((r == cc) ? 0.5 : 1.0) * (dR * minv - beta[r] * beta[cc]);
       const LfmPoint pi = pts[r], pj = pts[cc];
@@ -665,12 +707,24 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       w_h_core<true>(pi, pj, l, inv_l, pair_terms(pi, pj), H2, dH2_da, dH2_db, dH2_dl);
       const double mult = pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l);
       const double k = mult * (H1 + H2);
-      const double dr = mult * (dH1_db + dH2_da);
-      const double dc = mult * (dH1_da + dH2_db);
-      const double dl = mult * (dH1_dl + dH2_dl) + k * inv_l;
-      dl_part += wgt * dl;
-      if (r == cc) dsum[r] = wgt * (dr + dc);
-      else { S[r * ld + cc] = wgt * dr; S[cc * ld + r] = wgt * dc; }
+      g.wr = wgt * (mult * (dH1_db + dH2_da));
+      g.wc = wgt * (mult * (dH1_da + dH2_db));
+      g.wl = wgt * (mult * (dH1_dl + dH2_dl) + k * inv_l);
+      return g;
+    };
+    auto grad_store = [&](const GradPair& g) {
+      if (g.r == g.cc) dsum[g.r] = g.wr + g.wc;
+      else { S[g.r * ld + g.cc] = g.wr; S[g.cc * ld + g.r] = g.wc; }
+    };
+    // two pairs per lane and iteration (independent chains interleave); every pair reads and writes only its own
+    // entries of S, so the loads of the second pair may precede the stores of the first
+    for (int p = lane; p < npairs; p += 64) {
+      const bool two = p + 32 < npairs;
+      const GradPair g0 = grad_pair(p);
+      const GradPair g1 = grad_pair(two ? p + 32 : p);
+      dl_part += g0.wl;
+      grad_store(g0);
+      if (two) { dl_part += g1.wl; grad_store(g1); }
     }
     const double gl = wsum(dl_part);
     __syncwarp();
@@ -773,6 +827,12 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     const double v = a.hist[bidx * a.ld_hist + a.first_step + a.steps - 1];
     if (v == v) atomicMin(a.best_key, lfm_loss_key(v));
   }
+}
+
+size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
+  if (MU <= 0 || MT <= 0) return 0;
+  const WarpLayout L = warp_layout(N, G, MU, MT);
+  return ((32 + (L.bytes - L.ints) + 8 * ((size_t)MT + (size_t)MT * MT)) + 15) & ~(size_t)15;
 }
 
 // Launch the warp-per-LFM kernel if the problem fits its limits; returns LFM_ERR_UNSUPPORTED otherwise

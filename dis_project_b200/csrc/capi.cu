@@ -259,7 +259,7 @@ extern "C" int lfm_batched_fit_host(lfm_handle* h, int64_t B, int64_t N, int G, 
   if (st == LFM_OK)
     st = lfm_batched_fit_tg(h->stream, B, N, G, d + oX, d + oy, d + ou, d + oadam, jitter, lr, b1, b2, eps, 0, steps,
                             steps, fix_params, steps_per_epoch, lfm_count_unique_rows(N, X),
-                            (int)lfm_count_distinct_times(N, X), d + ohist, steps, d + oth, dinfo, nullptr);
+                            (int)lfm_count_distinct_times(N, X), d + ohist, steps, d + oth, dinfo, nullptr, nullptr);
   // d + oth (the start points, dead after lfm_unconstrain) receives the constrained result
   if (st == LFM_OK) {
     cudaMemcpyAsync(hp + ou, d + oth, (size_t)B * P * 8, cudaMemcpyDeviceToHost, h->stream);

@@ -347,6 +347,7 @@ class BatchedFitState:
         self.step = 0
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
+        self.struct_cache = None  # device bytes that carry the structure of X from the first launch to the later ones
 
 
 def loss_key_to_float(keys):
@@ -373,13 +374,17 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     if state.B == 0 or steps <= 0:
         return
     steps = min(steps, state.total_steps - state.step)
+    if state.struct_cache is None:
+        nb = int(_lib.lib().lfm_batched_structure_bytes(X.shape[0], state.G, state.unique_hint, int(state.time_grid)))
+        state.struct_cache = torch.zeros(max(nb, 16), dtype=torch.uint8, device=X.device)
     _lib.check(_lib.lib().lfm_batched_fit_tg(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
                                              state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
                                              state.step, steps, state.total_steps, int(bool(fix_params)),
                                              int(steps_per_epoch), state.unique_hint, int(state.time_grid),
                                              state.hist.data_ptr(), state.hist.shape[1],
                                              state.theta.data_ptr(), state.info.data_ptr(),
-                                             best_key.data_ptr() if best_key is not None else None),
+                                             best_key.data_ptr() if best_key is not None else None,
+                                             state.struct_cache.data_ptr()),
                "lfm_batched_fit_tg")
     state.step += steps
 

@@ -179,7 +179,11 @@ int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const d
                        double* theta_unc_io, double* adam_state, double jitter, double lr, double b1, double b2,
                        double eps, int first_step, int steps, int total_steps, int fix_params,
                        int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
-                       int64_t ld_hist, double* out_theta, int* info, long long* best_key);
+                       int64_t ld_hist, double* out_theta, int* info, long long* best_key, void* structure_cache);
+/* structure_cache (may be NULL): lfm_batched_structure_bytes() device bytes the caller keeps between the calls of ONE
+ * chunked fit.  The call with first_step == 0 stores the structure of X (duplicate rows, distinct times and time
+ * differences, pair table) there; calls with first_step > 0 load it instead of repeating the O(N^2) scans. */
+size_t lfm_batched_structure_bytes(int64_t N, int G, int unique_rows_hint, int time_grid_hint);
 /* best_key (may be NULL): one device word that receives atomicMin over the batch of the order-preserving integer
  * image of each LFM's loss after the last step of this call (finite losses only; initialise it to INT64_MAX).
  * key(v) = bits(v) for v >= 0, bits(v) ^ 0x7fff...f otherwise -- monotone in v, so the global best objective of a
