@@ -52,7 +52,7 @@ __device__ __forceinline__ void load_tile(double* s, const double* __restrict__ 
 //   <8,4,2> 128 x 128, 8 warps     <4,4,4> 128 x 128, 16 warps (4 per scheduler: better DMMA/LDS overlap)
 //   <4,4,2> 64 x 128 (in-place panel)       <4,2,2> 64 x 64 (small problems, 2 CTAs / SM)
 //   <1,4,2> 16 x 128 (one 128-row panel spread over 8 CTAs: the look-ahead chain of the factorisation)
-template <int TA, int TBN, int WM, int WN, int GM>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: K x N
+template <int TA, int TBN, int WM, int WN, int GM, bool SPREAD>  // TA: op(A)=A^T ; TBN = 1: B stored N x K ("NT"), 0: K x N
 __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dgemm_kernel(LfmGemm g, int tiles_n) {
   constexpr int BM = 8 * WM * GM, BN = 32 * WN, NT = 128 * GM;
   constexpr int A_STAGE = BM * LDK, B_STAGE = BN * LDK;  // >= 16 * (BM + 4), 16 * (BN + 4)
@@ -104,27 +104,62 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   const int wn = (warp & 3) * (8 * WN);
   const int fr = lane >> 2, fc = lane & 3;
 
-  // Two k-tiles (32 deep) per barrier: the four stages form two units; unit u is computed while unit
-  // u+1 streams in, so there is one wait_group + one __syncthreads per 256 DMMAs of every warp.
+  // Two k-tiles (32 deep) per barrier: the four stages form two units; unit u is computed while unit u+1 streams
+  // in, so there is one wait_group + one __syncthreads per 256 DMMAs of every warp.  The cp.async of unit u+1 are
+  // issued from per-thread pointers computed once; with SPREAD (short and medium K, where unit boundaries are a
+  // visible share of a tile) not in one burst behind the barrier but in PIECES, one eighth after each k4-step of
+  // unit u (measured: +4..6 % on K <= 4096 shapes, -3 % on K >= 8192, hence the switch).
+  constexpr int PA = (BM * 8 + NT - 1) / NT;   // 16-byte chunks per thread and k-tile, operand A
+  constexpr int PB = (BN * 8 + NT - 1) / NT;   //                                         operand B
+  constexpr int PP = 2 * (PA + PB);            // chunks per thread and unit
+  const double* gsrc[PA + PB];                 // global source of chunk i at k-tile 0 (advances by BK per k-tile)
+  int sdst[PA + PB];                           // shared-memory offset of chunk i inside its stage (doubles)
+  bool live[PA + PB];
+#pragma unroll
+  for (int i = 0; i < PA + PB; ++i) {
+    const bool isA = i < PA;
+    const int id = tid + NT * (isA ? i : i - PA);
+    const int rows = isA ? BM : BN;
+    const bool trans = isA ? (TA != 0) : (TBN == 0);   // operand stored [k][row]
+    live[i] = id < rows * 8;
+    const double* g0 = isA ? gA : gB;
+    const int64_t ldg = isA ? g.lda : g.ldb;
+    const int64_t r0g = isA ? row0 : col0;
+    if (!trans) {
+      const int r = id >> 3, kc = id & 7;
+      gsrc[i] = g0 + (r0g + r) * ldg + kb + kc * 2;
+      sdst[i] = r * LDK + kc * 2;
+    } else {
+      const int kr = id / (rows / 2), mc = id % (rows / 2);
+      gsrc[i] = g0 + (kb + kr) * ldg + r0g + mc * 2;
+      sdst[i] = kr * (rows + 4) + mc * 2;
+    }
+  }
+  const int64_t kstepA = (TA != 0) ? (int64_t)BK * g.lda : BK;
+  const int64_t kstepB = (TBN == 0) ? (int64_t)BK * g.ldb : BK;
+  // piece q in [0, PP): k-tile t = q / (PA + PB), chunk i = q % (PA + PB)
+  auto issue_piece = [&](int uslot, int kt0, int q) {
+    const int t = q / (PA + PB), i = q % (PA + PB);
+    if (kt0 + t < nk && live[i]) {
+      const int slot = uslot * 2 + t;
+      if (i < PA) cp_async16(sA + slot * A_STAGE + sdst[i], gsrc[i] + (int64_t)(kt0 + t) * kstepA);
+      else cp_async16(sB + slot * B_STAGE + sdst[i], gsrc[i] + (int64_t)(kt0 + t) * kstepB);
+    }
+  };
   auto issue_unit = [&](int uslot, int kt0) {
 #pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      if (kt0 + t < nk) {
-        const int slot = uslot * 2 + t;
-        load_tile<TA, BM, NT>(sA + slot * A_STAGE, gA, g.lda, row0, kb + (int64_t)(kt0 + t) * BK, tid);
-        load_tile<TBN ? 0 : 1, BN, NT>(sB + slot * B_STAGE, gB, g.ldb, col0, kb + (int64_t)(kt0 + t) * BK, tid);
-      }
-    }
+    for (int q = 0; q < PP; ++q) issue_piece(uslot, kt0, q);
     cp_async_commit();
   };
   issue_unit(0, 0);
   for (int u = 0; 2 * u < nk; ++u) {
     cp_async_wait<0>();
     __syncthreads();
-    issue_unit((u + 1) & 1, 2 * (u + 1));
     // the unit's (up to) 8 k4-steps with explicitly double-buffered fragments: the LDS of step s+1
     // are issued before the 32 DMMAs of step s
     const int nsteps = (2 * u + 1 < nk) ? 8 : 4;
+    const bool spread = SPREAD && nsteps == 8;
+    if (!spread) issue_unit((u + 1) & 1, 2 * (u + 1));
     const double* a_u = sA + ((u & 1) * 2) * A_STAGE;
     const double* b_u = sB + ((u & 1) * 2) * B_STAGE;
     double af[2][WM], bf[2][WN];
@@ -152,6 +187,12 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
         for (int i = 0; i < WM; ++i)
 #pragma unroll
           for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[step & 1][i], bf[step & 1][j]);
+        if (spread) {
+          // this step's share of the next unit's loads (slot (u+1)&1 was last read before this iteration's barrier)
+#pragma unroll
+          for (int q = step * PP / 8; q < (step + 1) * PP / 8; ++q) issue_piece((u + 1) & 1, 2 * (u + 1), q);
+          if (step == 7) cp_async_commit();
+        }
       }
     }
   }
@@ -270,13 +311,13 @@ static cudaEvent_t prof_event() {
   return g_prof.ev[g_prof.used++];
 }
 
-template <int TA, int TBN, int WM, int WN, int GM>
+template <int TA, int TBN, int WM, int WN, int GM, bool SPREAD>
 static int launch(cudaStream_t st, const LfmGemm& g) {
   constexpr int BM = 8 * WM * GM, BN = 32 * WN;
   constexpr int SMEM = STAGES * (BM + BN) * LDK * 8;
   static bool configured = false;
   if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      SMEM));
     configured = true;
   }
@@ -298,19 +339,28 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
     else { g_prof.flops += f; g_prof.launches += 1; }
   }
   const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
-  lfm_dgemm_kernel<TA, TBN, WM, WN, GM><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
+  lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
   if (g_prof.on) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
 }
 
+template <int WM, int WN, int GM, bool SPREAD>
+static int dispatch2(cudaStream_t st, const LfmGemm& g) {
+  if (g.transA == 0 && g.transB == 1) return launch<0, 1, WM, WN, GM, SPREAD>(st, g);
+  if (g.transA == 0 && g.transB == 0) return launch<0, 0, WM, WN, GM, SPREAD>(st, g);
+  if (g.transA == 1 && g.transB == 0) return launch<1, 0, WM, WN, GM, SPREAD>(st, g);
+  return launch<1, 1, WM, WN, GM, SPREAD>(st, g);
+}
+static int64_t spread_max_k() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("LFM_GEMM_SPREAD_K"); v = e ? atoll(e) : 4096; }
+  return v;
+}
 template <int WM, int WN, int GM>
 static int dispatch(cudaStream_t st, const LfmGemm& g) {
-  if (g.transA == 0 && g.transB == 1) return launch<0, 1, WM, WN, GM>(st, g);
-  if (g.transA == 0 && g.transB == 0) return launch<0, 0, WM, WN, GM>(st, g);
-  if (g.transA == 1 && g.transB == 0) return launch<1, 0, WM, WN, GM>(st, g);
-  return launch<1, 1, WM, WN, GM>(st, g);
+  return g.K <= spread_max_k() ? dispatch2<WM, WN, GM, true>(st, g) : dispatch2<WM, WN, GM, false>(st, g);
 }
 static int big_variant() {
   static int v = -1;
