@@ -39,6 +39,57 @@ __device__ __forceinline__ double w_rsqrt(double x) {
 
 #define WEX 4             // most "extra" rows beyond 32 the warp kernel takes (U <= 36)
 #define XLD (WEX + 1)
+#define GJN (32 + WEX)    // padded order of the Gauss-Jordan sweep of the team kernels
+
+// ---- team primitives: a team of NW warps (NT = 32 NW threads, one CTA) owns one LFM.  NW = 1 is the warp-synchronous
+// kernel (every primitive degenerates to a shuffle / __syncwarp); NW > 1 trades CTA barriers for a shorter dependent
+// chain per optimiser step and is used when the batch leaves SMs idle (few restarts per GPU).
+template <int NW> __device__ __forceinline__ void tsync() {
+  if (NW == 1) __syncwarp(); else __syncthreads();
+}
+// Team sum.  NW > 1: the warp partials go through one of two alternating slot groups of `red` (flip toggles per call),
+// so ONE barrier per sum is enough: a group is rewritten only after the barrier of the next call, which every thread
+// passes after it has read the group.
+template <int NW> __device__ __forceinline__ double tsum(double v, double* red, int& flip) {
+  v = wsum(v);
+  if (NW == 1) return v;
+  double* r = red + flip * NW;
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = r[0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) s += r[w];
+  return s;
+}
+template <int NW> __device__ __forceinline__ int tsum_int(int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if constexpr (NW == 1) {
+    return v;
+  } else {
+    __shared__ int red_i[NW];
+    if ((threadIdx.x & 31) == 0) red_i[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red_i[w];
+    __syncthreads();
+    return s;
+  }
+}
+template <int NW> __device__ __forceinline__ int tany(int v) {
+  if (NW == 1) return __any_sync(0xffffffffu, v);
+  return __syncthreads_or(v);
+}
+// 1/x for x > 0 normal: MUFU.RCP64H seed + two Newton steps (branch free; on the pivot chain of the sweep)
+__device__ __forceinline__ double w_rcp(double x) {
+  double y0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  double e = fma(-x, y0, 1.0);
+  y0 = fma(y0, e, y0);
+  e = fma(-x, y0, 1.0);
+  return fma(y0, e, y0);
+}
 // lfm_h_core (sim_math.cuh) with the Gaussian factors entering pre-multiplied by A1: pt.g1 = A1 g1, pt.g2 = A1 g2
 template <bool GRAD>
 __device__ __forceinline__ void w_h_core(const LfmPoint& pa, const LfmPoint& pb, double l, double inv_l,
@@ -66,7 +117,7 @@ __device__ __forceinline__ void w_h_core(const LfmPoint& pa, const LfmPoint& pb,
 
 struct WarpLayout {
   int ld;
-  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
+  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, red, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
   size_t pts;       // byte offset
   size_t ints;      // byte offset: umap[N], urow[MU], rows_of[N], mflag[N]
   size_t bytes;
@@ -90,7 +141,8 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   L.dsum = take(MU);
   L.th = take(P); L.u = take(P); L.gr = take(P); L.am = take(P); L.av = take(P); L.mu = take(G);
   L.ys = take(N);
-  L.ring = take(4 * 32);
+  L.ring = take(4 * GJN);   // NW = 1: four pivot columns in flight; NW > 1: pivot row / column, double buffered
+  L.red = take(16);
   L.gterm = take(4 * (size_t)G);
   L.dval = take((size_t)MT * MT);
   {  // aliases inside S
@@ -113,10 +165,14 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   return L;
 }
 
-__global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int MT) {
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_batched_warp_kernel(BatchedArgs a, int MT) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = 32 * NW;
   const int N = a.N, G = a.G, P = 3 * G + 2;
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
+  (void)wid;
   const int64_t bidx = blockIdx.x;
   const int MU = a.max_unique;
   const WarpLayout L = warp_layout(N, G, MU, MT);
@@ -129,9 +185,10 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   double* sdiag = base + L.sdiag; double* dsum = base + L.dsum;
   double* th = base + L.th; double* u = base + L.u; double* gr = base + L.gr; double* am = base + L.am;
   double* av = base + L.av; double* mu = base + L.mu; double* ys = base + L.ys; double* ring = base + L.ring;
+  double* red = base + L.red;
   double* Msm = base + L.Msm; double* Xs = base + L.Xs;
   double* gterm = base + L.gterm;
-  double* Em = base + L.Em; double* Ep = base + L.Ep; double* e3 = base + L.e3; double* g3t = base + L.g3t;
+  double* Em = base + L.Em; double* Ep = base + L.Ep; double* e3 = base + L.e3;
   double* Gt = base + L.Gt; double* Gd = base + L.Gd; double* er1 = base + L.er1; double* dval = base + L.dval;
   LfmPoint* pts = reinterpret_cast<LfmPoint*>(smem_raw + L.pts);
   int* umap = reinterpret_cast<int*>(smem_raw + L.ints);  // row -> unique index       (N)
@@ -142,7 +199,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   int* tiarr = pgene + MU;                                // distinct-time index of every unique row (MU)
   unsigned short* pairs = reinterpret_cast<unsigned short*>(tiarr + MU);  // lower-triangle pair p -> (r << 8) | c
 
-  for (int p = lane; p < P; p += 32) {
+  for (int p = tid; p < P; p += NT) {
     u[p] = a.u_io[bidx * P + p];
     const bool have = a.adam != nullptr && a.first_step > 0;
     am[p] = have ? a.adam[bidx * 2 * P + p] : 0.0;
@@ -161,20 +218,20 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     U = cache_i[0]; R = cache_i[1]; Tu = cache_i[2]; nD = cache_i[3]; fail = cache_i[4];
     const int* src = cache_i + 8;
     int* dst = reinterpret_cast<int*>(smem_raw + L.ints);
-    for (size_t i = lane; i < int_bytes / 4; i += 32) dst[i] = src[i];
+    for (size_t i = tid; i < int_bytes / 4; i += NT) dst[i] = src[i];
     const double* srcd = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(src) + int_bytes);
-    for (int i = lane; i < MT; i += 32) utime[i] = srcd[i];
-    for (int i = lane; i < MT * MT; i += 32) dval[i] = srcd[MT + i];
-    for (int i = lane; i < N; i += 32) ys[i] = a.y[i];
+    for (int i = tid; i < MT; i += NT) utime[i] = srcd[i];
+    for (int i = tid; i < MT * MT; i += NT) dval[i] = srcd[MT + i];
+    for (int i = tid; i < N; i += NT) ys[i] = a.y[i];
     ld = U | 1;
     npairs = U * (U + 1) / 2;
-    __syncwarp();
+    tsync<NW>();
   } else {
   // ---- once per launch: duplicate rows (class representative = first identical row), multiplicity ---------
   double* Xsm = S;   // X (N x 3) staged in shared memory for the O(N^2) scans below (S is not in use yet)
-  for (int i = lane; i < 3 * N; i += 32) Xsm[i] = a.X[i];
-  __syncwarp();
-  for (int i = lane; i < N; i += 32) {
+  for (int i = tid; i < 3 * N; i += NT) Xsm[i] = a.X[i];
+  tsync<NW>();
+  for (int i = tid; i < N; i += NT) {
     int rep = i;
     const double t0 = Xsm[3 * i], g0 = Xsm[3 * i + 1], f0 = Xsm[3 * i + 2];
     for (int j = 0; j < i; ++j)
@@ -185,32 +242,31 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     if (m > G - 1) m = G - 1;
     mflag[i] = 2 * m + (((int)f0) != 0 ? 1 : 0);
   }
-  __syncwarp();
+  tsync<NW>();
   int uniform = 1;
   {
-    int nrep = 0, cnt0 = 0;
-    for (int i = lane; i < N; i += 32) {
+    int nrep = 0;
+    for (int i = tid; i < N; i += NT) {
       const int rep = umap[i];
       if (rep == i) ++nrep;
       int cnt = 0;
       for (int j = 0; j < N; ++j) cnt += (umap[j] == rep);
-      if (i == 0) cnt0 = cnt;
       rows_of[i] = cnt;  // temporarily the multiplicity of row i's class
     }
-    __syncwarp();
-    for (int o = 16; o > 0; o >>= 1) nrep += __shfl_xor_sync(0xffffffffu, nrep, o);
-    cnt0 = __shfl_sync(0xffffffffu, cnt0, 0);
+    tsync<NW>();
+    nrep = tsum_int<NW>(nrep);
+    const int cnt0 = rows_of[0];
     int bad = 0;
-    for (int i = lane; i < N; i += 32) bad |= (rows_of[i] != cnt0);
-    bad = __any_sync(0xffffffffu, bad);
+    for (int i = tid; i < N; i += NT) bad |= (rows_of[i] != cnt0);
+    bad = tany<NW>(bad);
     U = nrep; R = cnt0; uniform = !bad;
     if (!uniform || R == 1) { U = N; R = 1; }
   }
-  __syncwarp();
+  tsync<NW>();
   if (U > MU) { U = 0; fail = -1; }  // caller's unique-row bound was wrong: refuse (info = -1)
   if (fail == 0) {
     // compact index of every class (ordered by representative row), its rows in ascending order
-    for (int i = lane; i < N; i += 32) {
+    for (int i = tid; i < N; i += NT) {
       int idx = i;
       if (R > 1) {
         const int rep = umap[i];
@@ -219,34 +275,33 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
       mflag[i] |= idx << 8;  // park the compact index above the 8 low bits (2 * m + flag < 256)
     }
-    __syncwarp();
-    for (int i = lane; i < N; i += 32) {
+    tsync<NW>();
+    for (int i = tid; i < N; i += NT) {
       const int idx = mflag[i] >> 8;
       int ord = 0;
       if (R > 1) for (int j = 0; j < i; ++j) ord += ((mflag[j] >> 8) == idx);
       rows_of[idx * R + ord] = i;
       if (ord == 0) urow[idx] = i;
     }
-    __syncwarp();
-    for (int i = lane; i < N; i += 32) { umap[i] = mflag[i] >> 8; mflag[i] &= 255; }
-    __syncwarp();
+    tsync<NW>();
+    for (int i = tid; i < N; i += NT) { umap[i] = mflag[i] >> 8; mflag[i] &= 255; }
+    tsync<NW>();
   }
   // ---- distinct times of the unique rows -> pts[].ti, utime[] ------------------------------------------------
   if (fail == 0) {
     int nfirst = 0;
-    for (int r = lane; r < U; r += 32) {
+    for (int r = tid; r < U; r += NT) {
       const double t = Xsm[3 * urow[r]];
       int first = 1;
       for (int j = 0; j < r; ++j) if (Xsm[3 * urow[j]] == t) { first = 0; break; }
       nfirst += first;
       pts[r].flag = first;  // temporary marker
     }
-    __syncwarp();
-    for (int o = 16; o > 0; o >>= 1) nfirst += __shfl_xor_sync(0xffffffffu, nfirst, o);
-    Tu = nfirst;
+    tsync<NW>();
+    Tu = tsum_int<NW>(nfirst);
     if (Tu > MT) { fail = -2; }  // caller's time-grid bound was wrong: refuse (info = -2)
     else {
-      for (int r = lane; r < U; r += 32) {
+      for (int r = tid; r < U; r += NT) {
         const double t = Xsm[3 * urow[r]];
         int idx = 0, rep = r;
         for (int j = 0; j < r; ++j) if (Xsm[3 * urow[j]] == t) { rep = j; break; }
@@ -255,13 +310,13 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
         if (rep == r) utime[idx] = t;
       }
     }
-    __syncwarp();
+    tsync<NW>();
   }
   if (fail != 0) { U = 0; Tu = 0; }
 
   ld = U | 1;
   npairs = U * (U + 1) / 2;
-  for (int p = lane; p < npairs; p += 32) {
+  for (int p = tid; p < npairs; p += NT) {
     int r, cc;
     wpair_decode(p, r, cc);
     pairs[p] = (unsigned short)((r << 8) | cc);
@@ -270,39 +325,37 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   // regular grid has 2 T - 1 distinct differences, not T^2 (compared bit for bit; an irregular grid keeps T^2)
   {
     const int TTp = Tu * Tu;
-    for (int p = lane; p < TTp; p += 32) {
+    for (int p = tid; p < TTp; p += NT) {
       const double dv = utime[p % Tu] - utime[p / Tu];   // pair p = ia * Tu + ib
       int first = p;
       for (int j = 0; j < p; ++j)
         if (utime[j % Tu] - utime[j / Tu] == dv) { first = j; break; }
       didx[p] = (unsigned short)first;  // temporarily the representative pair
     }
-    __syncwarp();
-    for (int p = lane; p < TTp; p += 32) {
+    tsync<NW>();
+    for (int p = tid; p < TTp; p += NT) {
       const int rep = didx[p];
       int idx = 0;
       for (int j = 0; j < rep; ++j) idx += (didx[j] == j);
       if (rep == p) dval[idx] = utime[p % Tu] - utime[p / Tu];
       Gd[p] = (double)idx;  // park the compact index (Gd is rebuilt every step)
     }
-    __syncwarp();
+    tsync<NW>();
     int cnt = 0;
-    for (int p = lane; p < TTp; p += 32) cnt += (didx[p] == p);
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    nD = cnt;
-    __syncwarp();
-    for (int p = lane; p < TTp; p += 32) didx[p] = (unsigned short)(int)Gd[p];
+    for (int p = tid; p < TTp; p += NT) cnt += (didx[p] == p);
+    nD = tsum_int<NW>(cnt);
+    tsync<NW>();
+    for (int p = tid; p < TTp; p += NT) didx[p] = (unsigned short)(int)Gd[p];
   }
-  __syncwarp();
+  tsync<NW>();
   if (cache_i && a.first_step == 0 && a.eval_val == nullptr && bidx == 0) {
-    __syncwarp();
-    if (lane == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; }
+    if (tid == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; }
     int* dst = cache_i + 8;
     const int* src = reinterpret_cast<const int*>(smem_raw + L.ints);
-    for (size_t i = lane; i < int_bytes / 4; i += 32) dst[i] = src[i];
+    for (size_t i = tid; i < int_bytes / 4; i += NT) dst[i] = src[i];
     double* dstd = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(dst) + int_bytes);
-    for (int i = lane; i < MT; i += 32) dstd[i] = utime[i];
-    for (int i = lane; i < MT * MT; i += 32) dstd[MT + i] = dval[i];
+    for (int i = tid; i < MT; i += NT) dstd[i] = utime[i];
+    for (int i = tid; i < MT * MT; i += NT) dstd[MT + i] = dval[i];
   }
   }
   const bool eval_only = a.eval_val != nullptr;
@@ -312,15 +365,20 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
   const int TT = Tu * Tu;
 
   int nstamp = 0;
+  int flip = 0;
+  (void)flip;
   // Adam bias corrections b^(step+1), carried multiplicatively (pow once per launch, not twice per step per leaf)
   double b1t = pow(a.b1, (double)a.first_step), b2t = pow(a.b2, (double)a.first_step);
-#define WSTAMP() do { if (a.stamps && bidx == 0 && sidx == 1 && lane == 0) a.stamps[nstamp++] = clock64(); } while (0)
+#define WSTAMP() do { if (a.stamps && bidx == 0 && sidx == 1 && tid == 0) a.stamps[nstamp++] = clock64(); } while (0)
+  // item e of a loop of n independent items goes to thread (base + e) % NT: consecutive loops of one stage land on
+  // different threads, so that a team spreads the transcendentals of a stage over all of its lanes
+#define TEAM_ITEMS(e, n, base) for (int e = (tid + NT - ((base) % NT)) % NT; e < (n); e += NT)
   for (int sidx = 0; sidx < nsteps; ++sidx) {
     const int step = a.first_step + sidx;
     WSTAMP();
     // ---- A. constrain -----------------------------------------------------------------------
-    for (int p = lane; p < P; p += 32) th[p] = (p == 3 * G) ? lfm_l_forward(u[p]) : lfm_softplus(u[p]);
-    __syncwarp();
+    for (int p = tid; p < P; p += NT) th[p] = (p == 3 * G) ? lfm_l_forward(u[p]) : lfm_softplus(u[p]);
+    tsync<NW>();
     const double l = th[3 * G], inv_l = 1.0 / l, sigma = th[3 * G + 1];
     const double c = a.jitter + sigma * sigma;
     WSTAMP();
@@ -333,8 +391,12 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     //   per time pair       : Gd = exp(-(t_ib - t_ia)^2 / l^2)
     //   per (b, difference) : erf or erfc of (t_ib - t_ia)/l - gamma_b
     // and per table entry (b, ia, ib) only products remain: A1 = Em[ib] Ep[ia], A1 g1 = g4_b Gd.
-    // |d_b t_i| > 600 (Ep would overflow) switches the whole warp to direct evaluation of A1 and g1.
+    // |d_b t_i| > 600 (Ep would overflow) switches the whole team to direct evaluation of A1 and g1.
+    // Stage 1: every item is ONE transcendental of (theta, l, times) alone; stage 2: the products.
     int slow = 0;
+    double zz = 0.0;
+    if constexpr (NW == 1) {
+    double* g3t = base + L.g3t;
     for (int m = lane; m < G; m += 32) {
       mu[m] = th[2 * G + m] / th[m];
       const double gam = th[m] * l * 0.5;
@@ -392,7 +454,6 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       pgene[r] = p.gene;
     }
     __syncwarp();
-    double zz = 0.0;
     for (int i = lane; i < N; i += 32) {
       const double zi = ys[i] - mu[mflag[i] >> 1] * (double)(mflag[i] & 1);
       zz += zi * zi;
@@ -406,9 +467,110 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
       q[r] = acc;
     }
+    } else {
+    {
+      int ibase = 0;
+      TEAM_ITEMS(e, 3 * G, ibase) {
+        const int m = e / 3, w = e - 3 * m;
+        const double gam = th[m] * l * 0.5;
+        if (w == 0) {
+          mu[m] = th[2 * G + m] / th[m];
+          gterm[4 * m + 0] = gam;
+          gterm[4 * m + 1] = exp(gam * gam);
+        } else if (w == 1) {
+          gterm[4 * m + 2] = erf(gam);
+        } else {
+          gterm[4 * m + 3] = LFM_TWO_OVER_SQRT_PI * exp(-gam * gam);
+        }
+      }
+      ibase += 3 * G;
+      TEAM_ITEMS(i, Tu, ibase) { const double tl = utime[i] * inv_l; Gt[i] = exp(-tl * tl); }
+      ibase += Tu;
+      TEAM_ITEMS(p, TT, ibase) {
+        const double dl = (utime[p % Tu] - utime[p / Tu]) * inv_l;
+        Gd[p] = exp(-dl * dl);
+      }
+      ibase += TT;
+      TEAM_ITEMS(e3i, 3 * G * Tu, ibase) {
+        const int e = e3i / 3, w = e3i - 3 * e;
+        const int b = e / Tu, i = e % Tu;
+        const double t = utime[i], d_b = th[b], gam = d_b * l * 0.5;
+        const double x2 = t * inv_l + gam, x3 = t * inv_l - gam;
+        if (w == 0) {
+          if (fabs(d_b * t) > 600.0) slow = 1;
+          Em[b * MT + i] = exp(-d_b * t);
+        } else if (w == 1) {   // erf(x2) and erfc(|x2|) from ONE call: whichever is small is evaluated, the other is 1 - it
+          const double ax = fabs(x2);
+          double ev, cv;
+          if (ax > 0.5) { cv = erfc(ax); ev = copysign(1.0 - cv, x2); }
+          else { ev = erf(x2); cv = 1.0 - fabs(ev); }
+          e2[b * MT + i] = ev;
+          c2[b * MT + i] = cv;
+        } else {
+          e3[b * MT + i] = erf(x3);
+        }
+      }
+      ibase += 3 * G * Tu;
+      // erf-family factor per (gene, distinct difference): erfc(|x1|) beyond 0.5, erf(x1) inside
+      TEAM_ITEMS(e, G * nD, ibase) {
+        const int b = e / nD, k = e % nD;
+        const double x1 = dval[k] * inv_l - th[b] * l * 0.5;
+        er1[b * MT * MT + k] = (fabs(x1) > 0.5) ? erfc(fabs(x1)) : erf(x1);
+      }
+    }
+    slow = tany<NW>(slow);   // (NW > 1: also the barrier between the stages)
+    tsync<NW>();
+    {
+      int ibase = 0;
+      TEAM_ITEMS(e, G * Tu, ibase) {
+        const int b = e / Tu, i = e % Tu;
+        const double em = Em[b * MT + i];
+        Ep[b * MT + i] = 1.0 / em;
+        g2[b * MT + i] = gterm[4 * b + 3] * Gt[i] * em;
+      }
+      ibase += G * Tu;
+      TEAM_ITEMS(r, U, ibase) {
+        const double* row3 = a.X + 3 * urow[r];
+        LfmPoint p;
+        p.t = row3[0];
+        p.gene = lfm_resolve_gene(row3[1], G);
+        p.flag = ((int)row3[2]) != 0;
+        p.ti = tiarr[r];
+        p.d = th[p.gene];
+        p.s = th[G + p.gene];
+        p.gam = gterm[4 * p.gene + 0];
+        p.eg2 = gterm[4 * p.gene + 1];
+        p.erfg = gterm[4 * p.gene + 2];
+        p.g4 = gterm[4 * p.gene + 3];
+        p.e = Em[p.gene * MT + p.ti];
+        p.q = e3[p.gene * MT + p.ti] + p.erfg;
+        p.g3 = slow ? LFM_TWO_OVER_SQRT_PI * exp(-(p.t * inv_l - p.gam) * (p.t * inv_l - p.gam))
+                    : p.g4 * Gt[p.ti] * (1.0 / p.e);
+        pts[r] = p;
+        pgene[r] = p.gene;
+      }
+      ibase += U;
+      TEAM_ITEMS(e, G * G, ibase) inv[e] = 1.0 / (th[e / G] + th[e % G]);
+      ibase += G * G;
+      TEAM_ITEMS(r, U, ibase) {
+        double acc = 0.0;
+        for (int k = 0; k < R; ++k) {
+          const int i = rows_of[r * R + k];
+          acc += ys[i] - mu[mflag[i] >> 1] * (double)(mflag[i] & 1);
+        }
+        q[r] = acc;
+      }
+    }
+    for (int i = tid; i < N; i += NT) {
+      const double zi = ys[i] - mu[mflag[i] >> 1] * (double)(mflag[i] & 1);
+      zz += zi * zi;
+    }
+    zz = tsum<NW>(zz, red, flip);
+    tsync<NW>();
+    }
     WSTAMP();
     // ---- C. time-grid tables: per (b, ia, ib) products of the factors above (tG1 holds A1 * g1) -----------------
-    for (int e = lane; e < G * TT; e += 32) {
+    for (int e = tid; e < G * TT; e += NT) {
       const int b = e / TT, r2 = e % TT, ia = r2 / Tu, ib = r2 % Tu;
       const double gam = gterm[4 * b];
       const double delta = utime[ib] - utime[ia];
@@ -437,7 +599,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       tA1R1[o] = A1 * R1;
       tG1[o] = A1g1;
     }
-    __syncwarp();
+    tsync<NW>();
     // h(pa, pb) from the shared-memory tables
     auto pair_terms = [&](const LfmPoint& pa, const LfmPoint& pb) {
       LfmPairTerms pt;
@@ -461,15 +623,15 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       if (r == cc) k += c;
       return k;
     };
-    for (int p = lane; p < npairs; p += 64) {
-      const bool two = p + 32 < npairs;
+    for (int p = tid; p < npairs; p += 2 * NT) {
+      const bool two = p + NT < npairs;
       int r0, c0, r1, c1;
       const double k0 = kxx_pair(p, r0, c0);
-      const double k1 = kxx_pair(two ? p + 32 : p, r1, c1);
+      const double k1 = kxx_pair(two ? p + NT : p, r1, c1);
       S[r0 * ld + c0] = k0;
       if (two) S[r1 * ld + c1] = k1;
     }
-    __syncwarp();
+    tsync<NW>();
     WSTAMP();
     // ---- E. M^-1 and log det M.  M = [[M11, M21^T], [M21, M22]] with M22 the trailing n2 = U - ex (<= 32) rows.
     // M22 is factorised AND inverted in registers (lane i owns row i of M22 / L22 and column i of W22 = L22^-1; the
@@ -478,7 +640,7 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     //   B = M22^-1 M21,  S11 = M11 - M21^T B,  X11 = S11^-1,  Y = B X11,
     //   M^-1 = [[X11, -Y^T], [-Y, M22^-1 + Y B^T]],   log det M = log det M22 + log det S11.
     double logdetM;
-    {
+    if constexpr (NW == 1) {
       const int n2 = U - ex;
       double am[32], yw[32], m21[WEX];
 #pragma unroll
@@ -669,31 +831,131 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
       __syncwarp();
       logdetM = ld22 + ld11;
+    } else {
+      // Team version: symmetric sweep operator over the whole U x U matrix (no pivoting: M is SPD).  Sweeping pivot k,
+      //   a_ij -= a_ik a_kj / d (i, j != k),   a_ik = a_ki = a_ik / d,   a_kk = -1 / d,      d = a_kk,
+      // keeps the matrix symmetric, and after all U pivots it holds -M^-1; the pivots are the squares of the
+      // Cholesky diagonal: log det M = sum log d_k, d_k <= 0 = not SPD.  Only the lower triangle is kept: thread
+      // (ti >= tj) owns the TS x TS tile (ti, tj) in registers (diagonal tiles complete).  Per pivot the owners of row
+      // k (tiles ti = k / TS) and of column k below them (tiles tj = k / TS) publish v = a_k. through shared memory --
+      // double buffered, ONE barrier per pivot -- and every tile applies a_ij -= v_i v_j / d.  The pivot loop is
+      // unrolled over k % TS so that every register index is a compile-time constant.
+      constexpr int TS = NW == 2 ? 4 : 3;   // 78 tiles of 3 x 3 on three warps (measured: better than 45 tiles of 4 x 4 on two)
+      constexpr int TG = GJN / TS, NTILE = TG * (TG + 1) / 2;
+      static_assert(GJN % TS == 0 && NTILE <= NT, "tile grid");
+      const bool active = tid < NTILE;
+      int ti, tj;
+      wpair_decode(active ? tid : 0, ti, tj);
+      const int r0 = ti * TS, c0 = tj * TS;
+      double at[TS][TS];
+#pragma unroll
+      for (int ai = 0; ai < TS; ++ai)
+#pragma unroll
+        for (int bi = 0; bi < TS; ++bi) {
+          const int i = r0 + ai, j = c0 + bi;
+          double v = (i == j) ? 1.0 : 0.0;
+          if (i < U && j < U) v = (i >= j) ? S[i * ld + j] : S[j * ld + i];
+          at[ai][bi] = v;
+        }
+      double mypiv = 1.0;
+      WSTAMP();
+      // (unrolled over two tile rows = 2 TS pivots: buffer parity and register indices are compile-time constants)
+      double* const dump = ring + 2 * GJN;
+      double* const vr[2] = {active ? ring + r0 : dump, active ? ring + GJN + r0 : dump};
+      double* const vc[2] = {active ? ring + c0 : dump, active ? ring + GJN + c0 : dump};
+      for (int k0 = 0; k0 < U; k0 += 2 * TS) {
+#pragma unroll
+        for (int s2 = 0; s2 < 2 * TS; ++s2) {
+          const int s = s2 % TS, par = s2 & 1;   // k0 is even: parity of k
+          const int k = k0 + s2;
+          const int kq = k0 / TS + s2 / TS;
+          if (k < U) {
+            const bool rowk = ti == kq, colk = tj == kq;
+            {   // publish without branches: non-owners store into the dump slots behind the two buffers
+              double* dst = rowk ? vc[par] : (colk ? vr[par] : dump);
+#pragma unroll
+              for (int x = 0; x < TS; ++x) dst[x] = rowk ? at[s][x] : at[x][s];
+            }
+            __syncthreads();
+            const double d = ring[par * GJN + k];
+            if (!(d > 0.0) && fail == 0) fail = k + 1;
+            if (tid == k) mypiv = d;
+            if (active) {
+              const double pinv = w_rcp(d);
+              double f[TS], g[TS];
+#pragma unroll
+              for (int ai = 0; ai < TS; ++ai) f[ai] = vr[par][ai];
+#pragma unroll
+              for (int bi = 0; bi < TS; ++bi) g[bi] = vc[par][bi] * pinv;
+#pragma unroll
+              for (int ai = 0; ai < TS; ++ai)
+#pragma unroll
+                for (int bi = 0; bi < TS; ++bi) at[ai][bi] = fma(-f[ai], g[bi], at[ai][bi]);
+              if (rowk) {
+#pragma unroll
+                for (int bi = 0; bi < TS; ++bi) at[s][bi] = g[bi];
+              }
+              if (colk) {
+#pragma unroll
+                for (int ai = 0; ai < TS; ++ai) at[ai][s] = f[ai] * pinv;
+                if (rowk) at[s][s] = -pinv;
+              }
+            }
+          }
+        }
+      }
+      WSTAMP(); WSTAMP(); WSTAMP();
+      __syncthreads();   // (S was only read above)
+      if (active) {
+#pragma unroll
+        for (int ai = 0; ai < TS; ++ai)
+#pragma unroll
+          for (int bi = 0; bi < TS; ++bi) {
+            const int i = r0 + ai, j = c0 + bi;
+            if (i < U && j < i) S[i * ld + j] = -at[ai][bi];
+            else if (i < U && j == i) sdiag[i] = -at[ai][bi];
+          }
+      }
+      logdetM = tsum<NW>((tid < U) ? log(mypiv) : 0.0, red, flip);
+      tsync<NW>();
     }
     WSTAMP();
     // ---- F. beta = M^-1 q (M^-1 symmetric: lower triangle + sdiag), K_u beta = (q - c beta) / R ---------------
     double qkb = 0.0, kbkb = 0.0;
-    for (int r = lane; r < U; r += 32) {
+    for (int r = tid; r < U; r += NT) {
       double acc = sdiag[r] * q[r];
       const double* rowr = S + r * ld;
-      for (int cc = 0; cc < r; ++cc) acc = fma(rowr[cc], q[cc], acc);
-      for (int cc = r + 1; cc < U; ++cc) acc = fma(S[cc * ld + r], q[cc], acc);
+      if (NW == 1) {
+        for (int cc = 0; cc < r; ++cc) acc = fma(rowr[cc], q[cc], acc);
+        for (int cc = r + 1; cc < U; ++cc) acc = fma(S[cc * ld + r], q[cc], acc);
+      } else {   // the team is latency bound here: two independent chains
+        double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        int cc = 0;
+        for (; cc + 2 <= r; cc += 2) { acc = fma(rowr[cc], q[cc], acc); acc1 = fma(rowr[cc + 1], q[cc + 1], acc1); }
+        if (cc < r) acc = fma(rowr[cc], q[cc], acc);
+        for (cc = r + 1; cc + 2 <= U; cc += 2) {
+          acc2 = fma(S[cc * ld + r], q[cc], acc2);
+          acc3 = fma(S[(cc + 1) * ld + r], q[cc + 1], acc3);
+        }
+        if (cc < U) acc2 = fma(S[cc * ld + r], q[cc], acc2);
+        acc = (acc + acc1) + (acc2 + acc3);
+      }
       beta[r] = acc;
       const double kbv = (q[r] - c * acc) / dR;
       kb[r] = kbv;
       qkb += q[r] * kbv;
       kbkb += kbv * kbv;
     }
-    qkb = wsum(qkb);
-    kbkb = wsum(kbkb);
+    qkb = tsum<NW>(qkb, red, flip);
+    kbkb = tsum<NW>(kbkb, red, flip);
     const double quad = (zz - qkb) / c;
     const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
-    __syncwarp();
+    tsync<NW>();
     WSTAMP();
     // ---- I. fused derivative contraction over the lower triangle of the unique pairs --------------------
     double dl_part = 0.0;
-    for (int r = lane; r < U; r += 32) dsum[r] = 0.0;
-    __syncwarp();
+    for (int r = tid; r < U; r += NT) dsum[r] = 0.0;
+    tsync<NW>();
     struct GradPair { int r, cc; double wr, wc, wl; };
     auto grad_pair = [&](int p) {
       GradPair g;
@@ -718,17 +980,17 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
     };
     // two pairs per lane and iteration (independent chains interleave); every pair reads and writes only its own
     // entries of S, so the loads of the second pair may precede the stores of the first
-    for (int p = lane; p < npairs; p += 64) {
-      const bool two = p + 32 < npairs;
+    for (int p = tid; p < npairs; p += 2 * NT) {
+      const bool two = p + NT < npairs;
       const GradPair g0 = grad_pair(p);
-      const GradPair g1 = grad_pair(two ? p + 32 : p);
+      const GradPair g1 = grad_pair(two ? p + NT : p);
       dl_part += g0.wl;
       grad_store(g0);
       if (two) { dl_part += g1.wl; grad_store(g1); }
     }
-    const double gl = wsum(dl_part);
-    __syncwarp();
-    for (int r = lane; r < U; r += 32) {  // per-point totals: full row sums, fixed order
+    const double gl = tsum<NW>(dl_part, red, flip);
+    tsync<NW>();
+    for (int r = tid; r < U; r += NT) {  // per-point totals: full row sums, fixed order
       const double* rp = S + r * ld;
       double s0 = dsum[r], s1 = 0.0;
       int cc = 0;
@@ -739,9 +1001,10 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       if (cc < U) s0 += (cc == r) ? 0.0 : rp[cc];
       dsum[r] = s0 + s1;
     }
-    __syncwarp();
+    tsync<NW>();
     WSTAMP();
     // ---- J. fold by gene; mean-function terms; sigma ---------------------------------------------
+    if constexpr (NW == 1) {
     for (int m = lane; m < G; m += 32) {   // one lane per gene: fixed summation order, no shuffles
       double gd = 0.0, gs = 0.0, asum = 0.0;
       for (int i = 0; i < U; ++i) {
@@ -759,23 +1022,55 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       gr[G + m] = gs / Sm;
       gr[2 * G + m] = -asum / D;
     }
+    } else {
+    {   // one half-warp per gene, lanes over the points, butterfly sums inside the half-warp (fixed order)
+      const int hw = tid >> 4, hl = tid & 15;
+      const unsigned hmask = 0xffffu << (16 * (hw & 1));
+      const double inv_c = 1.0 / c;
+      for (int m = hw; m < G; m += NT / 16) {
+        double gd = 0.0, gs = 0.0, asum = 0.0;
+        for (int i = hl; i < U; i += 16) {
+          if (pgene[i] == m) {
+            gd += dsum[i];
+            gs += 1.0 - c * sdiag[i] - beta[i] * kb[i];
+          }
+        }
+        for (int i = m * blk + hl; i < (m + 1) * blk; i += 16)
+          asum += ys[i] - mu[m] * (double)(mflag[i] & 1) - kb[umap[i]];
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          gd += __shfl_xor_sync(hmask, gd, o);
+          gs += __shfl_xor_sync(hmask, gs, o);
+          asum += __shfl_xor_sync(hmask, asum, o);
+        }
+        if (hl == 0) {
+          asum *= inv_c;
+          const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
+          const double rD = 1.0 / D;
+          gr[m] = gd + asum * Bm * rD * rD;
+          gr[G + m] = gs / Sm;
+          gr[2 * G + m] = -asum * rD;
+        }
+      }
+    }
+    }
     {
       double tr = 0.0;
-      for (int i = lane; i < U; i += 32) tr += sdiag[i];
-      tr = wsum(tr);
-      if (lane == 0) {
+      for (int i = tid; i < U; i += NT) tr += sdiag[i];
+      tr = tsum<NW>(tr, red, flip);
+      if (tid == 0) {
         const double trSinv = ((double)(N - U) + c * tr) / c;
         const double aa = (zz - 2.0 * qkb + dR * kbkb) / (c * c);
         gr[3 * G] = gl;
         gr[3 * G + 1] = sigma * (trSinv - aa);
       }
     }
-    __syncwarp();
+    tsync<NW>();
     WSTAMP();
     // ---- K. chain rule, Adam, hook ----------------------------------------------------------------
     const bool bad = fail != 0;
     b1t *= a.b1; b2t *= a.b2;
-    for (int p = lane; p < P; p += 32) {
+    for (int p = tid; p < P; p += NT) {
       const double sg = lfm_sigmoid(u[p]);
       const double jac = (p == 3 * G) ? (LFM_L_HIGH - LFM_L_LOW) * sg * (1.0 - sg) : sg;
       double g = gr[p] * jac;
@@ -797,16 +1092,16 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
     }
     WSTAMP();
-    if (lane == 0) {
+    if (tid == 0) {
       const double v = bad ? nan("") : nlml;
       if (eval_only) a.eval_val[bidx] = v;
       else if (a.hist) a.hist[bidx * a.ld_hist + step] = v;
     }
-    __syncwarp();
+    tsync<NW>();
   }
 
   if (!eval_only) {
-    for (int p = lane; p < P; p += 32) {
+    for (int p = tid; p < P; p += NT) {
       a.u_io[bidx * P + p] = u[p];
       if (a.adam) { a.adam[bidx * 2 * P + p] = am[p]; a.adam[bidx * 2 * P + P + p] = av[p]; }
       if (a.theta_out && a.first_step + a.steps >= a.total_steps) {
@@ -819,11 +1114,11 @@ __global__ void __launch_bounds__(32) lfm_batched_warp_kernel(BatchedArgs a, int
       }
     }
   }
-  if (lane == 0 && a.info) {
+  if (tid == 0 && a.info) {
     if (a.first_step == 0 || eval_only) a.info[bidx] = fail;
     else if (fail) a.info[bidx] = fail;
   }
-  if (lane == 0 && a.best_key && !eval_only && a.hist && a.steps > 0) {
+  if (tid == 0 && a.best_key && !eval_only && a.hist && a.steps > 0) {
     const double v = a.hist[bidx * a.ld_hist + a.first_step + a.steps - 1];
     if (v == v) atomicMin(a.best_key, lfm_loss_key(v));
   }
@@ -835,8 +1130,57 @@ size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
   return ((32 + (L.bytes - L.ints) + 8 * ((size_t)MT + (size_t)MT * MT)) + 15) & ~(size_t)15;
 }
 
-// Launch the warp-per-LFM kernel if the problem fits its limits; returns LFM_ERR_UNSUPPORTED otherwise
-// (the caller then runs the CTA-per-LFM kernel).
+template <int NW>
+static int team_launch(cudaStream_t st, const BatchedArgs& a, int time_grid, size_t bytes) {
+  static size_t conf = 0;
+  if (bytes > conf) {
+    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    conf = bytes;
+  }
+  lfm_batched_warp_kernel<NW><<<(unsigned)a.B, 32 * NW, bytes, st>>>(a, time_grid);
+  LFM_LAUNCHED(1);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
+template <int NW>
+static int team_slots(size_t bytes) {   // LFMs of team size NW resident on the device at a time
+  int dev = 0, sms = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lfm_batched_warp_kernel<NW>, 32 * NW, bytes) != cudaSuccess) return 0;
+  return sms * per_sm;
+}
+
+// Team size for a batch of B LFMs.  The kernel time is the sum over waves of resident LFMs of the time of one wave;
+// measured on B200 for the p53 shape (tools/team_probe.py, gpurun_out/team5.log), in units of one warp-per-LFM fit:
+//   team 1 (warp per LFM, 7 per SM):   1.00 alone, 1.11 with every slot taken -- no contention to speak of;
+//   team 4 (four warps per LFM, 4 per SM): 0.42 up to one LFM per SM, 0.71 with every slot taken (issue contention).
+// A full GPU keeps the warp-per-LFM kernel (most LFMs resident per wave); a shard that leaves lanes idle -- the
+// multi-GPU case -- spends them on a shorter dependent chain per optimiser step.  Team 8 never wins (2 CTAs per SM)
+// and is only reachable through LFM_BATCHED_TEAM = 1 | 4 | 8, which overrides the choice (debug / measurements).
+static int team_choice(int64_t B, size_t bytes) {
+  const char* env = getenv("LFM_BATCHED_TEAM");
+  const int forced = env ? atoi(env) : 0;
+  if (forced == 1 || forced == 4 || forced == 8) return forced;
+  static size_t cached_bytes = 0;
+  static int s1 = 0, s4 = 0, sms = 0;
+  if (bytes != cached_bytes) {
+    int dev = 0;
+    s1 = team_slots<1>(bytes); s4 = team_slots<4>(bytes);
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    cached_bytes = bytes;
+  }
+  if (s1 <= 0 || s4 <= 0 || sms <= 0) return 1;
+  auto wave1 = [&](int64_t n) { return 1.0 + 0.11 * (double)n / (double)s1; };
+  auto wave4 = [&](int64_t n) { return n <= sms || s4 <= sms ? 0.42 : 0.42 + 0.29 * (double)(n - sms) / (double)(s4 - sms); };
+  const double c1 = (double)(B / s1) * wave1(s1) + (B % s1 ? wave1(B % s1) : 0.0);
+  const double c4 = (double)(B / s4) * wave4(s4) + (B % s4 ? wave4(B % s4) : 0.0);
+  return c4 < c1 ? 4 : 1;
+}
+
+// Launch the warp- / team-per-LFM kernel if the problem fits its limits; returns LFM_ERR_UNSUPPORTED otherwise
+// (the caller then runs the CTA-per-LFM kernel of batched.cu).
 int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) {
   const int P = 3 * a.G + 2;
   const int MU = a.max_unique;
@@ -844,13 +1188,9 @@ int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid
   if ((long long)a.G * time_grid * time_grid > 2048 || a.G > 127) return LFM_ERR_UNSUPPORTED;
   const WarpLayout L = warp_layout(a.N, a.G, MU, time_grid);
   if (L.bytes > 100 * 1024) return LFM_ERR_UNSUPPORTED;
-  static size_t conf = 0;
-  if (L.bytes > conf) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-    conf = L.bytes;
+  switch (team_choice(a.B, L.bytes)) {
+    case 8: return team_launch<8>(st, a, time_grid, L.bytes);
+    case 4: return team_launch<4>(st, a, time_grid, L.bytes);
+    default: return team_launch<1>(st, a, time_grid, L.bytes);
   }
-  lfm_batched_warp_kernel<<<(unsigned)a.B, 32, L.bytes, st>>>(a, time_grid);
-  LFM_LAUNCHED(1);
-  LFM_CUDA_OK(cudaGetLastError());
-  return LFM_OK;
 }

@@ -184,10 +184,13 @@ def test_batched_eval(cuda, G, T, R):
         assert relerr(grad[b], g) < RTOL
 
 
+@pytest.mark.parametrize("team", [1, 4])
 @pytest.mark.parametrize("R,fix", [(1, True), (3, True), (1, False)])
-def test_batched_fit_matches_trainer(cuda, R, fix):
-    """150 Adam steps with the p21 hook (trainer.py:162-228), B restarts, split into chunks."""
+def test_batched_fit_matches_trainer(cuda, R, fix, team, monkeypatch):
+    """150 Adam steps with the p21 hook (trainer.py:162-228), B restarts, split into chunks; warp-per-LFM kernel
+    (register Cholesky) and four-warp team kernel (symmetric sweep)."""
     from dis_project_b200 import ops
+    monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
     G, T = 5, 7
     x, y, var, _ = o.synthetic_problem(G, T, R, seed=11)
     rng = np.random.default_rng(12)
@@ -206,11 +209,14 @@ def test_batched_fit_matches_trainer(cuda, R, fix):
         assert relerr(theta[b], th_ref) < 1e-7
 
 
+@pytest.mark.parametrize("team", [1, 4, 8])
 @pytest.mark.parametrize("G,T,R", [(5, 7, 1), (5, 7, 3), (3, 12, 2), (8, 8, 1), (2, 20, 3), (4, 8, 2), (2, 9, 1), (3, 11, 1), (3, 12, 1), (2, 17, 1)])
-def test_batched_warp_kernel_matches_cta_kernel(cuda, G, T, R):
-    """One-warp-per-LFM kernel (time-grid tables in shared memory) against the one-CTA-per-LFM kernel
-    (time_grid=0) and the oracle: evaluation and a 40-step fit, unique rows 16..64 (both lane mappings)."""
+def test_batched_warp_kernel_matches_cta_kernel(cuda, G, T, R, team, monkeypatch):
+    """Warp- / team-per-LFM kernel (time-grid tables in shared memory; team = warps per LFM) against the
+    one-CTA-per-LFM kernel (time_grid=0) and the oracle: evaluation and a 40-step fit, unique rows 16..64
+    (both lane mappings of the warp kernel, partial tile rows of the team sweep)."""
     from dis_project_b200 import ops
+    monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
     x, y, var, _ = o.synthetic_problem(G, T, R, seed=41)
     rng = np.random.default_rng(42)
     B = 5
@@ -237,3 +243,22 @@ def test_batched_warp_kernel_matches_cta_kernel(cuda, G, T, R):
     if G * T <= 36:
         vv, gg, ii = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G, time_grid=T - 1)
         assert np.all(ii.cpu().numpy() == -2) and np.all(np.isnan(vv.cpu().numpy()))
+
+
+@pytest.mark.parametrize("team", [1, 4, 8])
+def test_batched_not_positive_definite_is_reported(cuda, team, monkeypatch):
+    """A negative jitter that makes Sigma indefinite: info > 0 and NaN objective from every team size, and the
+    team size chosen from the batch size (no override) agrees with the forced ones on a healthy problem."""
+    from dis_project_b200 import ops
+    monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
+    G, T = 5, 7
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=5)
+    u0 = o.unconstrain(o.Params.reference_init(G).pack())
+    U = np.tile(u0, (3, 1))
+    val, grad, info = ops.batched_nlml_grad_unc(x, y, U, -5.0, G)
+    assert np.all(info.cpu().numpy() > 0) and np.all(np.isnan(val.cpu().numpy()))
+    v1, g1, i1 = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G)
+    monkeypatch.delenv("LFM_BATCHED_TEAM")
+    v0, g0, i0 = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G)
+    assert not i1.cpu().numpy().any() and not i0.cpu().numpy().any()
+    assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-12 and relerr(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-10
