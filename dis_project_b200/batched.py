@@ -37,6 +37,17 @@ def make_restarts(theta_init: np.ndarray, B: int, scale: float = 0.5, seed: int 
 
 
 LAST_TIMING = None
+_SIDE = {}
+
+
+def _side_stream(device):
+    """One side stream per device for the best-objective all-reduces (created once, not per fit)."""
+    import torch
+
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
@@ -127,67 +138,70 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     lo, hi = shard_bounds(B, rank, world)
     Xd = ops._rows3(X, "x")
     yd = ops._dev(y).reshape(-1)
-    st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters) if hi > lo else None
+    nchunks = max((num_iters + chunk - 1) // chunk, 1)
+    # behind the state of the shard, in the same allocation: [loss, id, theta] of the shard's winner (P + 2), one
+    # best-objective word per chunk, and the winners of every rank (world x (P + 2)) -- read back in ONE copy
+    n_extra = (P + 2) + nchunks + world * (P + 2)
+    st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters, extra_doubles=n_extra) if hi > lo else None
     if st is not None and not isinstance(X, torch.Tensor):
         st.unique_hint = ops.unique_rows(X)  # from the host copy: no device->host round trip
         st.time_grid = ops.distinct_times(X)
-    main = torch.cuda.current_stream()
-    side = torch.cuda.Stream()
-    ids = torch.arange(lo, hi, dtype=torch.float64, device=Xd.device)
-    nchunks = (num_iters + chunk - 1) // chunk
+    extra = st.extra if st is not None else torch.empty(n_extra, dtype=torch.float64, device=Xd.device)
+    packed = extra[:P + 2]
     # per chunk ONE device word: the fit kernel atomic-mins the order-preserving integer image of every loss into
     # it, the side stream MIN-all-reduces it across ranks -- no extra kernels, nothing the fit ever waits for
-    keys = torch.full((max(nchunks, 1),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=Xd.device)
+    keys = extra[P + 2:P + 2 + nchunks].view(torch.int64)
+    keys.fill_(torch.iinfo(torch.int64).max)
+    allp = extra[P + 2 + nchunks:].view(world, P + 2)
+    main = torch.cuda.current_stream()
+    multi = distributed and world > 1
+    side = _side_stream(Xd.device) if multi else None
     done = 0
     mark()
-    for c in range(nchunks):
+    for c in range((num_iters + chunk - 1) // chunk):
         steps = min(chunk, num_iters - done)
         if st is not None:
             ops.batched_fit_steps(st, Xd, yd, jitter, steps, lr=lr, b1=b1, b2=b2, eps=eps, fix_params=fix_params,
                                   steps_per_epoch=num_steps_per_epoch, best_key=keys[c:c + 1])
         done += steps
-        if distributed and world > 1:
+        if multi:
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev)
                 dist.all_reduce(keys[c:c + 1], op=dist.ReduceOp.MIN)
     mark()
-    main.wait_stream(side)
-    # ---- global winner: ONE all-gather of [loss, id, theta(P)] per rank, ONE device->host copy --------------
-    packed = torch.full((P + 2,), float("inf"), dtype=torch.float64, device=Xd.device)
-    packed[1] = -1.0
-    if st is not None and num_iters > 0:
-        col = st.hist[:, num_iters - 1]
-        col = torch.where(torch.isfinite(col), col, torch.full_like(col, float("inf")))
-        k = torch.argmin(col)
-        packed[0] = col[k]
-        packed[1] = ids[k]
-        packed[2:] = st.theta[k]
-    if distributed and world > 1:
+    if multi:
+        main.wait_stream(side)
+    # ---- global winner: one launch packs the shard's [loss, id, theta(P)], ONE all-gather, ONE device->host copy ------
+    have = st is not None and num_iters > 0
+    ops.batched_best(st.hist if have else None, num_iters - 1 if have else 0, st.theta if have else None, float(lo), packed)
+    gathered_on_host = None
+    if multi:
         if dist.get_backend() == "nccl":
-            allp = torch.empty((world, P + 2), dtype=torch.float64, device=Xd.device)
-            dist.all_gather_into_tensor(allp, packed)
-            allp = allp.cpu().numpy()
+            dist.all_gather_into_tensor(allp.view(-1), packed)
         else:  # gloo (CPU tests): gather on the host
             buf = [torch.empty(P + 2, dtype=torch.float64) for _ in range(world)]
             dist.all_gather(buf, packed.cpu())
-            allp = torch.stack(buf).numpy()
+            gathered_on_host = torch.stack(buf).numpy()
     else:
-        allp = packed.cpu().numpy()[None, :]
-    best = reduce_best_gathered(allp)
+        allp[0].copy_(packed)
+    if st is not None:
+        theta, hist, info, ex = ops.batched_to_host(st)
+    else:
+        theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
+        ex = extra.cpu().numpy()
+    allp_h = gathered_on_host if gathered_on_host is not None else ex[P + 2 + nchunks:].reshape(world, P + 2)
+    keys_h = ex[P + 2:P + 2 + nchunks].view(np.int64)[:(num_iters + chunk - 1) // chunk]
+    best = reduce_best_gathered(allp_h)
     best_id = int(best[1]) if np.isfinite(best[0]) else -1
     best_theta = None
     if best_id >= 0:
-        owner = int(np.flatnonzero((allp[:, 0] == best[0]) & (allp[:, 1] == best[1]))[0])
-        best_theta = allp[owner, 2:].copy()
-    if st is not None:
-        theta, hist, info = st.theta.cpu().numpy(), st.hist.cpu().numpy(), st.info.cpu().numpy()
-    else:
-        theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
+        owner = int(np.flatnonzero((allp_h[:, 0] == best[0]) & (allp_h[:, 1] == best[1]))[0])
+        best_theta = allp_h[owner, 2:].copy()
     mark()
     if timing:
         global LAST_TIMING
         LAST_TIMING = [round(1e3 * (b - a), 3) for a, b in zip(tmarks[:-1], tmarks[1:])]
     return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
-                            ops.loss_key_to_float(keys.cpu().numpy()))
+                            ops.loss_key_to_float(keys_h))

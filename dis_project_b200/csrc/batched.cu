@@ -484,6 +484,45 @@ extern "C" int lfm_debug_batched_stamps(lfm_stream_t stream, int64_t B, int64_t 
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 
+// ---- winner of a shard: arg-min over the finite losses of one history column, packed with its theta -------------
+__global__ void __launch_bounds__(256) lfm_batched_best_kernel(int64_t B, int P, const double* __restrict__ hist,
+                                                               int64_t ld_hist, int64_t col,
+                                                               const double* __restrict__ theta, double id0,
+                                                               double* __restrict__ out) {
+  __shared__ double sv[8];
+  __shared__ long long si[8];
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double best = inf;
+  long long arg = -1;
+  for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {   // ascending b per thread: strict < keeps the smallest index
+    const double v = hist[b * ld_hist + col];
+    if (v - v == 0.0 && v < best) { best = v; arg = b; }
+  }
+  auto better = [](double v, long long i, double w, long long j) { return i >= 0 && (j < 0 || v < w || (v == w && i < j)); };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long i = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (better(v, i, best, arg)) { best = v; arg = i; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = arg; }
+  __syncthreads();
+  best = sv[0]; arg = si[0];
+  for (int w = 1; w < 8; ++w)
+    if (better(sv[w], si[w], best, arg)) { best = sv[w]; arg = si[w]; }
+  if (threadIdx.x == 0) { out[0] = arg >= 0 ? best : inf; out[1] = arg >= 0 ? id0 + (double)arg : -1.0; }
+  for (int p = threadIdx.x; p < P; p += blockDim.x) out[2 + p] = arg >= 0 ? theta[arg * P + p] : inf;
+}
+extern "C" int lfm_batched_best(lfm_stream_t stream, int64_t B, int P, const double* hist, int64_t ld_hist, int64_t col,
+                                const double* theta, double id0, double* out_packed) {
+  if (B < 0 || P <= 0 || !out_packed || col < 0 || col >= ld_hist) return LFM_ERR_INVALID;
+  if (B > 0 && (!hist || !theta)) return LFM_ERR_INVALID;
+  lfm_batched_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(B, P, hist, ld_hist, col, theta, id0, out_packed);
+  LFM_LAUNCHED(1);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
+
 extern "C" size_t lfm_batched_structure_bytes(int64_t N, int G, int unique_rows_hint, int time_grid_hint) {
   if (N <= 0 || N > 128 || G <= 0) return 0;
   int MU = unique_rows_hint;

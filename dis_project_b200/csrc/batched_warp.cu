@@ -53,7 +53,7 @@ template <int NW> __device__ __forceinline__ void tsync() {
 template <int NW> __device__ __forceinline__ double tsum(double v, double* red, int& flip) {
   v = wsum(v);
   if (NW == 1) return v;
-  double* r = red + flip * NW;
+  double* r = red + flip * 2 * NW;
   flip ^= 1;
   if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
   __syncthreads();
@@ -80,6 +80,17 @@ template <int NW> __device__ __forceinline__ int tsum_int(int v) {
 template <int NW> __device__ __forceinline__ int tany(int v) {
   if (NW == 1) return __any_sync(0xffffffffu, v);
   return __syncthreads_or(v);
+}
+template <int NW> __device__ __forceinline__ void tsum2(double& v0, double& v1, double* red, int& flip) {
+  v0 = wsum(v0); v1 = wsum(v1);   // (two independent butterflies interleave)
+  if (NW == 1) return;
+  double* r = red + flip * 2 * NW;
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) { r[threadIdx.x >> 5] = v0; r[NW + (threadIdx.x >> 5)] = v1; }
+  __syncthreads();
+  v0 = r[0]; v1 = r[NW];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) { v0 += r[w]; v1 += r[NW + w]; }
 }
 // 1/x for x > 0 normal: MUFU.RCP64H seed + two Newton steps (branch free; on the pivot chain of the sweep)
 __device__ __forceinline__ double w_rcp(double x) {
@@ -117,7 +128,7 @@ __device__ __forceinline__ void w_h_core(const LfmPoint& pa, const LfmPoint& pb,
 
 struct WarpLayout {
   int ld;
-  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, red, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
+  size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, red, side, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
   size_t pts;       // byte offset
   size_t ints;      // byte offset: umap[N], urow[MU], rows_of[N], mflag[N]
   size_t bytes;
@@ -142,7 +153,8 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   L.th = take(P); L.u = take(P); L.gr = take(P); L.am = take(P); L.av = take(P); L.mu = take(G);
   L.ys = take(N);
   L.ring = take(4 * GJN);   // NW = 1: four pivot columns in flight; NW > 1: pivot row / column, double buffered
-  L.red = take(16);
+  L.red = take(32);
+  L.side = take((size_t)P + 4);   // team kernels: Jacobians of the bijectors + scalars prepared by the spare warp
   L.gterm = take(4 * (size_t)G);
   L.dval = take((size_t)MT * MT);
   {  // aliases inside S
@@ -186,6 +198,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   double* th = base + L.th; double* u = base + L.u; double* gr = base + L.gr; double* am = base + L.am;
   double* av = base + L.av; double* mu = base + L.mu; double* ys = base + L.ys; double* ring = base + L.ring;
   double* red = base + L.red;
+  double* side = base + L.side;
+  (void)side;
   double* Msm = base + L.Msm; double* Xs = base + L.Xs;
   double* gterm = base + L.gterm;
   double* Em = base + L.Em; double* Ep = base + L.Ep; double* e3 = base + L.e3;
@@ -840,9 +854,16 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       // k (tiles ti = k / TS) and of column k below them (tiles tj = k / TS) publish v = a_k. through shared memory --
       // double buffered, ONE barrier per pivot -- and every tile applies a_ij -= v_i v_j / d.  The pivot loop is
       // unrolled over k % TS so that every register index is a compile-time constant.
-      constexpr int TS = NW == 2 ? 4 : 3;   // 78 tiles of 3 x 3 on three warps (measured: better than 45 tiles of 4 x 4 on two)
+      // Warps 0-2 sweep (78 tiles of 3 x 3; their barrier is a named one for 96 threads); meanwhile warp 3 prepares
+      // what depends on theta alone and would otherwise sit on the serial tail of the step: the Jacobians of the
+      // bijectors, 1 / c, log c and the reciprocals of Adam's bias corrections (side[]).
+      static_assert(NW >= 4, "the team kernels need a spare warp next to the three sweep warps");
+      constexpr int TS = 3, SWEEP_THREADS = 96;
       constexpr int TG = GJN / TS, NTILE = TG * (TG + 1) / 2;
-      static_assert(GJN % TS == 0 && NTILE <= NT, "tile grid");
+      static_assert(GJN % TS == 0 && NTILE <= SWEEP_THREADS, "tile grid");
+      __shared__ int fail_sh;
+      double mypiv = 1.0;
+      if (tid < SWEEP_THREADS) {
       const bool active = tid < NTILE;
       int ti, tj;
       wpair_decode(active ? tid : 0, ti, tj);
@@ -857,7 +878,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
           if (i < U && j < U) v = (i >= j) ? S[i * ld + j] : S[j * ld + i];
           at[ai][bi] = v;
         }
-      double mypiv = 1.0;
+      // every sweep thread has read its part of S before any of them may store the result (the loop has >= 1 barrier
+      // for U >= 1; with U == 0 nothing is stored)
       WSTAMP();
       // (unrolled over two tile rows = 2 TS pivots: buffer parity and register indices are compile-time constants)
       double* const dump = ring + 2 * GJN;
@@ -876,7 +898,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
 #pragma unroll
               for (int x = 0; x < TS; ++x) dst[x] = rowk ? at[s][x] : at[x][s];
             }
-            __syncthreads();
+            asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_THREADS) : "memory");
             const double d = ring[par * GJN + k];
             if (!(d > 0.0) && fail == 0) fail = k + 1;
             if (tid == k) mypiv = d;
@@ -905,7 +927,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         }
       }
       WSTAMP(); WSTAMP(); WSTAMP();
-      __syncthreads();   // (S was only read above)
+      asm volatile("bar.sync 1, %0;" ::"n"(SWEEP_THREADS) : "memory");   // every tile is in registers: S may be overwritten
       if (active) {
 #pragma unroll
         for (int ai = 0; ai < TS; ++ai)
@@ -916,12 +938,28 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
             else if (i < U && j == i) sdiag[i] = -at[ai][bi];
           }
       }
+      if (tid == 0) fail_sh = fail;
+      } else if (wid == 3) {
+        for (int p = lane; p < P; p += 32) {
+          const double sg = lfm_sigmoid(u[p]);
+          side[4 + p] = (p == 3 * G) ? (LFM_L_HIGH - LFM_L_LOW) * sg * (1.0 - sg) : sg;
+        }
+        if (lane == 0) {
+          side[0] = 1.0 / c;
+          side[1] = log(c);
+          side[2] = 1.0 / (1.0 - b1t * a.b1);
+          side[3] = 1.0 / (1.0 - b2t * a.b2);
+        }
+      }
+      __syncthreads();
+      fail = fail_sh;
       logdetM = tsum<NW>((tid < U) ? log(mypiv) : 0.0, red, flip);
       tsync<NW>();
     }
     WSTAMP();
     // ---- F. beta = M^-1 q (M^-1 symmetric: lower triangle + sdiag), K_u beta = (q - c beta) / R ---------------
     double qkb = 0.0, kbkb = 0.0;
+    const double inv_R = 1.0 / dR;   // (loop invariant; the team kernels multiply, the warp kernel divides as before)
     for (int r = tid; r < U; r += NT) {
       double acc = sdiag[r] * q[r];
       const double* rowr = S + r * ld;
@@ -941,15 +979,15 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         acc = (acc + acc1) + (acc2 + acc3);
       }
       beta[r] = acc;
-      const double kbv = (q[r] - c * acc) / dR;
+      const double kbv = (NW == 1) ? (q[r] - c * acc) / dR : (q[r] - c * acc) * inv_R;
       kb[r] = kbv;
       qkb += q[r] * kbv;
       kbkb += kbv * kbv;
     }
-    qkb = tsum<NW>(qkb, red, flip);
-    kbkb = tsum<NW>(kbkb, red, flip);
-    const double quad = (zz - qkb) / c;
-    const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * log(c) + logdetM + quad);
+    tsum2<NW>(qkb, kbkb, red, flip);
+    const double inv_c = (NW == 1) ? 1.0 / c : side[0];
+    const double quad = (NW == 1) ? (zz - qkb) / c : (zz - qkb) * inv_c;
+    const double nlml = 0.5 * ((double)N * LFM_LOG_2PI + (double)(N - U) * ((NW == 1) ? log(c) : side[1]) + logdetM + quad);
     tsync<NW>();
     WSTAMP();
     // ---- I. fused derivative contraction over the lower triangle of the unique pairs --------------------
@@ -1026,7 +1064,6 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     {   // one half-warp per gene, lanes over the points, butterfly sums inside the half-warp (fixed order)
       const int hw = tid >> 4, hl = tid & 15;
       const unsigned hmask = 0xffffu << (16 * (hw & 1));
-      const double inv_c = 1.0 / c;
       for (int m = hw; m < G; m += NT / 16) {
         double gd = 0.0, gs = 0.0, asum = 0.0;
         for (int i = hl; i < U; i += 16) {
@@ -1059,8 +1096,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       for (int i = tid; i < U; i += NT) tr += sdiag[i];
       tr = tsum<NW>(tr, red, flip);
       if (tid == 0) {
-        const double trSinv = ((double)(N - U) + c * tr) / c;
-        const double aa = (zz - 2.0 * qkb + dR * kbkb) / (c * c);
+        const double trSinv = (NW == 1) ? ((double)(N - U) + c * tr) / c : ((double)(N - U) + c * tr) * inv_c;
+        const double aa = (NW == 1) ? (zz - 2.0 * qkb + dR * kbkb) / (c * c) : (zz - 2.0 * qkb + dR * kbkb) * (inv_c * inv_c);
         gr[3 * G] = gl;
         gr[3 * G + 1] = sigma * (trSinv - aa);
       }
@@ -1071,8 +1108,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     const bool bad = fail != 0;
     b1t *= a.b1; b2t *= a.b2;
     for (int p = tid; p < P; p += NT) {
-      const double sg = lfm_sigmoid(u[p]);
-      const double jac = (p == 3 * G) ? (LFM_L_HIGH - LFM_L_LOW) * sg * (1.0 - sg) : sg;
+      double jac;
+      if (NW == 1) {
+        const double sg = lfm_sigmoid(u[p]);
+        jac = (p == 3 * G) ? (LFM_L_HIGH - LFM_L_LOW) * sg * (1.0 - sg) : sg;
+      } else {
+        jac = side[4 + p];
+      }
       double g = gr[p] * jac;
       if (bad) g = nan("");
       if (eval_only) {
@@ -1081,8 +1123,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         const double m1 = a.b1 * am[p] + (1.0 - a.b1) * g;
         const double v1 = a.b2 * av[p] + (1.0 - a.b2) * g * g;
         am[p] = m1; av[p] = v1;
-        const double mhat = m1 / (1.0 - b1t);
-        const double vhat = v1 / (1.0 - b2t);
+        const double mhat = (NW == 1) ? m1 / (1.0 - b1t) : m1 * side[2];
+        const double vhat = (NW == 1) ? v1 / (1.0 - b2t) : v1 * side[3];
         double un = u[p] - a.lr * mhat / (sqrt(vhat) + a.eps);
         if (a.fix_params && (step % a.steps_per_epoch) == 0 && G > 3) {
           if (p == G + 3) un = 1.0;  // true_s[3]  (trainer.py:152, unconstrained space: SURVEY Q5)

@@ -331,7 +331,7 @@ def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Opt
 class BatchedFitState:
     """Device-resident state of B independent fits (iterates, Adam moments, loss history)."""
 
-    def __init__(self, theta0, G: int, total_steps: int):
+    def __init__(self, theta0, G: int, total_steps: int, extra_doubles: int = 0):
         theta0 = _dev(theta0)
         self.G, self.P = G, 3 * G + 2
         if theta0.ndim != 2 or theta0.shape[1] != self.P:
@@ -341,13 +341,57 @@ class BatchedFitState:
         dev = theta0.device
         self.u = unconstrain(theta0, G)  # trainer.py:75
         self.adam = torch.zeros((self.B, 2 * self.P), dtype=F64, device=dev)
-        self.hist = torch.full((self.B, max(1, self.total_steps)), float("nan"), dtype=F64, device=dev)
-        self.theta = torch.empty((self.B, self.P), dtype=F64, device=dev)
-        self.info = torch.zeros(self.B, dtype=torch.int32, device=dev)
+        # everything a caller reads back lives in ONE device allocation (theta | hist | info | extra), so that the
+        # results of a fit cross PCIe as one copy (to_host)
+        S = max(1, self.total_steps)
+        n_theta, n_hist, n_info = self.B * self.P, self.B * S, (self.B + 1) // 2
+        self._cuts = (n_theta, n_theta + n_hist, n_theta + n_hist + n_info)
+        self.blob = torch.empty(self._cuts[2] + int(extra_doubles), dtype=F64, device=dev)
+        self.theta = self.blob[:n_theta].view(self.B, self.P)
+        self.hist = self.blob[n_theta:self._cuts[1]].view(self.B, S)
+        self.hist.fill_(float("nan"))
+        self.info = self.blob[self._cuts[1]:self._cuts[2]].view(torch.int32)[:self.B]
+        self.info.zero_()
+        self.extra = self.blob[self._cuts[2]:]
         self.step = 0
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
         self.struct_cache = None  # device bytes that carry the structure of X from the first launch to the later ones
+
+
+_PINNED: Dict[int, torch.Tensor] = {}
+
+
+def _pinned(n: int) -> torch.Tensor:
+    buf = _PINNED.get(n)
+    if buf is None:
+        buf = torch.empty(n, dtype=F64, pin_memory=True)
+        _PINNED[n] = buf
+    return buf
+
+
+def batched_to_host(state: "BatchedFitState"):
+    """(theta, hist, info, extra) of a fit as numpy arrays: ONE device->host copy through a cached pinned buffer."""
+    host = _pinned(state.blob.numel())
+    host.copy_(state.blob, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    a = host.numpy()
+    c0, c1, c2 = state._cuts
+    theta = a[:c0].reshape(state.B, state.P).copy()
+    hist = a[c0:c1].reshape(state.B, -1).copy()
+    info = a[c1:c2].view("int32")[:state.B].copy()
+    return theta, hist, info, a[c2:].copy()
+
+
+def batched_best(hist: Optional[torch.Tensor], col: int, theta: Optional[torch.Tensor], id0: float,
+                 out: torch.Tensor) -> None:
+    """out (P + 2) = [loss, id0 + b, theta_b] of the restart b with the smallest finite hist[b, col] (one launch)."""
+    P = out.numel() - 2
+    B = 0 if hist is None else hist.shape[0]
+    _lib.check(_lib.lib().lfm_batched_best(_stream(), B, P, hist.data_ptr() if B else None,
+                                           hist.stride(0) if B else max(col + 1, 1), int(col),
+                                           theta.data_ptr() if B else None, float(id0), out.data_ptr()),
+               "lfm_batched_best")
 
 
 def loss_key_to_float(keys):

@@ -190,6 +190,12 @@ size_t lfm_batched_structure_bytes(int64_t N, int G, int unique_rows_hint, int t
  * chunk of steps is ONE integer MIN all-reduce of that word across ranks (north_star: "one NCCL allreduce of
  * best-objective ... state per step"). */
 
+/* Winner of a shard after a fit: out_packed (P + 2 doubles) = [loss, id, theta(P)] of the LFM with the smallest FINITE
+ * hist[b * ld_hist + col] (ties: smallest b), id = id0 + b; [inf, -1, inf...] when no loss is finite.  One launch of
+ * one CTA; what multi_start_fit all-gathers across ranks (P + 2 doubles per rank). */
+int lfm_batched_best(lfm_stream_t stream, int64_t B, int P, const double* hist, int64_t ld_hist, int64_t col,
+                     const double* theta, double id0, double* out_packed);
+
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */
 

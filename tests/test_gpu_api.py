@@ -156,6 +156,28 @@ def test_multi_start_single_rank(cuda):
     assert res.best_trace[-1] == res.best_loss      # the atomicMin key of the last chunk IS the winner's loss, bit for bit
 
 
+def test_batched_best_packs_the_winner(cuda):
+    """lfm_batched_best: arg-min over the FINITE entries of one history column (ties -> smallest index), packed with
+    the winner's theta; empty shards and all-NaN columns give [inf, -1]."""
+    from dis_project_b200 import ops
+    rng = np.random.default_rng(3)
+    B, P, S = 1000, 17, 5
+    hist = rng.standard_normal((B, S))
+    hist[rng.integers(0, B, 50), 3] = np.nan
+    hist[[700, 123], 3] = hist[:, 3][np.isfinite(hist[:, 3])].min() - 1.0   # a tie: index 123 wins
+    hist[5, 3] = -np.inf                                                     # not finite: never wins
+    theta = rng.standard_normal((B, P))
+    out = torch.empty(P + 2, dtype=torch.float64, device="cuda")
+    ops.batched_best(torch.as_tensor(hist).cuda(), 3, torch.as_tensor(theta).cuda(), 4000.0, out)
+    got = out.cpu().numpy()
+    assert got[0] == hist[123, 3] and got[1] == 4123.0 and np.array_equal(got[2:], theta[123])
+    ops.batched_best(torch.full((7, S), float("nan"), dtype=torch.float64, device="cuda"), 0,
+                     torch.zeros((7, P), dtype=torch.float64, device="cuda"), 0.0, out)
+    assert out[0].item() == np.inf and out[1].item() == -1.0
+    ops.batched_best(None, 0, None, 0.0, out)
+    assert out[0].item() == np.inf and out[1].item() == -1.0
+
+
 def test_config2_full_size_parity(cuda):
     """BASELINE config 2 (N=4000) against the oracle on the host cores."""
     from dis_project_b200 import ops
