@@ -312,7 +312,8 @@ def main():
         data = JaxP53Data.synthetic()
         xb, yb, _ = dataset_3d(data)
         TH = make_restarts(np.concatenate([np.full(5, 0.4), np.ones(5), np.full(5, 0.05), [2.5, 1.0]]), 4096)
-        multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=10, chunk=5)  # warm-up at full size (allocator, NCCL)
+        # warm-up at full size and full length (allocator, pinned read-back buffer, NCCL, kernel attributes)
+        multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, chunk=10)
         barrier()
         t0 = time.perf_counter()
         res = multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, chunk=10)
@@ -320,7 +321,12 @@ def main():
         secondary["batched"] = {"workload": "config 4: 4096 p53-shaped restarts (N=105, G=5) x 150 Adam steps, sharded "
                                             f"over {world} GPU(s), best-objective all-reduce every 10 steps",
                                 "restarts_per_s": 4096 / bt, "seconds": bt, "best_nlml": res.best_loss,
-                                "evals_per_s": 4096 * 150 / bt}
+                                "evals_per_s": 4096 * 150 / bt,
+                                "restarts_per_gpu": res.hi - res.lo,
+                                "warps_per_lfm": int(_lib.lib().lfm_batched_team_size(
+                                    res.hi - res.lo, xb.shape[0], 5, ops.unique_rows(xb), ops.distinct_times(xb))),
+                                "timed": "host wall clock around multi_start_fit (host buffers in, numpy results "
+                                         "out, barrier before, max over ranks)"}
         if rank == 0:
             try:
                 X3h, y3h, th3h = _Inputs.make_problem(G_C3, T_C3)

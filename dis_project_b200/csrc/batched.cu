@@ -484,6 +484,13 @@ extern "C" int lfm_debug_batched_stamps(lfm_stream_t stream, int64_t B, int64_t 
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 
+extern "C" int lfm_batched_team_size(int64_t B, int64_t N, int G, int unique_rows_hint, int time_grid_hint) {
+  if (B <= 0 || N <= 0 || N > 128 || G <= 0) return 0;
+  int MU = unique_rows_hint;
+  if (MU <= 0 || MU > N) MU = (int)N;
+  return lfm_batched_warp_team(B, (int)N, G, MU, time_grid_hint);
+}
+
 // ---- winner of a shard: arg-min over the finite losses of one history column, packed with its theta -------------
 __global__ void __launch_bounds__(256) lfm_batched_best_kernel(int64_t B, int P, const double* __restrict__ hist,
                                                                int64_t ld_hist, int64_t col,

@@ -38,3 +38,4 @@ __host__ __device__ inline long long lfm_loss_key(double v) {
 // batched_warp.cu: launches the warp-per-LFM kernel when the problem fits its limits, else LFM_ERR_UNSUPPORTED
 int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid);
 size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT);
+int lfm_batched_warp_team(int64_t B, int N, int G, int MU, int time_grid);

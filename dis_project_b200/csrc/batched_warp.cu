@@ -1236,3 +1236,14 @@ int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid
     default: return team_launch<1>(st, a, time_grid, L.bytes);
   }
 }
+
+// Team size lfm_batched_warp_launch would use for a batch of B LFMs of this shape on the current device (1, 4 or 8 warps
+// per LFM); 0 when the shape is outside the limits of this file (the CTA-per-LFM kernel of batched.cu runs instead).
+int lfm_batched_warp_team(int64_t B, int N, int G, int MU, int time_grid) {
+  const int P = 3 * G + 2;
+  if (time_grid <= 0 || MU <= 0 || MU > 32 + WEX || N > 128 || P > 64) return 0;
+  if ((long long)G * time_grid * time_grid > 2048 || G > 127) return 0;
+  const WarpLayout L = warp_layout(N, G, MU, time_grid);
+  if (L.bytes > 100 * 1024) return 0;
+  return team_choice(B, L.bytes);
+}

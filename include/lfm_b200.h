@@ -190,6 +190,12 @@ size_t lfm_batched_structure_bytes(int64_t N, int G, int unique_rows_hint, int t
  * chunk of steps is ONE integer MIN all-reduce of that word across ranks (north_star: "one NCCL allreduce of
  * best-objective ... state per step"). */
 
+/* Warps per LFM the batched entry points use for a batch of B LFMs of this shape on the current device: 1 (one warp per
+ * LFM, register-resident Cholesky; a full GPU), 4 (a team of four warps per LFM, symmetric sweep in register tiles;
+ * shards that leave SMs idle, e.g. 4096 restarts over 8 GPUs), or 0 when the shape runs the CTA-per-LFM kernel.
+ * LFM_BATCHED_TEAM = 1 | 4 | 8 in the environment overrides the choice (measurements). */
+int lfm_batched_team_size(int64_t B, int64_t N, int G, int unique_rows_hint, int time_grid_hint);
+
 /* Winner of a shard after a fit: out_packed (P + 2 doubles) = [loss, id, theta(P)] of the LFM with the smallest FINITE
  * hist[b * ld_hist + col] (ties: smallest b), id = id0 + b; [inf, -1, inf...] when no loss is finite.  One launch of
  * one CTA; what multi_start_fit all-gathers across ranks (P + 2 doubles per rank). */

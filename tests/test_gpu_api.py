@@ -156,6 +156,18 @@ def test_multi_start_single_rank(cuda):
     assert res.best_trace[-1] == res.best_loss      # the atomicMin key of the last chunk IS the winner's loss, bit for bit
 
 
+def test_batched_team_size_follows_the_batch(cuda):
+    """lfm_batched_team_size: a shard that leaves SMs idle gets four warps per LFM, a full GPU one warp per LFM,
+    shapes outside the warp / team kernels report 0 (CTA-per-LFM kernel)."""
+    from dis_project_b200 import _lib
+    lib = _lib.lib()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    assert lib.lfm_batched_team_size(sms, 105, 5, 35, 7) == 4
+    assert lib.lfm_batched_team_size(64 * sms, 105, 5, 35, 7) == 1
+    assert lib.lfm_batched_team_size(512, 105, 5, 105, 7) == 0      # 105 unique rows: beyond the register / tile kernels
+    assert lib.lfm_batched_team_size(512, 105, 5, 35, 0) == 0       # no time grid
+
+
 def test_batched_best_packs_the_winner(cuda):
     """lfm_batched_best: arg-min over the FINITE entries of one history column (ties -> smallest index), packed with
     the winner's theta; empty shards and all-NaN columns give [inf, -1]."""
