@@ -640,10 +640,15 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     for (int p = tid; p < npairs; p += 2 * NT) {
       const bool two = p + NT < npairs;
       int r0, c0, r1, c1;
-      const double k0 = kxx_pair(p, r0, c0);
-      const double k1 = kxx_pair(two ? p + NT : p, r1, c1);
-      S[r0 * ld + c0] = k0;
-      if (two) S[r1 * ld + c1] = k1;
+      if (NW == 1 || two) {   // (warp kernel: the lone pair of the last iteration is evaluated twice rather than branched on)
+        const double k0 = kxx_pair(p, r0, c0);
+        const double k1 = kxx_pair(two ? p + NT : p, r1, c1);
+        S[r0 * ld + c0] = k0;
+        if (two) S[r1 * ld + c1] = k1;
+      } else {                // (team: under issue contention the duplicate would cost 16 % of the phase)
+        const double k0 = kxx_pair(p, r0, c0);
+        S[r0 * ld + c0] = k0;
+      }
     }
     tsync<NW>();
     WSTAMP();
@@ -653,7 +658,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     // Schur complement, every per-lane quantity in registers with compile-time indices:
     //   B = M22^-1 M21,  S11 = M11 - M21^T B,  X11 = S11^-1,  Y = B X11,
     //   M^-1 = [[X11, -Y^T], [-Y, M22^-1 + Y B^T]],   log det M = log det M22 + log det S11.
-    double logdetM;
+    double logdetM, tr_team = 0.0;
+    (void)tr_team;
     if constexpr (NW == 1) {
       const int n2 = U - ex;
       double am[32], yw[32], m21[WEX];
@@ -953,7 +959,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       }
       __syncthreads();
       fail = fail_sh;
-      logdetM = tsum<NW>((tid < U) ? log(mypiv) : 0.0, red, flip);
+      {   // log det M and tr M^-1 in one team sum (sdiag was stored before the barrier above)
+        double ldp = (tid < U) ? log(mypiv) : 0.0, trp = (tid < U) ? sdiag[tid] : 0.0;
+        tsum2<NW>(ldp, trp, red, flip);
+        logdetM = ldp;
+        tr_team = trp;
+      }
       tsync<NW>();
     }
     WSTAMP();
@@ -1020,11 +1031,17 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     // entries of S, so the loads of the second pair may precede the stores of the first
     for (int p = tid; p < npairs; p += 2 * NT) {
       const bool two = p + NT < npairs;
-      const GradPair g0 = grad_pair(p);
-      const GradPair g1 = grad_pair(two ? p + NT : p);
-      dl_part += g0.wl;
-      grad_store(g0);
-      if (two) { dl_part += g1.wl; grad_store(g1); }
+      if (NW == 1 || two) {
+        const GradPair g0 = grad_pair(p);
+        const GradPair g1 = grad_pair(two ? p + NT : p);
+        dl_part += g0.wl;
+        grad_store(g0);
+        if (two) { dl_part += g1.wl; grad_store(g1); }
+      } else {
+        const GradPair g0 = grad_pair(p);
+        dl_part += g0.wl;
+        grad_store(g0);
+      }
     }
     const double gl = tsum<NW>(dl_part, red, flip);
     tsync<NW>();
@@ -1093,8 +1110,12 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     }
     {
       double tr = 0.0;
-      for (int i = tid; i < U; i += NT) tr += sdiag[i];
-      tr = tsum<NW>(tr, red, flip);
+      if constexpr (NW == 1) {
+        for (int i = tid; i < U; i += NT) tr += sdiag[i];
+        tr = tsum<NW>(tr, red, flip);
+      } else {
+        tr = tr_team;
+      }
       if (tid == 0) {
         const double trSinv = (NW == 1) ? ((double)(N - U) + c * tr) / c : ((double)(N - U) + c * tr) * inv_c;
         const double aa = (NW == 1) ? (zz - 2.0 * qkb + dR * kbkb) / (c * c) : (zz - 2.0 * qkb + dR * kbkb) * (inv_c * inv_c);
