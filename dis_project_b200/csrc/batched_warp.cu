@@ -126,14 +126,40 @@ __device__ __forceinline__ void w_h_core(const LfmPoint& pa, const LfmPoint& pb,
   }
 }
 
+// Stage-1 work items of an optimiser step (team kernels): every item is ONE transcendental of (theta, l, times).
+// Flat item f -> (kind << 24) | (gene << 16) | index:
+//   kind 0 / 1 / 2 : per gene: gamma and exp(gamma^2) / erf(gamma) / 2/sqrt(pi) exp(-gamma^2)
+//   kind 3         : per time i: exp(-t_i^2 / l^2)
+//   kind 4         : per time pair p: exp(-(t_ib - t_ia)^2 / l^2)
+//   kind 5 / 6 / 7 : per (gene, time i): exp(-d t) / erf and erfc of t/l + gamma / erf(t/l - gamma)
+//   kind 8         : per (gene, distinct time difference k): erf or erfc of dt/l - gamma
+__device__ __forceinline__ int stage1_items(int G, int Tu, int nD) { return 3 * G + Tu + Tu * Tu + 3 * G * Tu + G * nD; }
+__device__ __forceinline__ unsigned stage1_decode(int f, int G, int Tu, int nD) {
+  if (f < 3 * G) { const int m = f / 3; return ((unsigned)(f - 3 * m) << 24) | ((unsigned)m << 16); }
+  f -= 3 * G;
+  if (f < Tu) return (3u << 24) | (unsigned)f;
+  f -= Tu;
+  if (f < Tu * Tu) return (4u << 24) | (unsigned)f;
+  f -= Tu * Tu;
+  if (f < 3 * G * Tu) {
+    const int e = f / 3, w = f - 3 * e, b = e / Tu;
+    return ((unsigned)(5 + w) << 24) | ((unsigned)b << 16) | (unsigned)(e - b * Tu);
+  }
+  f -= 3 * G * Tu;
+  const int b = f / nD;
+  return (8u << 24) | ((unsigned)b << 16) | (unsigned)(f - b * nD);
+}
+
 struct WarpLayout {
   int ld;
   size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, red, side, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
   size_t pts;       // byte offset
   size_t ints;      // byte offset: umap[N], urow[MU], rows_of[N], mflag[N]
+  size_t itab;      // byte offset (inside the integer region, so that it travels with the structure cache)
   size_t bytes;
 };
-__host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) {
+#define ITAB 512          // stage-1 items of a step whose decoding is tabulated once per fit (team kernels)
+__host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT, bool team) {
   WarpLayout L;
   const int P = 3 * G + 2;
   L.ld = MU | 1;
@@ -173,6 +199,9 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT) 
   b += sizeof(int) * ((size_t)3 * N + 3 * MU);
   b += sizeof(unsigned short) * ((size_t)MU * (MU + 1) / 2 + 2);  // pair table
   b += sizeof(unsigned short) * ((size_t)MT * MT + 2);             // distinct time-difference index of every time pair
+  b = (b + 3) & ~(size_t)3;
+  L.itab = b;
+  if (team) b += sizeof(unsigned) * ITAB;                          // decoded stage-1 items (kind, gene, index)
   L.bytes = (b + 15) & ~(size_t)15;
   return L;
 }
@@ -187,7 +216,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   (void)wid;
   const int64_t bidx = blockIdx.x;
   const int MU = a.max_unique;
-  const WarpLayout L = warp_layout(N, G, MU, MT);
+  const WarpLayout L = warp_layout(N, G, MU, MT, NW > 1);
   double* base = reinterpret_cast<double*>(smem_raw);
   double* S = base + L.S;
   double* tA1R1 = base + L.tA1R1; double* tA1 = base + L.tA1; double* tG1 = base + L.tG1;
@@ -212,6 +241,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   int* pgene = mflag + N;                                 // gene of every unique row (MU)
   int* tiarr = pgene + MU;                                // distinct-time index of every unique row (MU)
   unsigned short* pairs = reinterpret_cast<unsigned short*>(tiarr + MU);  // lower-triangle pair p -> (r << 8) | c
+  unsigned* itab = reinterpret_cast<unsigned*>(smem_raw + L.itab);
+  (void)itab;
 
   for (int p = tid; p < P; p += NT) {
     u[p] = a.u_io[bidx * P + p];
@@ -362,6 +393,11 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     for (int p = tid; p < TTp; p += NT) didx[p] = (unsigned short)(int)Gd[p];
   }
   tsync<NW>();
+  if constexpr (NW > 1) {
+    const int nitems = stage1_items(G, Tu, nD);
+    for (int f = tid; f < ITAB && f < nitems; f += NT) itab[f] = stage1_decode(f, G, Tu, nD);
+    tsync<NW>();
+  }
   if (cache_i && a.first_step == 0 && a.eval_val == nullptr && bidx == 0) {
     if (tid == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; }
     int* dst = cache_i + 8;
@@ -380,6 +416,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
 
   int nstamp = 0;
   int flip = 0;
+  int sweep_ti = 0, sweep_tj = 0;   // team kernels: tile (ti >= tj) of the symmetric sweep this thread owns
+  if constexpr (NW > 1) wpair_decode(tid < (GJN / 3) * (GJN / 3 + 1) / 2 ? tid : 0, sweep_ti, sweep_tj);
   (void)flip;
   // Adam bias corrections b^(step+1), carried multiplicatively (pow once per launch, not twice per step per leaf)
   double b1t = pow(a.b1, (double)a.first_step), b2t = pow(a.b2, (double)a.first_step);
@@ -483,53 +521,47 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     }
     } else {
     {
-      int ibase = 0;
-      TEAM_ITEMS(e, 3 * G, ibase) {
-        const int m = e / 3, w = e - 3 * m;
-        const double gam = th[m] * l * 0.5;
-        if (w == 0) {
-          mu[m] = th[2 * G + m] / th[m];
-          gterm[4 * m + 0] = gam;
-          gterm[4 * m + 1] = exp(gam * gam);
-        } else if (w == 1) {
-          gterm[4 * m + 2] = erf(gam);
-        } else {
-          gterm[4 * m + 3] = LFM_TWO_OVER_SQRT_PI * exp(-gam * gam);
+      const int nitems = stage1_items(G, Tu, nD);
+      for (int f = tid; f < nitems; f += NT) {
+        const unsigned code = f < ITAB ? itab[f] : stage1_decode(f, G, Tu, nD);
+        const int kind = (int)(code >> 24), b = (int)((code >> 16) & 255u), idx = (int)(code & 0xffffu);
+        const double gam = th[b] * l * 0.5;
+        if (kind < 3) {
+          if (kind == 0) {
+            mu[b] = th[2 * G + b] / th[b];
+            gterm[4 * b + 0] = gam;
+            gterm[4 * b + 1] = exp(gam * gam);
+          } else if (kind == 1) {
+            gterm[4 * b + 2] = erf(gam);
+          } else {
+            gterm[4 * b + 3] = LFM_TWO_OVER_SQRT_PI * exp(-gam * gam);
+          }
+        } else if (kind == 3) {
+          const double tl = utime[idx] * inv_l;
+          Gt[idx] = exp(-tl * tl);
+        } else if (kind == 4) {
+          const double dl = dval[didx[idx]] * inv_l;   // (the same difference, bit for bit)
+          Gd[idx] = exp(-dl * dl);
+        } else if (kind < 8) {
+          const double t = utime[idx], d_b = th[b];
+          const double x2 = t * inv_l + gam, x3 = t * inv_l - gam;
+          if (kind == 5) {
+            if (fabs(d_b * t) > 600.0) slow = 1;
+            Em[b * MT + idx] = exp(-d_b * t);
+          } else if (kind == 6) {   // erf(x2) and erfc(|x2|) from ONE call: the small one is evaluated, the other is 1 - it
+            const double ax = fabs(x2);
+            double ev, cv;
+            if (ax > 0.5) { cv = erfc(ax); ev = copysign(1.0 - cv, x2); }
+            else { ev = erf(x2); cv = 1.0 - fabs(ev); }
+            e2[b * MT + idx] = ev;
+            c2[b * MT + idx] = cv;
+          } else {
+            e3[b * MT + idx] = erf(x3);
+          }
+        } else {   // erf-family factor per (gene, distinct difference): erfc(|x1|) beyond 0.5, erf(x1) inside
+          const double x1 = dval[idx] * inv_l - gam;
+          er1[b * MT * MT + idx] = (fabs(x1) > 0.5) ? erfc(fabs(x1)) : erf(x1);
         }
-      }
-      ibase += 3 * G;
-      TEAM_ITEMS(i, Tu, ibase) { const double tl = utime[i] * inv_l; Gt[i] = exp(-tl * tl); }
-      ibase += Tu;
-      TEAM_ITEMS(p, TT, ibase) {
-        const double dl = (utime[p % Tu] - utime[p / Tu]) * inv_l;
-        Gd[p] = exp(-dl * dl);
-      }
-      ibase += TT;
-      TEAM_ITEMS(e3i, 3 * G * Tu, ibase) {
-        const int e = e3i / 3, w = e3i - 3 * e;
-        const int b = e / Tu, i = e % Tu;
-        const double t = utime[i], d_b = th[b], gam = d_b * l * 0.5;
-        const double x2 = t * inv_l + gam, x3 = t * inv_l - gam;
-        if (w == 0) {
-          if (fabs(d_b * t) > 600.0) slow = 1;
-          Em[b * MT + i] = exp(-d_b * t);
-        } else if (w == 1) {   // erf(x2) and erfc(|x2|) from ONE call: whichever is small is evaluated, the other is 1 - it
-          const double ax = fabs(x2);
-          double ev, cv;
-          if (ax > 0.5) { cv = erfc(ax); ev = copysign(1.0 - cv, x2); }
-          else { ev = erf(x2); cv = 1.0 - fabs(ev); }
-          e2[b * MT + i] = ev;
-          c2[b * MT + i] = cv;
-        } else {
-          e3[b * MT + i] = erf(x3);
-        }
-      }
-      ibase += 3 * G * Tu;
-      // erf-family factor per (gene, distinct difference): erfc(|x1|) beyond 0.5, erf(x1) inside
-      TEAM_ITEMS(e, G * nD, ibase) {
-        const int b = e / nD, k = e % nD;
-        const double x1 = dval[k] * inv_l - th[b] * l * 0.5;
-        er1[b * MT * MT + k] = (fabs(x1) > 0.5) ? erfc(fabs(x1)) : erf(x1);
       }
     }
     slow = tany<NW>(slow);   // (NW > 1: also the barrier between the stages)
@@ -871,8 +903,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       double mypiv = 1.0;
       if (tid < SWEEP_THREADS) {
       const bool active = tid < NTILE;
-      int ti, tj;
-      wpair_decode(active ? tid : 0, ti, tj);
+      const int ti = sweep_ti, tj = sweep_tj;
       const int r0 = ti * TS, c0 = tj * TS;
       double at[TS][TS];
 #pragma unroll
@@ -1189,7 +1220,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
 
 size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
   if (MU <= 0 || MT <= 0) return 0;
-  const WarpLayout L = warp_layout(N, G, MU, MT);
+  const WarpLayout L = warp_layout(N, G, MU, MT, true);
   return ((32 + (L.bytes - L.ints) + 8 * ((size_t)MT + (size_t)MT * MT)) + 15) & ~(size_t)15;
 }
 
@@ -1222,7 +1253,7 @@ static int team_slots(size_t bytes) {   // LFMs of team size NW resident on the 
 // A full GPU keeps the warp-per-LFM kernel (most LFMs resident per wave); a shard that leaves lanes idle -- the
 // multi-GPU case -- spends them on a shorter dependent chain per optimiser step.  Team 8 never wins (2 CTAs per SM)
 // and is only reachable through LFM_BATCHED_TEAM = 1 | 4 | 8, which overrides the choice (debug / measurements).
-static int team_choice(int64_t B, size_t bytes) {
+static int team_choice(int64_t B, size_t bytes, size_t bytes_team) {
   const char* env = getenv("LFM_BATCHED_TEAM");
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 4 || forced == 8) return forced;
@@ -1230,7 +1261,7 @@ static int team_choice(int64_t B, size_t bytes) {
   static int s1 = 0, s4 = 0, sms = 0;
   if (bytes != cached_bytes) {
     int dev = 0;
-    s1 = team_slots<1>(bytes); s4 = team_slots<4>(bytes);
+    s1 = team_slots<1>(bytes); s4 = team_slots<4>(bytes_team);
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
     cached_bytes = bytes;
   }
@@ -1249,11 +1280,11 @@ int lfm_batched_warp_launch(cudaStream_t st, const BatchedArgs& a, int time_grid
   const int MU = a.max_unique;
   if (time_grid <= 0 || MU <= 0 || MU > 32 + WEX || a.N > 128 || P > 64) return LFM_ERR_UNSUPPORTED;
   if ((long long)a.G * time_grid * time_grid > 2048 || a.G > 127) return LFM_ERR_UNSUPPORTED;
-  const WarpLayout L = warp_layout(a.N, a.G, MU, time_grid);
-  if (L.bytes > 100 * 1024) return LFM_ERR_UNSUPPORTED;
-  switch (team_choice(a.B, L.bytes)) {
-    case 8: return team_launch<8>(st, a, time_grid, L.bytes);
-    case 4: return team_launch<4>(st, a, time_grid, L.bytes);
+  const WarpLayout L = warp_layout(a.N, a.G, MU, time_grid, false), Lt = warp_layout(a.N, a.G, MU, time_grid, true);
+  if (Lt.bytes > 100 * 1024) return LFM_ERR_UNSUPPORTED;
+  switch (team_choice(a.B, L.bytes, Lt.bytes)) {
+    case 8: return team_launch<8>(st, a, time_grid, Lt.bytes);
+    case 4: return team_launch<4>(st, a, time_grid, Lt.bytes);
     default: return team_launch<1>(st, a, time_grid, L.bytes);
   }
 }
@@ -1264,7 +1295,7 @@ int lfm_batched_warp_team(int64_t B, int N, int G, int MU, int time_grid) {
   const int P = 3 * G + 2;
   if (time_grid <= 0 || MU <= 0 || MU > 32 + WEX || N > 128 || P > 64) return 0;
   if ((long long)G * time_grid * time_grid > 2048 || G > 127) return 0;
-  const WarpLayout L = warp_layout(N, G, MU, time_grid);
-  if (L.bytes > 100 * 1024) return 0;
-  return team_choice(B, L.bytes);
+  const WarpLayout L = warp_layout(N, G, MU, time_grid, false), Lt = warp_layout(N, G, MU, time_grid, true);
+  if (Lt.bytes > 100 * 1024) return 0;
+  return team_choice(B, L.bytes, Lt.bytes);
 }
