@@ -156,6 +156,23 @@ def test_multi_start_single_rank(cuda):
     assert res.best_trace[-1] == res.best_loss      # the atomicMin key of the last chunk IS the winner's loss, bit for bit
 
 
+def test_examples_main_runs_the_reference_script(cuda, tmp_path):
+    """examples/main.py = the reference's src/main.py call sequence: runs end to end on the synthetic p53 set and
+    writes the tables behind the reference's three figures; p21 stays pinned (trainer.py:218-220)."""
+    import csv
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "examples", "main.py"), "--out-dir", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert sorted(os.listdir(tmp_path)) == ["comparison.csv", "gene_expression.csv", "hyperparams.csv", "latent_force.csv"]
+    lf = list(csv.DictReader(open(tmp_path / "latent_force.csv")))
+    assert len(lf) == 100 and all(np.isfinite(float(x["mean"])) and float(x["stddev"]) > 0 for x in lf)
+    cmp_rows = list(csv.DictReader(open(tmp_path / "comparison.csv")))
+    assert len(cmp_rows) == 5 and float(cmp_rows[3]["S_learned"]) == 1.0 and float(cmp_rows[3]["D_learned"]) == 0.8
+
+
 def test_batched_team_size_follows_the_batch(cuda):
     """lfm_batched_team_size: a shard that leaves SMs idle gets four warps per LFM, a full GPU one warp per LFM,
     shapes outside the warp / team kernels report 0 (CTA-per-LFM kernel)."""
