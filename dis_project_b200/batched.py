@@ -111,7 +111,9 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     """Fit all restarts of this rank's shard on the current CUDA device.
 
     `theta0_all` is the (B, P) array of constrained start points of the WHOLE job (every rank passes
-    the same array); the function slices its own shard.  `chunk` optimiser steps run per kernel
+    the same array); the function slices its own shard.  `y` is (N,) -- B restarts of one data set -- or
+    (B, N): LFM b fits y[b] on the shared design X (replicas, gene subsets of equal size, candidate transcription
+    factors); the "winner" is then the LFM with the smallest final NLML over all data sets.  `chunk` optimiser steps run per kernel
     launch; after every chunk the global best objective is all-reduced asynchronously.
     """
     import torch
@@ -137,7 +139,11 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     G = (P - 2) // 3
     lo, hi = shard_bounds(B, rank, world)
     Xd = ops._rows3(X, "x")
-    yd = ops._dev(y).reshape(-1)
+    yh = y if isinstance(y, torch.Tensor) else np.asarray(y, dtype=np.float64)
+    if yh.ndim == 2 and yh.shape[0] == B and yh.shape[1] == Xd.shape[0] and B != 1:
+        yd = ops._dev(yh[lo:hi])      # one row of observations per LFM (replicas / candidate TFs): this rank's rows
+    else:
+        yd = ops._dev(yh).reshape(-1)  # multi-start: every LFM fits the same observations
     nchunks = max((num_iters + chunk - 1) // chunk, 1)
     # behind the state of the shard, in the same allocation: [loss, id, theta] of the shard's winner (P + 2), one
     # best-objective word per chunk, and the winners of every rank (world x (P + 2)) -- read back in ONE copy

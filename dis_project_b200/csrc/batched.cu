@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
   const int N = a.N, G = a.G, P = 3 * G + 2;
   const int tid = threadIdx.x;
   const int64_t bidx = blockIdx.x;
+  const double* yb = a.y + bidx * a.y_stride;   // this LFM's observations (y_stride = 0: shared)
   // ---- carve shared memory (matrix sized for the worst case U = N) ---------------------------------
   const int MU = a.max_unique;
   double* S = reinterpret_cast<double*>(smem_raw);
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
     if (tid < N) {
       int m = tid / blk;
       if (m > G - 1) m = G - 1;
-      const double zi = a.y[tid] - mu[m] * (double)((int)a.X[3 * tid + 2]);
+      const double zi = yb[tid] - mu[m] * (double)((int)a.X[3 * tid + 2]);
       zz_part = zi * zi;
     }
     const double zz = block_sum<BT>(zz_part, red);
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
         if (umap[i] == tid) {
           int m = i / blk;
           if (m > G - 1) m = G - 1;
-          acc += a.y[i] - mu[m] * (double)((int)a.X[3 * i + 2]);
+          acc += yb[i] - mu[m] * (double)((int)a.X[3 * i + 2]);
         }
       }
       q[tid] = acc;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
       }
       // asum_m = sum_{i in positional block m} alpha_i,  alpha_i = (z_i - (K_u beta)_{u(i)}) / c
       for (int i = m * blk; i < (m + 1) * blk; ++i)
-        asum += a.y[i] - mu[m] * (double)((int)a.X[3 * i + 2]) - kb[umap[i]];
+        asum += yb[i] - mu[m] * (double)((int)a.X[3 * i + 2]) - kb[umap[i]];
       asum /= c;
       const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
       gr[m] = gd + asum * Bm / (D * D);
@@ -399,6 +400,7 @@ static size_t batched_smem_bytes(int N, int G, int MU) {
 static int batched_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) {
   if (a.B <= 0 || a.N <= 0 || a.G <= 0 || !a.X || !a.y || !a.u_io) return LFM_ERR_INVALID;
   if (a.N % a.G) return LFM_ERR_INVALID;
+  if (a.y_stride != 0 && a.y_stride < a.N) return LFM_ERR_INVALID;
   if (a.N > 128 || a.B > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
   BatchedArgs b = a;
   if (b.max_unique <= 0 || b.max_unique > b.N) b.max_unique = b.N;
@@ -429,19 +431,26 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) 
   return LFM_OK;
 }
 
-extern "C" int lfm_batched_nlml_grad_unc_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
-                                            const double* y, const double* theta_unc, double jitter,
-                                            int unique_rows_hint, int time_grid_hint, double* out_val,
-                                            double* out_grad, int* info) {
+extern "C" int lfm_batched_nlml_grad_unc_multi(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                               const double* y, int64_t y_stride, const double* theta_unc, double jitter,
+                                               int unique_rows_hint, int time_grid_hint, double* out_val,
+                                               double* out_grad, int* info) {
   if (!out_val || !out_grad) return LFM_ERR_INVALID;
   BatchedArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y;
+  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y; a.y_stride = y_stride;
   a.u_io = const_cast<double*>(theta_unc);  // read-only in eval mode
   a.jitter = jitter; a.steps = 1; a.total_steps = 1; a.steps_per_epoch = 1;
   a.eval_val = out_val; a.eval_grad = out_grad; a.info = info; a.max_unique = unique_rows_hint;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
+}
+extern "C" int lfm_batched_nlml_grad_unc_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                            const double* y, const double* theta_unc, double jitter,
+                                            int unique_rows_hint, int time_grid_hint, double* out_val,
+                                            double* out_grad, int* info) {
+  return lfm_batched_nlml_grad_unc_multi(stream, B, N, G, X, y, 0, theta_unc, jitter, unique_rows_hint, time_grid_hint,
+                                         out_val, out_grad, info);
 }
 extern "C" int lfm_batched_nlml_grad_unc(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
                                          const double* y, const double* theta_unc, double jitter,
@@ -456,12 +465,22 @@ extern "C" int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int
                                   int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
                                   int64_t ld_hist, double* out_theta, int* info, long long* best_key,
                                   void* structure_cache) {
+  return lfm_batched_fit_multi(stream, B, N, G, X, y, 0, theta_unc_io, adam_state, jitter, lr, b1, b2, eps, first_step,
+                               steps, total_steps, fix_params, steps_per_epoch, unique_rows_hint, time_grid_hint,
+                               out_hist, ld_hist, out_theta, info, best_key, structure_cache);
+}
+extern "C" int lfm_batched_fit_multi(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                                     int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter,
+                                     double lr, double b1, double b2, double eps, int first_step, int steps,
+                                     int total_steps, int fix_params, int steps_per_epoch, int unique_rows_hint,
+                                     int time_grid_hint, double* out_hist, int64_t ld_hist, double* out_theta,
+                                     int* info, long long* best_key, void* structure_cache) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
   BatchedArgs a;
   memset(&a, 0, sizeof(a));
-  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y; a.u_io = theta_unc_io; a.adam = adam_state;
+  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y; a.y_stride = y_stride; a.u_io = theta_unc_io; a.adam = adam_state;
   a.jitter = jitter; a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;

@@ -8,6 +8,7 @@ struct BatchedArgs {
   int N, G;
   const double* X;
   const double* y;
+  int64_t y_stride;   // 0: every LFM fits the same y (multi-start); N or more: LFM b fits y + b * y_stride (replicas / candidate TFs)
   double* u_io;       // B x P unconstrained (in/out)
   double* adam;       // B x 2P (m, v) or NULL
   double jitter, lr, b1, b2, eps;

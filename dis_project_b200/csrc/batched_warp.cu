@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     const double* srcd = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(src) + int_bytes);
     for (int i = tid; i < MT; i += NT) utime[i] = srcd[i];
     for (int i = tid; i < MT * MT; i += NT) dval[i] = srcd[MT + i];
-    for (int i = tid; i < N; i += NT) ys[i] = a.y[i];
+    for (int i = tid; i < N; i += NT) ys[i] = a.y[bidx * a.y_stride + i];
     ld = U | 1;
     npairs = U * (U + 1) / 2;
     tsync<NW>();
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     for (int j = 0; j < i; ++j)
       if (Xsm[3 * j] == t0 && Xsm[3 * j + 1] == g0 && Xsm[3 * j + 2] == f0) { rep = j; break; }
     umap[i] = rep;
-    ys[i] = a.y[i];
+    ys[i] = a.y[bidx * a.y_stride + i];
     int m = i / blk;
     if (m > G - 1) m = G - 1;
     mflag[i] = 2 * m + (((int)f0) != 0 ? 1 : 0);
@@ -1224,13 +1224,19 @@ size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
   return ((32 + (L.bytes - L.ints) + 8 * ((size_t)MT + (size_t)MT * MT)) + 15) & ~(size_t)15;
 }
 
+// Opt-in dynamic shared memory of one instantiation: only ever raised (the occupancy query and the launches of
+// differently sized problems share it).
+template <int NW>
+static cudaError_t team_smem(size_t bytes) {
+  static size_t conf = 0;
+  if (bytes <= conf) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) conf = bytes;
+  return e;
+}
 template <int NW>
 static int team_launch(cudaStream_t st, const BatchedArgs& a, int time_grid, size_t bytes) {
-  static size_t conf = 0;
-  if (bytes > conf) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    conf = bytes;
-  }
+  LFM_CUDA_OK(team_smem<NW>(bytes));
   lfm_batched_warp_kernel<NW><<<(unsigned)a.B, 32 * NW, bytes, st>>>(a, time_grid);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
@@ -1241,7 +1247,7 @@ static int team_slots(size_t bytes) {   // LFMs of team size NW resident on the 
   int dev = 0, sms = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-  if (cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return 0;
+  if (team_smem<NW>(bytes) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lfm_batched_warp_kernel<NW>, 32 * NW, bytes) != cudaSuccess) return 0;
   return sms * per_sm;
 }
@@ -1257,13 +1263,13 @@ static int team_choice(int64_t B, size_t bytes, size_t bytes_team) {
   const char* env = getenv("LFM_BATCHED_TEAM");
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 4 || forced == 8) return forced;
-  static size_t cached_bytes = 0;
+  static size_t cached_bytes = 0, cached_team = 0;
   static int s1 = 0, s4 = 0, sms = 0;
-  if (bytes != cached_bytes) {
+  if (bytes != cached_bytes || bytes_team != cached_team) {
     int dev = 0;
     s1 = team_slots<1>(bytes); s4 = team_slots<4>(bytes_team);
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
-    cached_bytes = bytes;
+    cached_bytes = bytes; cached_team = bytes_team;
   }
   if (s1 <= 0 || s4 <= 0 || sms <= 0) return 1;
   auto wave1 = [&](int64_t n) { return 1.0 + 0.11 * (double)n / (double)s1; };

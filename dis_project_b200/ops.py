@@ -304,27 +304,39 @@ def unique_rows(X) -> int:
     return int(_lib.lib().lfm_count_unique_rows(Xh.shape[0], Xh.ctypes.data))
 
 
+def _batched_y(y, B: int, N: int) -> Tuple[torch.Tensor, int]:
+    """y (N,) shared by every LFM -> (y, 0); y (B, N), one row of observations per LFM -> (y, N)."""
+    y = _dev(y)
+    if y.ndim == 2 and y.shape[0] == B and y.shape[1] == N and not (B == N and N == 1):
+        return y, N
+    y = y.reshape(-1)
+    if y.numel() != N:
+        raise ValueError(f"y must hold N={N} observations (shared) or be (B, N)=({B}, {N}) (one row per LFM), got {tuple(y.shape)}")
+    return y, 0
+
+
 def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Optional[int] = None):
     """B independent value_and_grad evaluations.  theta_unc (B, P) -> (val[B], grad[B,P], info[B]).
+    y is (N,) -- every LFM sees the same observations -- or (B, N): LFM b sees y[b] (replicas / candidate TFs).
     `time_grid`: bound on the distinct times of X (None: counted from X; 0: one CTA per LFM, no tables)."""
     hint = unique_rows(X)
     tg = distinct_times(X) if time_grid is None else int(time_grid)
     X = _rows3(X, "x")
-    y = _dev(y).reshape(-1)
     u = _dev(theta_unc)
     P = 3 * G + 2
     if u.ndim != 2 or u.shape[1] != P:
         raise ValueError(f"theta_unc must be (B, {P})")
     B, N = u.shape[0], X.shape[0]
+    y, y_stride = _batched_y(y, B, N)
     val = torch.empty(B, dtype=F64, device=X.device)
     grad = torch.empty((B, P), dtype=F64, device=X.device)
     info = torch.zeros(B, dtype=torch.int32, device=X.device)
     if B == 0:
         return val, grad, info
-    _lib.check(_lib.lib().lfm_batched_nlml_grad_unc_tg(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), u.data_ptr(),
-                                                       float(jitter), hint, tg, val.data_ptr(), grad.data_ptr(),
-                                                       info.data_ptr()),
-               "lfm_batched_nlml_grad_unc_tg")
+    _lib.check(_lib.lib().lfm_batched_nlml_grad_unc_multi(_stream(), B, N, G, X.data_ptr(), y.data_ptr(), y_stride,
+                                                          u.data_ptr(), float(jitter), hint, tg, val.data_ptr(),
+                                                          grad.data_ptr(), info.data_ptr()),
+               "lfm_batched_nlml_grad_unc_multi")
     return val, grad, info
 
 
@@ -408,28 +420,29 @@ def loss_key_to_float(keys):
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
                       b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
                       steps_per_epoch: int = 1000, best_key: Optional[torch.Tensor] = None) -> None:
-    """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216)."""
+    """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216).
+    y is (N,) (multi-start: one data set, B start points) or (B, N) (one row of observations per LFM)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
     if state.time_grid is None:
         state.time_grid = distinct_times(X)
     X = _rows3(X, "x")
-    y = _dev(y).reshape(-1)
+    y, y_stride = _batched_y(y, state.B, X.shape[0])
     if state.B == 0 or steps <= 0:
         return
     steps = min(steps, state.total_steps - state.step)
     if state.struct_cache is None:
         nb = int(_lib.lib().lfm_batched_structure_bytes(X.shape[0], state.G, state.unique_hint, int(state.time_grid)))
         state.struct_cache = torch.zeros(max(nb, 16), dtype=torch.uint8, device=X.device)
-    _lib.check(_lib.lib().lfm_batched_fit_tg(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
-                                             state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
-                                             state.step, steps, state.total_steps, int(bool(fix_params)),
-                                             int(steps_per_epoch), state.unique_hint, int(state.time_grid),
-                                             state.hist.data_ptr(), state.hist.shape[1],
-                                             state.theta.data_ptr(), state.info.data_ptr(),
-                                             best_key.data_ptr() if best_key is not None else None,
-                                             state.struct_cache.data_ptr()),
-               "lfm_batched_fit_tg")
+    _lib.check(_lib.lib().lfm_batched_fit_multi(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
+                                                y_stride, state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr,
+                                                b1, b2, eps, state.step, steps, state.total_steps,
+                                                int(bool(fix_params)), int(steps_per_epoch), state.unique_hint,
+                                                int(state.time_grid), state.hist.data_ptr(), state.hist.shape[1],
+                                                state.theta.data_ptr(), state.info.data_ptr(),
+                                                best_key.data_ptr() if best_key is not None else None,
+                                                state.struct_cache.data_ptr()),
+               "lfm_batched_fit_multi")
     state.step += steps
 
 

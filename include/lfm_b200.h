@@ -180,6 +180,21 @@ int lfm_batched_fit_tg(lfm_stream_t stream, int64_t B, int64_t N, int G, const d
                        double eps, int first_step, int steps, int total_steps, int fix_params,
                        int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
                        int64_t ld_hist, double* out_theta, int* info, long long* best_key, void* structure_cache);
+/* Per-LFM observations: LFM b fits y + b * y_stride (y_stride >= N; 0 = every LFM fits the same y, which is what the
+ * entry points above do).  X -- and with it the duplicate-row / time-grid structure -- stays shared, so this is the
+ * batch over replicas, gene subsets of equal size and candidate transcription factors of north_star: same design
+ * points, different expression data, independent hyper-parameters.  Everything else as lfm_batched_fit_tg /
+ * lfm_batched_nlml_grad_unc_tg. */
+int lfm_batched_fit_multi(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                          int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter, double lr,
+                          double b1, double b2, double eps, int first_step, int steps, int total_steps,
+                          int fix_params, int steps_per_epoch, int unique_rows_hint, int time_grid_hint,
+                          double* out_hist, int64_t ld_hist, double* out_theta, int* info, long long* best_key,
+                          void* structure_cache);
+int lfm_batched_nlml_grad_unc_multi(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X,
+                                    const double* y, int64_t y_stride, const double* theta_unc, double jitter,
+                                    int unique_rows_hint, int time_grid_hint, double* out_val, double* out_grad,
+                                    int* info);
 /* structure_cache (may be NULL): lfm_batched_structure_bytes() device bytes the caller keeps between the calls of ONE
  * chunked fit.  The call with first_step == 0 stores the structure of X (duplicate rows, distinct times and time
  * differences, pair table) there; calls with first_step > 0 load it instead of repeating the O(N^2) scans. */

@@ -262,3 +262,39 @@ def test_batched_not_positive_definite_is_reported(cuda, team, monkeypatch):
     v0, g0, i0 = ops.batched_nlml_grad_unc(x, y, U, 1e-4, G)
     assert not i1.cpu().numpy().any() and not i0.cpu().numpy().any()
     assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-12 and relerr(g1.cpu().numpy(), g0.cpu().numpy()) < 1e-10
+
+
+@pytest.mark.parametrize("team,time_grid", [(1, None), (4, None), (1, 0)])
+def test_batched_per_lfm_observations(cuda, team, time_grid, monkeypatch):
+    """One row of observations per LFM on a shared design X (north_star: replicas / candidate TFs): evaluation and
+    a 30-step fit of every LFM against the oracle on its own data -- warp kernel, team kernel, CTA kernel."""
+    from dis_project_b200 import ops
+    from dis_project_b200.batched import multi_start_fit
+    monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
+    G, T, R, B = 5, 7, 3, 6
+    x, y0, var, _ = o.synthetic_problem(G, T, R, seed=21)
+    rng = np.random.default_rng(22)
+    Y = np.stack([o.synthetic_problem(G, T, R, seed=30 + b)[1].reshape(-1) for b in range(B)])
+    u0 = o.unconstrain(o.Params.reference_init(G).pack())
+    U = u0[None, :] + 0.3 * rng.standard_normal((B, u0.shape[0]))
+    val, grad, info = ops.batched_nlml_grad_unc(x, Y, U, 1e-4, G, time_grid=time_grid)
+    val, grad = val.cpu().numpy(), grad.cpu().numpy()
+    assert not info.cpu().numpy().any()
+    for b in range(B):
+        v, g = o.nlml_and_grad_unc(U[b], x, Y[b], 1e-4)
+        assert abs(val[b] - v) <= RTOL * abs(v) and relerr(grad[b], g) < RTOL
+    TH = o.constrain(U)
+    st = ops.BatchedFitState(TH, G, 30)
+    if time_grid is not None:
+        st.time_grid = time_grid
+    for chunk in (11, 19):
+        ops.batched_fit_steps(st, x, Y, 1e-4, chunk)
+    hist, theta = st.hist.cpu().numpy(), st.theta.cpu().numpy()
+    for b in range(B):
+        th_ref, h_ref = o.fit(TH[b], x, Y[b], 1e-4, num_iters=30)
+        assert relerr(hist[b], h_ref) < 1e-9 and relerr(theta[b], th_ref) < 1e-8
+    if time_grid is None:
+        res = multi_start_fit(x, Y, TH, 1e-4, num_iters=30, chunk=10)
+        assert relerr(res.history, hist) < 1e-12 and res.best_id == int(np.argmin(hist[:, -1]))
+    with pytest.raises(ValueError):
+        ops.batched_nlml_grad_unc(x, Y[:, :-1], U, 1e-4, G)
