@@ -150,6 +150,37 @@ __device__ __forceinline__ unsigned stage1_decode(int f, int G, int Tu, int nD) 
   return (8u << 24) | ((unsigned)b << 16) | (unsigned)(f - b * nD);
 }
 
+// The same items enumerated by cost class, so that a warp's 32 items of a round run ONE transcendental routine instead of
+// diverging over three: class 0 = erf-or-erfc (kinds 6, 8), class 1 = erf (kinds 1, 7), class 2 = exp (kinds 0, 2, 3, 4, 5).
+#define STAGE1_SKIP (15u << 24)
+__device__ __forceinline__ int stage1_class_count(int cls, int G, int Tu, int nD) {
+  return cls == 0 ? G * Tu + G * nD : (cls == 1 ? G + G * Tu : 2 * G + Tu + Tu * Tu + G * Tu);
+}
+__device__ __forceinline__ unsigned stage1_class_decode(int cls, int i, int G, int Tu, int nD) {
+  if (cls == 0) {
+    if (i < G * Tu) { const int b = i / Tu; return (6u << 24) | ((unsigned)b << 16) | (unsigned)(i - b * Tu); }
+    i -= G * Tu;
+    const int b = i / nD;
+    return (8u << 24) | ((unsigned)b << 16) | (unsigned)(i - b * nD);
+  }
+  if (cls == 1) {
+    if (i < G) return (1u << 24) | ((unsigned)i << 16);
+    i -= G;
+    const int b = i / Tu;
+    return (7u << 24) | ((unsigned)b << 16) | (unsigned)(i - b * Tu);
+  }
+  if (i < G) return (0u << 24) | ((unsigned)i << 16);
+  i -= G;
+  if (i < G) return (2u << 24) | ((unsigned)i << 16);
+  i -= G;
+  if (i < Tu) return (3u << 24) | (unsigned)i;
+  i -= Tu;
+  if (i < Tu * Tu) return (4u << 24) | (unsigned)i;
+  i -= Tu * Tu;
+  const int b = i / Tu;
+  return (5u << 24) | ((unsigned)b << 16) | (unsigned)(i - b * Tu);
+}
+
 struct WarpLayout {
   int ld;
   size_t S, tA1R1, tA1, tG1, g2, inv, utime, e2, c2, q, beta, kb, sdiag, dsum, th, u, gr, am, av, mu, ys, ring, red, side, Msm, Xs, gterm, Em, Ep, e3, g3t, Gt, Gd, er1, dval;
@@ -180,7 +211,7 @@ __host__ __device__ inline WarpLayout warp_layout(int N, int G, int MU, int MT, 
   L.ys = take(N);
   L.ring = take(4 * GJN);   // NW = 1: four pivot columns in flight; NW > 1: pivot row / column, double buffered
   L.red = take(32);
-  L.side = take((size_t)P + 4);   // team kernels: Jacobians of the bijectors + scalars prepared by the spare warp
+  L.side = take((size_t)P + 4 + 2 * (size_t)G);   // team kernels: Jacobians of the bijectors + scalars + 1/D, 1/S prepared by the spare warp
   L.gterm = take(4 * (size_t)G);
   L.dval = take((size_t)MT * MT);
   {  // aliases inside S
@@ -256,11 +287,13 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   // LFM and every launch of a fit, so the first launch (first_step == 0) stores LFM 0's copy in a.struct_cache and
   // later launches load it instead of repeating the O(N^2) scans
   int U = 0, R = 0, Tu = 0, nD = 0, ld = 1, npairs = 0;
+  int s1_rounds = 0;   // team kernels: rounds of the stage-1 schedule held in itab (0 = decode the flat list on the fly)
+  (void)s1_rounds;
   unsigned short* didx = pairs + ((size_t)MU * (MU + 1) / 2 + 2);
   int* const cache_i = reinterpret_cast<int*>(a.struct_cache);
   const size_t int_bytes = L.bytes - L.ints;
   if (cache_i && a.first_step > 0 && a.eval_val == nullptr) {
-    U = cache_i[0]; R = cache_i[1]; Tu = cache_i[2]; nD = cache_i[3]; fail = cache_i[4];
+    U = cache_i[0]; R = cache_i[1]; Tu = cache_i[2]; nD = cache_i[3]; fail = cache_i[4]; s1_rounds = cache_i[5];
     const int* src = cache_i + 8;
     int* dst = reinterpret_cast<int*>(smem_raw + L.ints);
     for (size_t i = tid; i < int_bytes / 4; i += NT) dst[i] = src[i];
@@ -394,12 +427,45 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   }
   tsync<NW>();
   if constexpr (NW > 1) {
-    const int nitems = stage1_items(G, Tu, nD);
-    for (int f = tid; f < ITAB && f < nitems; f += NT) itab[f] = stage1_decode(f, G, Tu, nD);
+    // Stage-1 schedule: the items of a class are cut into chunks of 32 (one warp, one round), the chunks are handed
+    // heaviest class first to the least loaded warp (erf-or-erfc 8, erf 5, exp 2 cost units, measured order of
+    // magnitude), and slot (round r, warp w) of itab receives its chunk: itab[(r * NW + w) * 32 + lane].  A problem
+    // whose chunks do not fit ITAB keeps s1_rounds = 0 and decodes the flat item list on the fly.
+    __shared__ int sched_sh[ITAB / 32 + 1];
+    if (tid == 0) {
+      int load[NW], used[NW];
+      for (int w = 0; w < NW; ++w) { load[w] = 0; used[w] = 0; }
+      for (int sl = 0; sl < ITAB / 32; ++sl) sched_sh[sl] = -1;
+      int ok = 1, rounds = 0;
+      for (int cls = 0; cls < 3 && ok; ++cls) {
+        const int cnt = stage1_class_count(cls, G, Tu, nD), wgt = cls == 0 ? 8 : (cls == 1 ? 5 : 2);
+        for (int j = 0; j * 32 < cnt; ++j) {
+          int best = 0;
+          for (int w = 1; w < NW; ++w) if (load[w] < load[best]) best = w;
+          const int sl = used[best] * NW + best;
+          if (sl >= ITAB / 32 || j > 255) { ok = 0; break; }
+          sched_sh[sl] = (cls << 8) | j;
+          load[best] += wgt;
+          if (++used[best] > rounds) rounds = used[best];
+        }
+      }
+      sched_sh[ITAB / 32] = ok ? rounds : 0;
+    }
+    tsync<NW>();
+    s1_rounds = sched_sh[ITAB / 32];
+    for (int f = tid; f < s1_rounds * NT; f += NT) {
+      const int sc = sched_sh[f >> 5];
+      unsigned code = STAGE1_SKIP;
+      if (sc >= 0) {
+        const int cls = sc >> 8, i = (sc & 255) * 32 + (f & 31);
+        if (i < stage1_class_count(cls, G, Tu, nD)) code = stage1_class_decode(cls, i, G, Tu, nD);
+      }
+      itab[f] = code;
+    }
     tsync<NW>();
   }
   if (cache_i && a.first_step == 0 && a.eval_val == nullptr && bidx == 0) {
-    if (tid == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; }
+    if (tid == 0) { cache_i[0] = U; cache_i[1] = R; cache_i[2] = Tu; cache_i[3] = nD; cache_i[4] = fail; cache_i[5] = s1_rounds; }
     int* dst = cache_i + 8;
     const int* src = reinterpret_cast<const int*>(smem_raw + L.ints);
     for (size_t i = tid; i < int_bytes / 4; i += NT) dst[i] = src[i];
@@ -422,6 +488,8 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   // Adam bias corrections b^(step+1), carried multiplicatively (pow once per launch, not twice per step per leaf)
   double b1t = pow(a.b1, (double)a.first_step), b2t = pow(a.b2, (double)a.first_step);
 #define WSTAMP() do { if (a.stamps && bidx == 0 && sidx == 1 && tid == 0) a.stamps[nstamp++] = clock64(); } while (0)
+  // finer stamps inside a phase (slots 16..31 of the same buffer; tools/team_quick.py prints them)
+#define WSTAMPX(i) do { if (a.stamps && bidx == 0 && sidx == 1 && tid == 0) a.stamps[16 + (i)] = clock64(); } while (0)
   // item e of a loop of n independent items goes to thread (base + e) % NT: consecutive loops of one stage land on
   // different threads, so that a team spreads the transcendentals of a stage over all of its lanes
 #define TEAM_ITEMS(e, n, base) for (int e = (tid + NT - ((base) % NT)) % NT; e < (n); e += NT)
@@ -521,51 +589,62 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     }
     } else {
     {
-      const int nitems = stage1_items(G, Tu, nD);
-      for (int f = tid; f < nitems; f += NT) {
-        const unsigned code = f < ITAB ? itab[f] : stage1_decode(f, G, Tu, nD);
+      const int nloop = s1_rounds > 0 ? s1_rounds * NT : stage1_items(G, Tu, nD);
+      for (int f = tid; f < nloop; f += NT) {
+        const unsigned code = s1_rounds > 0 ? itab[f] : stage1_decode(f, G, Tu, nD);
         const int kind = (int)(code >> 24), b = (int)((code >> 16) & 255u), idx = (int)(code & 0xffffu);
+        if (kind == 15) continue;
         const double gam = th[b] * l * 0.5;
-        if (kind < 3) {
+        // ONE call site per routine (exp / erf / erf-or-erfc): the lanes of a scheduled chunk differ in how the argument
+        // is formed and where the value goes, not in the routine they run
+        if (kind == 1 || kind == 7) {
+          const double x = (kind == 1) ? gam : utime[idx] * inv_l - gam;
+          const double v = erf(x);
+          if (kind == 1) gterm[4 * b + 2] = v; else e3[b * MT + idx] = v;
+        } else if (kind == 6 || kind == 8) {
+          // the small one of erf(x) / erfc(|x|) is evaluated, the other is 1 - it (kind 6 keeps both, kind 8 the small one)
+          const double x = (kind == 6) ? utime[idx] * inv_l + gam : dval[idx] * inv_l - gam;
+          const double ax = fabs(x);
+          const bool big = ax > 0.5;
+          const double v = big ? erfc(ax) : erf(x);
+          if (kind == 6) {
+            e2[b * MT + idx] = big ? copysign(1.0 - v, x) : v;
+            c2[b * MT + idx] = big ? v : 1.0 - fabs(v);
+          } else {
+            er1[b * MT * MT + idx] = v;
+          }
+        } else {
+          double arg;
           if (kind == 0) {
             mu[b] = th[2 * G + b] / th[b];
             gterm[4 * b + 0] = gam;
-            gterm[4 * b + 1] = exp(gam * gam);
-          } else if (kind == 1) {
-            gterm[4 * b + 2] = erf(gam);
+            arg = gam * gam;
+          } else if (kind == 2) {
+            arg = -gam * gam;
+          } else if (kind == 3) {
+            const double tl = utime[idx] * inv_l;
+            arg = -tl * tl;
+          } else if (kind == 4) {
+            const double dl = dval[didx[idx]] * inv_l;   // (the same difference, bit for bit)
+            arg = -dl * dl;
           } else {
-            gterm[4 * b + 3] = LFM_TWO_OVER_SQRT_PI * exp(-gam * gam);
-          }
-        } else if (kind == 3) {
-          const double tl = utime[idx] * inv_l;
-          Gt[idx] = exp(-tl * tl);
-        } else if (kind == 4) {
-          const double dl = dval[didx[idx]] * inv_l;   // (the same difference, bit for bit)
-          Gd[idx] = exp(-dl * dl);
-        } else if (kind < 8) {
-          const double t = utime[idx], d_b = th[b];
-          const double x2 = t * inv_l + gam, x3 = t * inv_l - gam;
-          if (kind == 5) {
+            const double t = utime[idx], d_b = th[b];
             if (fabs(d_b * t) > 600.0) slow = 1;
-            Em[b * MT + idx] = exp(-d_b * t);
-          } else if (kind == 6) {   // erf(x2) and erfc(|x2|) from ONE call: the small one is evaluated, the other is 1 - it
-            const double ax = fabs(x2);
-            double ev, cv;
-            if (ax > 0.5) { cv = erfc(ax); ev = copysign(1.0 - cv, x2); }
-            else { ev = erf(x2); cv = 1.0 - fabs(ev); }
-            e2[b * MT + idx] = ev;
-            c2[b * MT + idx] = cv;
-          } else {
-            e3[b * MT + idx] = erf(x3);
+            arg = -d_b * t;
           }
-        } else {   // erf-family factor per (gene, distinct difference): erfc(|x1|) beyond 0.5, erf(x1) inside
-          const double x1 = dval[idx] * inv_l - gam;
-          er1[b * MT * MT + idx] = (fabs(x1) > 0.5) ? erfc(fabs(x1)) : erf(x1);
+          const double ev = exp(arg);
+          if (kind == 0) gterm[4 * b + 1] = ev;
+          else if (kind == 2) gterm[4 * b + 3] = LFM_TWO_OVER_SQRT_PI * ev;
+          else if (kind == 3) Gt[idx] = ev;
+          else if (kind == 4) Gd[idx] = ev;
+          else Em[b * MT + idx] = ev;
         }
       }
     }
+    WSTAMPX(0);
     slow = tany<NW>(slow);   // (NW > 1: also the barrier between the stages)
     tsync<NW>();
+    WSTAMPX(1);
     {
       int ibase = 0;
       TEAM_ITEMS(e, G * Tu, ibase) {
@@ -607,6 +686,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         q[r] = acc;
       }
     }
+    WSTAMPX(2);
     for (int i = tid; i < N; i += NT) {
       const double zi = ys[i] - mu[mflag[i] >> 1] * (double)(mflag[i] & 1);
       zz += zi * zi;
@@ -894,7 +974,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       // unrolled over k % TS so that every register index is a compile-time constant.
       // Warps 0-2 sweep (78 tiles of 3 x 3; their barrier is a named one for 96 threads); meanwhile warp 3 prepares
       // what depends on theta alone and would otherwise sit on the serial tail of the step: the Jacobians of the
-      // bijectors, 1 / c, log c and the reciprocals of Adam's bias corrections (side[]).
+      // bijectors, 1 / c, log c, the reciprocals of Adam's bias corrections and 1 / D, 1 / S of the fold (side[]).
       static_assert(NW >= 4, "the team kernels need a spare warp next to the three sweep warps");
       constexpr int TS = 3, SWEEP_THREADS = 96;
       constexpr int TG = GJN / TS, NTILE = TG * (TG + 1) / 2;
@@ -987,6 +1067,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
           side[2] = 1.0 / (1.0 - b1t * a.b1);
           side[3] = 1.0 / (1.0 - b2t * a.b2);
         }
+        for (int m = lane; m < 2 * G; m += 32) side[4 + P + m] = 1.0 / th[m];   // 1 / D_m, 1 / S_m
       }
       __syncthreads();
       fail = fail_sh;
@@ -1026,6 +1107,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
       qkb += q[r] * kbv;
       kbkb += kbv * kbv;
     }
+    WSTAMPX(5);
     tsum2<NW>(qkb, kbkb, red, flip);
     const double inv_c = (NW == 1) ? 1.0 / c : side[0];
     const double quad = (NW == 1) ? (zz - qkb) / c : (zz - qkb) * inv_c;
@@ -1074,8 +1156,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         grad_store(g0);
       }
     }
+    WSTAMPX(3);
     const double gl = tsum<NW>(dl_part, red, flip);
     tsync<NW>();
+    WSTAMPX(4);
     for (int r = tid; r < U; r += NT) {  // per-point totals: full row sums, fixed order
       const double* rp = S + r * ld;
       double s0 = dsum[r], s1 = 0.0;
@@ -1130,10 +1214,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
         }
         if (hl == 0) {
           asum *= inv_c;
-          const double D = th[m], Sm = th[G + m], Bm = th[2 * G + m];
-          const double rD = 1.0 / D;
+          const double Bm = th[2 * G + m];
+          const double rD = side[4 + P + m];
           gr[m] = gd + asum * Bm * rD * rD;
-          gr[G + m] = gs / Sm;
+          gr[G + m] = gs * side[4 + P + G + m];
           gr[2 * G + m] = -asum * rD;
         }
       }
