@@ -12,6 +12,7 @@
 // 32 x 32 sub-blocks: warp-shuffle Cholesky on the diagonal sub-blocks, DMMA for everything else);
 // the inverted diagonal blocks turn every leaf-level TRSM into a GEMM.
 #include <cstdlib>
+#include <cuda.h>
 #include "lfm_common.cuh"
 
 #define NB LFM_NB
@@ -571,17 +572,67 @@ static int chain_fused_mode() {
 // Fork/join is by events only (no host synchronisation; legal under stream capture).
 struct LookAhead {
   cudaStream_t chain = nullptr, tri = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr;
+  cudaStream_t bulk = nullptr;   // SM partition only: the bulk stream of the large partition (else the caller's stream)
+  cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr, bulk_join = nullptr;
   cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
   bool ok = false;
+  int chain_sms = 0;             // SMs of the chain partition (0: no partition, priorities only)
+  // SM partition (green contexts, driver API >= 12.4, reached through cudaGetDriverEntryPoint so that the library
+  // has no link-time dependency on libcuda): the leaf needs a whole SM (all registers, 170 KB of shared memory) and
+  // the chain step a cluster of 8 such SMs, so on a device that the 64 x 64-tile bulk GEMMs keep full -- two CTAs per
+  // SM, refilled slot by slot -- a pending chain kernel only starts when a bulk launch drains, whatever its stream
+  // priority (measured: the chain waited for the tail of every trailing update, and 265 us for the 2048^3 product of
+  // the inverse in the middle of an N = 4096 factorisation).  The chain therefore gets 8 SMs of its own (one
+  // cluster-capable group); the trailing updates and the inverse share the other 140.
+  bool init_partition(int dev, int prio_lo, int prio_hi) {
+    const char* env = getenv("LFM_SM_PARTITION");
+    if (env && atoi(env) == 0) return false;
+    CUresult (*pDevGet)(CUdevice*, int) = nullptr;
+    CUresult (*pGetRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*pSplit)(CUdevResource*, unsigned*, const CUdevResource*, CUdevResource*, unsigned, unsigned) = nullptr;
+    CUresult (*pDesc)(CUdevResourceDesc*, CUdevResource*, unsigned) = nullptr;
+    CUresult (*pCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned) = nullptr;
+    CUresult (*pStream)(CUstream*, CUgreenCtx, unsigned, int) = nullptr;
+    auto ep = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult q;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr;
+    };
+    if (!ep("cuDeviceGet", (void**)&pDevGet) || !ep("cuDeviceGetDevResource", (void**)&pGetRes) ||
+        !ep("cuDevSmResourceSplitByCount", (void**)&pSplit) || !ep("cuDevResourceGenerateDesc", (void**)&pDesc) ||
+        !ep("cuGreenCtxCreate", (void**)&pCreate) || !ep("cuGreenCtxStreamCreate", (void**)&pStream)) {
+      cudaGetLastError();
+      return false;
+    }
+    CUdevice cudev;
+    CUdevResource all, grp[1], rem;
+    unsigned nb = 1;
+    if (pDevGet(&cudev, dev) != CUDA_SUCCESS || pGetRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
+    if (all.sm.smCount < 64) return false;
+    if (pSplit(grp, &nb, &all, &rem, 0, 8) != CUDA_SUCCESS || nb != 1 || grp[0].sm.smCount < 8 || rem.sm.smCount < 32) return false;
+    CUdevResourceDesc dA, dB;
+    if (pDesc(&dA, &grp[0], 1) != CUDA_SUCCESS || pDesc(&dB, &rem, 1) != CUDA_SUCCESS) return false;
+    CUgreenCtx gA, gB;   // (live as long as the process: the streams below are never destroyed either)
+    if (pCreate(&gA, dA, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    if (pCreate(&gB, dB, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
+    CUstream sc, sb, stri;
+    if (pStream(&sc, gA, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+    if (pStream(&sb, gB, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+    if (pStream(&stri, gB, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
+    chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri;
+    chain_sms = (int)grp[0].sm.smCount;
+    return true;
+  }
   bool init() {
     if (ok) return true;
-    int lo = 0, hi = 0;
-    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return false;
-    if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
-    if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
-    cudaEvent_t* all[] = {&fork, &join, &tri_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1], &bulk_done[0],
-                          &bulk_done[1]};
+    int lo = 0, hi = 0, dev = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (!init_partition(dev, lo, hi)) {
+      bulk = nullptr; chain_sms = 0;
+      if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+      if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
+    }
+    cudaEvent_t* all[] = {&fork, &join, &tri_join, &bulk_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1],
+                          &bulk_done[0], &bulk_done[1]};
     for (cudaEvent_t* e : all)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
     ok = true;
@@ -627,19 +678,21 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
   LookAhead& la = g_la_dev[dev];
   cudaStream_t ch = la.chain;
   cudaStream_t tr = la.tri;
+  cudaStream_t bk = la.bulk ? la.bulk : st;   // bulk work: the large SM partition, or the caller's stream
   LFM_CUDA_OK(cudaEventRecord(la.fork, st));
   LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.fork, 0));
+  if (bk != st) LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.fork, 0));
   if (with_trtri) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.fork, 0));
   const int64_t nb = n / NB;
   // one product of the trtri node with half size mb blocks whose first block is ob (see trtri_levels)
-  auto tri_g1 = [&](int64_t ob, int64_t mb) {  // T^T = W11^T L21^T into the strictly upper block of W
+  auto tri_g1 = [&](int64_t ob, int64_t mb) -> int {  // T^T = W11^T L21^T into the strictly upper block of W
     const int64_t o = ob * NB, m = mb * NB;
     return lfm_dgemm(tr, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
                             1.0, 0.0, 0, LFM_K_GE_ROW));
   };
-  auto tri_g2 = [&](int64_t ob, int64_t mb) {  // W21 = -W22 T
+  auto tri_g2 = [&](cudaStream_t s2, int64_t ob, int64_t mb) -> int {  // W21 = -W22 T
     const int64_t o = ob * NB, m = mb * NB;
-    return lfm_dgemm(tr, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
+    return lfm_dgemm(s2, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
                             W + (o + m) * ldw + o, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW));
   };
   int step = 0;
@@ -653,9 +706,11 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     LFM_CUDA_OK(cudaEventRecord(la.leaf_done[e], ch));
     if (with_trtri) {
       // nodes that END at block `step`: their right half is now inverted (lower levels first)
+      // (the nodes that end at the LAST block are the serial tail of the inverse -- every level waits for the one
+      // below: they run after the join, on the caller's stream, i.e. on all SMs of the device)
       LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.leaf_done[e], 0));
-      for (int64_t mb = 1; 2 * mb <= nb; mb *= 2)
-        if ((step + 1) % (2 * mb) == 0) LFM_TRY(tri_g2(step + 1 - 2 * mb, mb));
+      for (int64_t mb = 1; 2 * mb <= nb && m > 0; mb *= 2)
+        if ((step + 1) % (2 * mb) == 0) LFM_TRY(tri_g2(tr, step + 1 - 2 * mb, mb));
     }
     if (m <= 0) break;
     double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
@@ -685,26 +740,31 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     // ---- bulk (caller's stream)
     double* P2 = P + NB * lda;  // rows >= k+2 of the panel, (m - 128) x 128
     const int64_t m2 = m - NB;
-    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.leaf_done[e], 0));
-    LFM_TRY(lfm_dgemm(st, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
-    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.p1_done[e], 0));
+    LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.leaf_done[e], 0));
+    LFM_TRY(lfm_dgemm(bk, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.p1_done[e], 0));
     // trailing update A(k+1:, k+1:) -= L(k+1:, k) L(k+1:, k)^T on the lower tiles, minus the diagonal block
     // (k+1, k+1) that the chain has already updated: one launch over a trapezoid of tiles
     {
       LfmGemm u = mk(0, 1, m, m, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 1, LFM_K_FULL);
       u.tri_skip = NB;
-      LFM_TRY(lfm_dgemm(st, u));
+      LFM_TRY(lfm_dgemm(bk, u));
     }
-    LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], st));
+    LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], bk));
     bulk_used = true;
     LFM_TRY(tri_front(true));
   }
   // join: everything after the factorisation is ordered behind the chain (and the inverse)
   LFM_CUDA_OK(cudaEventRecord(la.join, ch));
   LFM_CUDA_OK(cudaStreamWaitEvent(st, la.join, 0));
+  if (bk != st) {
+    LFM_CUDA_OK(cudaEventRecord(la.bulk_join, bk));
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.bulk_join, 0));
+  }
   if (with_trtri) {
     LFM_CUDA_OK(cudaEventRecord(la.tri_join, tr));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.tri_join, 0));
+    for (int64_t mb = 1; 2 * mb <= nb; mb *= 2) LFM_TRY(tri_g2(st, nb - 2 * mb, mb));
   }
   return LFM_OK;
 }
