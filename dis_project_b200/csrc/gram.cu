@@ -139,14 +139,22 @@ int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused derivative contraction.  Work item = (row tile I, chunk of GC_TILES column tiles), lower
+// Fused derivative contraction.  Work item = (row tile I, chunk of gc_tiles column tiles), lower
 // triangle only; off-diagonal entries carry weight 2 (K_bar and dK are symmetric).
 // Per entry (i,j), w = weight * K_bar_ij, K_bar_ij = 1/2 (Sinv_ij - alpha_i alpha_j):
 //   rowacc[i] += w * (dk/dD_row, k)      colacc[j] += w * (dk/dD_col, k)      lacc += w * dk/dl
 // Row partials go to rowpart[chunk][i][2], column partials to colpart[I][j][2]; a fixed-order
 // second pass (lfm_grad_finish_kernel) folds them per gene -> deterministic results.
 // ---------------------------------------------------------------------------------------------
-#define GC_TILES 16
+// Column tiles per work item: few enough that the launch fills both CTA slots of every SM for more than one wave
+// (N = 4000: 63 row tiles -> 1040 work items of <= 2 tiles instead of 156 of <= 16 on 296 slots; measured 3.83 -> 3.65 ms per evaluation), many for large N where
+// the row partials (one N64 x 2 slab per chunk) would otherwise dominate the scratch.
+static int lfm_gc_tiles(int64_t ntile) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("LFM_GC_TILES"); forced = e ? atoi(e) : 0; }
+  if (forced > 0) return forced;
+  return ntile <= 128 ? 2 : 16;
+}
 
 template <bool TAB>
 __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
                                                               double* __restrict__ rowpart,  // [nchunk][Npad64][2]
                                                               double* __restrict__ colpart,  // [ntile][Npad64][2]
                                                               double* __restrict__ lpart,    // [ntile][nchunk]
-                                                              int64_t N64, int nchunk, LfmGrid grid) {
+                                                              int64_t N64, int nchunk, int gc_tiles, LfmGrid grid) {
   __shared__ LfmPoint rowp[GT];
   __shared__ LfmPoint colp[GT];
   __shared__ double red[8][GT][2];
@@ -165,9 +173,9 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
   const int chunk = blockIdx.x;
   const int tid = threadIdx.y * 32 + threadIdx.x;
   const int lane = threadIdx.x, wy = threadIdx.y;
-  const int jt0 = chunk * GC_TILES;
+  const int jt0 = chunk * gc_tiles;
   if (jt0 > I) return;
-  const int jt1 = min(I, jt0 + GC_TILES - 1);
+  const int jt1 = min(I, jt0 + gc_tiles - 1);
   const double l = theta[3 * G];
   const double inv_l = 1.0 / l;
   const bool tab = grid.Tu > 0 && *grid.count <= grid.Tu;
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
 }
 
 // Per-point totals: pt[i] = (sum of row partials over chunks) + (sum of column partials over I >= tile(i))
-__global__ void lfm_grad_point_kernel(int64_t N, int64_t N64, int ntile, int nchunk,
+__global__ void lfm_grad_point_kernel(int64_t N, int64_t N64, int ntile, int nchunk, int gc_tiles,
                                       const double* __restrict__ rowpart, const double* __restrict__ colpart,
                                       double* __restrict__ pt /* [N][2] */) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -265,7 +273,7 @@ __global__ void lfm_grad_point_kernel(int64_t N, int64_t N64, int ntile, int nch
   const int q = (int)(idx & 1);
   const int ti = (int)(i / GT);
   double acc = 0.0;
-  const int my_chunks = ti / GC_TILES + 1;  // chunks that exist for row tile ti
+  const int my_chunks = ti / gc_tiles + 1;  // chunks that exist for row tile ti
   for (int c = 0; c < my_chunks && c < nchunk; ++c) acc += rowpart[((int64_t)c * N64 + i) * 2 + q];
   for (int I = ti; I < ntile; ++I) acc += colpart[((int64_t)I * N64 + i) * 2 + q];
   pt[idx] = acc;
@@ -324,7 +332,8 @@ __global__ void __launch_bounds__(256) lfm_grad_finish_kernel(int64_t N, const d
 size_t lfm_grad_scratch_doubles(int64_t N) {
   const int64_t ntile = (N + GT - 1) / GT;
   const int64_t N64 = ntile * GT;
-  const int64_t nchunk = (ntile + GC_TILES - 1) / GC_TILES;
+  const int64_t gct = lfm_gc_tiles(ntile);
+  const int64_t nchunk = (ntile + gct - 1) / gct;
   return (size_t)(nchunk * N64 * 2 + ntile * N64 * 2 + ntile * nchunk + N * 2);
 }
 
@@ -336,7 +345,8 @@ int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G,
   if (tg) tgv = *tg;
   const int64_t ntile = (N + GT - 1) / GT;
   const int64_t N64 = ntile * GT;
-  const int64_t nchunk = (ntile + GC_TILES - 1) / GC_TILES;
+  const int gct = lfm_gc_tiles(ntile);
+  const int64_t nchunk = (ntile + gct - 1) / gct;
   double* rowpart = scratch;
   double* colpart = rowpart + nchunk * N64 * 2;
   double* lpart = colpart + ntile * N64 * 2;
@@ -345,14 +355,14 @@ int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G,
   LFM_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(double) * (size_t)(nchunk * N64 * 2 + ntile * N64 * 2 + ntile * nchunk), st));
   dim3 grid((unsigned)nchunk, (unsigned)ntile);
   lfm_grad_contract_kernel<false><<<grid, dim3(32, 8), 0, st>>>(N, X, G, theta, Sinv, ld, alpha, rowpart, colpart,
-                                                               lpart, N64, (int)nchunk, tgv);
+                                                               lpart, N64, (int)nchunk, gct, tgv);
   if (tgv.Tu > 0) {
     lfm_grad_contract_kernel<true><<<grid, dim3(32, 8), 0, st>>>(N, X, G, theta, Sinv, ld, alpha, rowpart, colpart,
-                                                                lpart, N64, (int)nchunk, tgv);
+                                                                lpart, N64, (int)nchunk, gct, tgv);
     LFM_LAUNCHED(1);
   }
   LFM_CUDA_OK(cudaGetLastError());
-  lfm_grad_point_kernel<<<(unsigned)((N * 2 + 255) / 256), 256, 0, st>>>(N, N64, (int)ntile, (int)nchunk, rowpart,
+  lfm_grad_point_kernel<<<(unsigned)((N * 2 + 255) / 256), 256, 0, st>>>(N, N64, (int)ntile, (int)nchunk, gct, rowpart,
                                                                         colpart, pt);
   LFM_CUDA_OK(cudaGetLastError());
   lfm_grad_finish_kernel<<<G + 1, 256, 0, st>>>(N, X, G, theta, pt, lpart, ntile * nchunk, alpha, Sinv, ld, grad);
