@@ -284,16 +284,59 @@ extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, 
   return lfm_nlml_tg(stream, N, G, X, y, theta, jitter, 0, ws, ws_bytes, out, info);
 }
 
+// Side stream of an evaluation: w = W z, alpha = W^T w and the NLML reduction only read W, z and the diagonal of L,
+// so they run beside Sigma^-1 = W^T W (the longest single launch of an evaluation) instead of in front of it.
+struct EvalSide {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+  bool init() {
+    if (ok) return true;
+    if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return false;
+    ok = true;
+    return true;
+  }
+};
+static thread_local EvalSide g_eval_side[16];  // per host thread and device
+
+__global__ void lfm_diag_copy_kernel(int64_t n, const double* __restrict__ A, int64_t lda, double* __restrict__ d) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) d[i] = A[i * lda + i];
+}
+
 static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, const double* y,
                           const double* theta, double jitter, const NlmlWs& s, double* out, int* info) {
   const int P = 3 * G + 2;
   LfmGrid grid;
   LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, true, &grid, info));
-  LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
-  lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
-  LFM_LAUNCHED(1);
-  LFM_CUDA_OK(cudaGetLastError());
-  LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
+  if (dev >= 0 && g_eval_side[dev].init()) {
+    EvalSide& es = g_eval_side[dev];
+    // the diagonal of L moves out of the way first (the gradient scratch is idle until the contraction): Sigma^-1
+    // overwrites L while the side stream is still reducing
+    double* ldiag = s.gscratch;
+    lfm_diag_copy_kernel<<<(unsigned)((s.Np + 255) / 256), 256, 0, st>>>(s.Np, s.A, s.Np, ldiag);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+    LFM_CUDA_OK(cudaEventRecord(es.fork, st));
+    LFM_CUDA_OK(cudaStreamWaitEvent(es.side, es.fork, 0));
+    LFM_TRY(lfm_launch_alpha(es.side, s.Np, s.W, s.z, s.w, s.part, s.alpha));
+    lfm_nlml_reduce_kernel<<<1, 1024, 0, es.side>>>(N, s.Np, ldiag, 0, s.w, info, out);   // ldl = 0: L[i * 0 + i]
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+    LFM_CUDA_OK(cudaEventRecord(es.join, es.side));
+    LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, es.join, 0));
+  } else {
+    LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
+    lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+    LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
+  }
   LFM_TRY(lfm_launch_grad_contract(st, N, X, G, theta, s.A, s.Np, s.alpha, s.gscratch, out + 1, &grid));
   lfm_poison_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, info, out + 1);
   LFM_LAUNCHED(1);
