@@ -587,6 +587,9 @@ struct LookAhead {
   bool init_partition(int dev, int prio_lo, int prio_hi) {
     const char* env = getenv("LFM_SM_PARTITION");
     if (env && atoi(env) == 0) return false;
+    // Nsight Compute cannot replay kernels launched into a green context ("Failed to prepare kernel for profiling"):
+    // under ncu the chain falls back to stream priorities (ncu serialises the launches anyway)
+    if (!env && (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_TPS_LAUNCH_TOKEN"))) return false;
     CUresult (*pDevGet)(CUdevice*, int) = nullptr;
     CUresult (*pGetRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
     CUresult (*pSplit)(CUdevResource*, unsigned*, const CUdevResource*, CUdevResource*, unsigned, unsigned) = nullptr;
