@@ -573,7 +573,8 @@ static int chain_fused_mode() {
 struct LookAhead {
   cudaStream_t chain = nullptr, tri = nullptr;
   cudaStream_t bulk = nullptr;   // SM partition only: the bulk stream of the large partition (else the caller's stream)
-  cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr, bulk_join = nullptr;
+  cudaStream_t tri2 = nullptr;   // SM partition only: a SUBSET of the large partition for the one long product of the inverse
+  cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr, bulk_join = nullptr, tri_mid = nullptr, tri2_join = nullptr;
   cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
   bool ok = false;
   int chain_sms = 0;             // SMs of the chain partition (0: no partition, priorities only)
@@ -596,6 +597,7 @@ struct LookAhead {
     CUresult (*pDesc)(CUdevResourceDesc*, CUdevResource*, unsigned) = nullptr;
     CUresult (*pCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned) = nullptr;
     CUresult (*pStream)(CUstream*, CUgreenCtx, unsigned, int) = nullptr;
+    CUresult (*pGreenRes)(CUgreenCtx, CUdevResource*, CUdevResourceType) = nullptr;
     auto ep = [](const char* name, void** fn) {
       cudaDriverEntryPointQueryResult q;
       return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr;
@@ -623,6 +625,25 @@ struct LookAhead {
     if (pStream(&stri, gB, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
     chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri;
     chain_sms = (int)grp[0].sm.smCount;
+    // A third context on HALF of the large partition (its SMs belong to both): the top node of the interleaved inverse
+    // issues T = L21 W11, (n/2)^3 flops in one launch of long-lived 64 x 64-tile CTAs, in the middle of the
+    // factorisation.  On the whole partition it took every slot for 280 us and the (short) trailing updates of the
+    // chain-bound second half queued behind it; confined to half of the SMs it runs underneath that half instead.
+    const char* e2 = getenv("LFM_TRI2_SMS");
+    const int want = e2 ? atoi(e2) : 72;
+    CUdevResource resB, sub[1], rem2;
+    unsigned nb2 = 1;
+    CUdevResourceDesc dC;
+    CUgreenCtx gC;
+    CUstream st2;
+    if (want > 0 && ep("cuGreenCtxGetDevResource", (void**)&pGreenRes) &&
+        pGreenRes(gB, &resB, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+        pSplit(sub, &nb2, &resB, &rem2, 0, (unsigned)want) == CUDA_SUCCESS && nb2 == 1 &&
+        pDesc(&dC, &sub[0], 1) == CUDA_SUCCESS && pCreate(&gC, dC, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
+        pStream(&st2, gC, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS)
+      tri2 = (cudaStream_t)st2;
+    else
+      cudaGetLastError();
     return true;
   }
   bool init() {
@@ -630,11 +651,11 @@ struct LookAhead {
     int lo = 0, hi = 0, dev = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) return false;
     if (!init_partition(dev, lo, hi)) {
-      bulk = nullptr; chain_sms = 0;
+      bulk = nullptr; tri2 = nullptr; chain_sms = 0;
       if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
       if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
     }
-    cudaEvent_t* all[] = {&fork, &join, &tri_join, &bulk_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1],
+    cudaEvent_t* all[] = {&fork, &join, &tri_join, &bulk_join, &tri_mid, &tri2_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1],
                           &bulk_done[0], &bulk_done[1]};
     for (cudaEvent_t* e : all)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
@@ -688,9 +709,17 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
   if (with_trtri) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.fork, 0));
   const int64_t nb = n / NB;
   // one product of the trtri node with half size mb blocks whose first block is ob (see trtri_levels)
+  bool tri2_used = false;
   auto tri_g1 = [&](int64_t ob, int64_t mb) -> int {  // T^T = W11^T L21^T into the strictly upper block of W
     const int64_t o = ob * NB, m = mb * NB;
-    return lfm_dgemm(tr, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
+    cudaStream_t s1 = tr;
+    if (la.tri2 && 2 * mb == nb && nb >= 16) {   // the top node: everything the low-priority stream was told to wait for
+      LFM_CUDA_OK(cudaEventRecord(la.tri_mid, tr));   // and everything it has been given so far precedes it
+      LFM_CUDA_OK(cudaStreamWaitEvent(la.tri2, la.tri_mid, 0));
+      s1 = la.tri2;
+      tri2_used = true;
+    }
+    return lfm_dgemm(s1, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
                             1.0, 0.0, 0, LFM_K_GE_ROW));
   };
   auto tri_g2 = [&](cudaStream_t s2, int64_t ob, int64_t mb) -> int {  // W21 = -W22 T
@@ -767,6 +796,10 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
   if (with_trtri) {
     LFM_CUDA_OK(cudaEventRecord(la.tri_join, tr));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.tri_join, 0));
+    if (tri2_used) {
+      LFM_CUDA_OK(cudaEventRecord(la.tri2_join, la.tri2));
+      LFM_CUDA_OK(cudaStreamWaitEvent(st, la.tri2_join, 0));
+    }
     for (int64_t mb = 1; 2 * mb <= nb; mb *= 2) LFM_TRY(tri_g2(st, nb - 2 * mb, mb));
   }
   return LFM_OK;
