@@ -12,6 +12,8 @@
 // 32 x 32 sub-blocks: warp-shuffle Cholesky on the diagonal sub-blocks, DMMA for everything else);
 // the inverted diagonal blocks turn every leaf-level TRSM into a GEMM.
 #include <cstdlib>
+#include <functional>
+#include <mutex>
 #include <cuda.h>
 #include "lfm_common.cuh"
 
@@ -585,69 +587,12 @@ struct LookAhead {
   // priority (measured: the chain waited for the tail of every trailing update, and 265 us for the 2048^3 product of
   // the inverse in the middle of an N = 4096 factorisation).  The chain therefore gets 8 SMs of its own (one
   // cluster-capable group); the trailing updates and the inverse share the other 140.
-  bool init_partition(int dev, int prio_lo, int prio_hi) {
-    const char* env = getenv("LFM_SM_PARTITION");
-    if (env && atoi(env) == 0) return false;
-    // Nsight Compute cannot replay kernels launched into a green context ("Failed to prepare kernel for profiling"):
-    // under ncu the chain falls back to stream priorities (ncu serialises the launches anyway)
-    if (!env && (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_TPS_LAUNCH_TOKEN"))) return false;
-    CUresult (*pDevGet)(CUdevice*, int) = nullptr;
-    CUresult (*pGetRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
-    CUresult (*pSplit)(CUdevResource*, unsigned*, const CUdevResource*, CUdevResource*, unsigned, unsigned) = nullptr;
-    CUresult (*pDesc)(CUdevResourceDesc*, CUdevResource*, unsigned) = nullptr;
-    CUresult (*pCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned) = nullptr;
-    CUresult (*pStream)(CUstream*, CUgreenCtx, unsigned, int) = nullptr;
-    CUresult (*pGreenRes)(CUgreenCtx, CUdevResource*, CUdevResourceType) = nullptr;
-    auto ep = [](const char* name, void** fn) {
-      cudaDriverEntryPointQueryResult q;
-      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr;
-    };
-    if (!ep("cuDeviceGet", (void**)&pDevGet) || !ep("cuDeviceGetDevResource", (void**)&pGetRes) ||
-        !ep("cuDevSmResourceSplitByCount", (void**)&pSplit) || !ep("cuDevResourceGenerateDesc", (void**)&pDesc) ||
-        !ep("cuGreenCtxCreate", (void**)&pCreate) || !ep("cuGreenCtxStreamCreate", (void**)&pStream)) {
-      cudaGetLastError();
-      return false;
-    }
-    CUdevice cudev;
-    CUdevResource all, grp[1], rem;
-    unsigned nb = 1;
-    if (pDevGet(&cudev, dev) != CUDA_SUCCESS || pGetRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return false;
-    if (all.sm.smCount < 64) return false;
-    if (pSplit(grp, &nb, &all, &rem, 0, 8) != CUDA_SUCCESS || nb != 1 || grp[0].sm.smCount < 8 || rem.sm.smCount < 32) return false;
-    CUdevResourceDesc dA, dB;
-    if (pDesc(&dA, &grp[0], 1) != CUDA_SUCCESS || pDesc(&dB, &rem, 1) != CUDA_SUCCESS) return false;
-    CUgreenCtx gA, gB;   // (live as long as the process: the streams below are never destroyed either)
-    if (pCreate(&gA, dA, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    if (pCreate(&gB, dB, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return false;
-    CUstream sc, sb, stri;
-    if (pStream(&sc, gA, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
-    if (pStream(&sb, gB, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
-    if (pStream(&stri, gB, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
-    chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri;
-    chain_sms = (int)grp[0].sm.smCount;
-    // A third context on HALF of the large partition (its SMs belong to both): the top node of the interleaved inverse
-    // issues T = L21 W11, (n/2)^3 flops in one launch of long-lived 64 x 64-tile CTAs, in the middle of the
-    // factorisation.  On the whole partition it took every slot for 280 us and the (short) trailing updates of the
-    // chain-bound second half queued behind it; confined to half of the SMs it runs underneath that half instead.
-    const char* e2 = getenv("LFM_TRI2_SMS");
-    const int want = e2 ? atoi(e2) : 72;
-    CUdevResource resB, sub[1], rem2;
-    unsigned nb2 = 1;
-    CUdevResourceDesc dC;
-    CUgreenCtx gC;
-    CUstream st2;
-    if (want > 0 && ep("cuGreenCtxGetDevResource", (void**)&pGreenRes) &&
-        pGreenRes(gB, &resB, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
-        pSplit(sub, &nb2, &resB, &rem2, 0, (unsigned)want) == CUDA_SUCCESS && nb2 == 1 &&
-        pDesc(&dC, &sub[0], 1) == CUDA_SUCCESS && pCreate(&gC, dC, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS &&
-        pStream(&st2, gC, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS)
-      tri2 = (cudaStream_t)st2;
-    else
-      cudaGetLastError();
-    return true;
-  }
+  // streams of this host thread inside the process-wide SM partition of the device (sm_partition below)
+  bool init_partition(int dev, int prio_lo, int prio_hi);
+  bool tried = false;
   bool init() {
-    if (ok) return true;
+    if (ok || tried) return ok;
+    tried = true;
     int lo = 0, hi = 0, dev = 0;
     if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) return false;
     if (!init_partition(dev, lo, hi)) {
@@ -664,6 +609,85 @@ struct LookAhead {
   }
 };
 static thread_local LookAhead g_la_dev[16];  // per host thread and device
+
+// Process-wide SM partition of one device: the green contexts are created once (first use, any thread) and live as
+// long as the process; every host thread creates its own streams inside them.
+struct SmPartition {
+  std::once_flag once;
+  bool ok = false;
+  bool have_sub = false;
+  int chain_sms = 0;
+  CUgreenCtx chain_ctx{}, bulk_ctx{}, sub_ctx{};
+  CUresult (*stream_create)(CUstream*, CUgreenCtx, unsigned, int) = nullptr;
+};
+static SmPartition g_sm_partition[16];
+
+static void sm_partition_create(SmPartition& P, int dev) {
+  const char* env = getenv("LFM_SM_PARTITION");
+  if (env && atoi(env) == 0) return;
+  // Nsight Compute cannot replay kernels launched into a green context ("Failed to prepare kernel for profiling"):
+  // under ncu the chain falls back to stream priorities (ncu serialises the launches anyway)
+  if (!env && (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NV_TPS_LAUNCH_TOKEN"))) return;
+  CUresult (*pDevGet)(CUdevice*, int) = nullptr;
+  CUresult (*pGetRes)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+  CUresult (*pSplit)(CUdevResource*, unsigned*, const CUdevResource*, CUdevResource*, unsigned, unsigned) = nullptr;
+  CUresult (*pDesc)(CUdevResourceDesc*, CUdevResource*, unsigned) = nullptr;
+  CUresult (*pCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned) = nullptr;
+  CUresult (*pGreenRes)(CUgreenCtx, CUdevResource*, CUdevResourceType) = nullptr;
+  auto ep = [](const char* name, void** fn) {
+    cudaDriverEntryPointQueryResult q;
+    return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && *fn != nullptr;
+  };
+  if (!ep("cuDeviceGet", (void**)&pDevGet) || !ep("cuDeviceGetDevResource", (void**)&pGetRes) ||
+      !ep("cuDevSmResourceSplitByCount", (void**)&pSplit) || !ep("cuDevResourceGenerateDesc", (void**)&pDesc) ||
+      !ep("cuGreenCtxCreate", (void**)&pCreate) || !ep("cuGreenCtxStreamCreate", (void**)&P.stream_create)) {
+    cudaGetLastError();
+    return;
+  }
+  CUdevice cudev;
+  CUdevResource all, grp[1], rem;
+  unsigned nb = 1;
+  if (pDevGet(&cudev, dev) != CUDA_SUCCESS || pGetRes(cudev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+  if (all.sm.smCount < 64) return;
+  if (pSplit(grp, &nb, &all, &rem, 0, 8) != CUDA_SUCCESS || nb != 1 || grp[0].sm.smCount < 8 || rem.sm.smCount < 32) return;
+  CUdevResourceDesc dA, dB;
+  if (pDesc(&dA, &grp[0], 1) != CUDA_SUCCESS || pDesc(&dB, &rem, 1) != CUDA_SUCCESS) return;
+  if (pCreate(&P.chain_ctx, dA, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+  if (pCreate(&P.bulk_ctx, dB, cudev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+  P.chain_sms = (int)grp[0].sm.smCount;
+  P.ok = true;
+  // A third context on HALF of the large partition (its SMs belong to both): the top node of the interleaved inverse
+  // issues T = L21 W11, (n/2)^3 flops in one launch of long-lived 64 x 64-tile CTAs, in the middle of the
+  // factorisation.  On the whole partition it took every slot for 280 us and the (short) trailing updates of the
+  // chain-bound second half queued behind it; confined to half of the SMs it runs underneath that half instead.
+  const char* e2 = getenv("LFM_TRI2_SMS");
+  const int want = e2 ? atoi(e2) : 72;
+  CUdevResource resB, sub[1], rem2;
+  unsigned nb2 = 1;
+  CUdevResourceDesc dC;
+  if (want > 0 && ep("cuGreenCtxGetDevResource", (void**)&pGreenRes) &&
+      pGreenRes(P.bulk_ctx, &resB, CU_DEV_RESOURCE_TYPE_SM) == CUDA_SUCCESS &&
+      pSplit(sub, &nb2, &resB, &rem2, 0, (unsigned)want) == CUDA_SUCCESS && nb2 == 1 &&
+      pDesc(&dC, &sub[0], 1) == CUDA_SUCCESS && pCreate(&P.sub_ctx, dC, cudev, CU_GREEN_CTX_DEFAULT_STREAM) == CUDA_SUCCESS)
+    P.have_sub = true;
+  else
+    cudaGetLastError();
+}
+
+bool LookAhead::init_partition(int dev, int prio_lo, int prio_hi) {
+  if (dev < 0 || dev >= 16) return false;
+  SmPartition& P = g_sm_partition[dev];
+  std::call_once(P.once, sm_partition_create, std::ref(P), dev);
+  if (!P.ok) return false;
+  CUstream sc, sb, stri, st2;
+  if (P.stream_create(&sc, P.chain_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+  if (P.stream_create(&sb, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+  if (P.stream_create(&stri, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
+  chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri;
+  chain_sms = P.chain_sms;
+  if (P.have_sub && P.stream_create(&st2, P.sub_ctx, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS) tri2 = (cudaStream_t)st2;
+  return true;
+}
 
 static int lookahead_mode() {
   static int v = -1;

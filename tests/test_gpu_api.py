@@ -414,3 +414,34 @@ def test_evaluation_plan_replays_the_eager_path(cuda):
     m2, hist = tr.fit()
     _, h_ref = o.fit(model.pack(), x, y, 1e-4, num_iters=5)
     assert relerr(hist, h_ref) < 1e-9
+
+
+def test_sm_partition_is_a_scheduling_choice_only(cuda, tmp_path):
+    """The factorisation's streams live in green contexts (8-SM chain partition, 140-SM bulk partition, 72-SM
+    sub-partition: csrc/chol.cu).  Which SMs a kernel runs on must not change a single bit of the result: the same
+    N = 2048 evaluation (one right-looking sweep with the interleaved inverse, 16 blocks) in a child process with
+    LFM_SM_PARTITION=0 (ordinary priority streams) equals this process's, eager and through a CUDA-graph plan."""
+    import subprocess
+    import sys
+    from dis_project_b200 import ops
+    G, T = 32, 64
+    x, y, var, _ = o.synthetic_problem(G, T, 1, seed=61)
+    th = o.Params.reference_init(G).pack()
+    out, info = ops.nlml_grad(x, y, th, 1e-4, G)
+    plan = ops.NlmlGradPlan(x, y, G, 1e-4)
+    out_p, _ = plan(th)
+    assert int(info.item()) == 0 and torch.equal(out, out_p)
+    plan.close()
+    v_ref, g_ref = o.nlml_and_grad(o.Params.reference_init(G), x, y)
+    got = out.cpu().numpy()
+    assert abs(got[0] - v_ref) <= RTOL * abs(v_ref) and relerr(got[1:], g_ref) < RTOL
+    np.savez(tmp_path / "in.npz", x=x, y=y, th=th)
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); from dis_project_b200 import ops; "
+            "d = np.load(%r); out, info = ops.nlml_grad(d['x'], d['y'], d['th'], 1e-4, %d); "
+            "np.save(%r, out.cpu().numpy())"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "in.npz"), G,
+               str(tmp_path / "out.npy")))
+    env = dict(os.environ, LFM_SM_PARTITION="0")
+    subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+    other = np.load(tmp_path / "out.npy")
+    assert np.array_equal(other, got)
