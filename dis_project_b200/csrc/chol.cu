@@ -566,12 +566,12 @@ static int chain_fused_mode() {
 
 // Right-looking blocked Cholesky with 128-wide panels and one step of look-ahead for small / medium n.
 // The dependent chain  leaf(k) -> L(k+1,k) = A(k+1,k) W_kk^T -> A(k+1,k+1) -= L(k+1,k) L(k+1,k)^T -> leaf(k+1)
-// runs on an internal HIGH-PRIORITY stream (its CTAs are placed before pending bulk CTAs whenever an SM
-// frees up; the two 128-row products run as 16 x 128 tiles over 8 CTAs each); the rest of the panel and of
-// the trailing update of step k stays on the caller's stream underneath leaf(k+1):
+// runs on an internal stream of its own SM partition (below); the rest of the panel and of the trailing update of
+// step k runs on the bulk stream underneath leaf(k+1):
 //   bulk : wait leaf(k) | rows >= k+2 of the panel | wait L(k+1,k) | trailing update minus block (k+1,k+1)
 //   chain: wait bulk(k-1) before the panel of step k reads A(k+1, k)
-// Fork/join is by events only (no host synchronisation; legal under stream capture).
+// Fork/join is by events only (no host synchronisation; legal under stream capture).  Without the partition the chain
+// stream is a high-priority stream and the bulk stream is the caller's.
 struct LookAhead {
   cudaStream_t chain = nullptr, tri = nullptr;
   cudaStream_t bulk = nullptr;   // SM partition only: the bulk stream of the large partition (else the caller's stream)

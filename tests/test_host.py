@@ -220,3 +220,16 @@ def test_loss_key_is_order_preserving():
     back = loss_key_to_float(keys)
     assert np.array_equal(back, v)
     assert loss_key_to_float(np.array([np.iinfo(np.int64).max]))[0] == np.inf
+
+
+def test_library_links_against_the_runtime_only():
+    """The SM partition of the factorisation uses driver-API entry points (green contexts) obtained through
+    cudaGetDriverEntryPoint at run time: the shared library must not gain a link-time dependency on libcuda, or it
+    would stop loading on a host without a driver (this container, a reference maintainer's build box)."""
+    import re
+    import subprocess
+    from dis_project_b200 import _lib
+    out = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    needed = re.findall(r"\(NEEDED\)\s+Shared library: \[([^\]]+)\]", out)
+    assert any(n.startswith("libcudart") for n in needed), needed
+    assert not any(n.startswith("libcuda.so") for n in needed), needed
