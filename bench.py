@@ -37,7 +37,10 @@ CONFIG = {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000
                       "initial hyper-parameters", "N": 4000, "G": G_C2, "T": T_C2,
           "launch": "one CUDA-graph replay per evaluation (ops.NlmlGradPlan / lfm_plan_launch); e2e: lfm_nlml_grad_host",
           "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
-          "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2"}
+          "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2",
+          "scheduling": "factorisation streams in green contexts when the driver exports them (8-SM chain partition, 140-SM "
+                        "bulk partition, 72-SM sub-partition for the top-node product of the inverse; LFM_SM_PARTITION=0 "
+                        "= stream priorities only)"}
 
 
 # synthetic inputs built here so that the product arm never imports oracle/
