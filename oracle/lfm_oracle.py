@@ -271,18 +271,23 @@ def mean_function(p: Params, x: np.ndarray) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 # objective (objectives.py:64-78) and its gradient
 # --------------------------------------------------------------------------- #
-def sigma_matrix(p: Params, x: np.ndarray) -> np.ndarray:
+def sigma_matrix(p: Params, x: np.ndarray, variances=None) -> np.ndarray:
+    """K + jitter I + sigma^2 I (objectives.py:70-73).  `variances` (N,) adds diag(variances): the heteroscedastic
+    convention of the GPyTorch twin, which puts the measurement variances inside the kernel when it trains
+    (src/gpytorch_alfi/model_alfi.py:294-299); None = the GPJax objective."""
     K = gram(p, x)
     n = K.shape[0]
     K[np.diag_indices(n)] += p.jitter
     K[np.diag_indices(n)] += p.sigma**2
+    if variances is not None:
+        K[np.diag_indices(n)] += np.asarray(variances, dtype=np.float64).reshape(-1)
     return K
 
 
-def nlml(p: Params, x: np.ndarray, y: np.ndarray) -> float:
+def nlml(p: Params, x: np.ndarray, y: np.ndarray, variances=None) -> float:
     """CustomConjMLL(negative=True) (objectives.py:21-78)."""
     y = np.asarray(y, dtype=np.float64).reshape(-1)
-    S = sigma_matrix(p, x)
+    S = sigma_matrix(p, x, variances)
     z = y - mean_function(p, x)
     L = cholesky(S, lower=True)
     a = solve_triangular(L, z, lower=True)
@@ -315,7 +320,8 @@ def _h_partials(p: Params, a, b, u, v):
     return H, dH_da, dH_db, dH_dl
 
 
-def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 256, threads: int | None = None):
+def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 256, threads: int | None = None,
+                  variances=None):
     """Closed-form NLML and gradient w.r.t. the CONSTRAINED theta=[d,s,b,l,sigma].
 
     K_bar = 1/2 (S^-1 - a a^T); dNLML/dtheta = sum_ij K_bar_ij dK_ij/dtheta (+ mean terms).
@@ -345,6 +351,8 @@ def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 256, 
         list(ex.map(build, bounds))
         S[np.diag_indices(n)] += p.jitter
         S[np.diag_indices(n)] += p.sigma**2
+        if variances is not None:   # heteroscedastic convention (see sigma_matrix): constant in theta, the gradient
+            S[np.diag_indices(n)] += np.asarray(variances, dtype=np.float64).reshape(-1)   # formulas are unchanged
         mu = mean_function(p, x)
         z = y - mu
         c, info = dpotrf(S, lower=1, overwrite_a=1, clean=0)
@@ -401,17 +409,17 @@ def nlml_and_grad(p: Params, x: np.ndarray, y: np.ndarray, *, chunk: int = 256, 
     return float(val), grad
 
 
-def nlml_and_grad_unc(theta_unc: np.ndarray, x, y, jitter: float):
+def nlml_and_grad_unc(theta_unc: np.ndarray, x, y, jitter: float, variances=None):
     """value_and_grad of JaxTrainer.loss w.r.t. the UNCONSTRAINED leaves (trainer.py:86-131)."""
     theta = constrain(theta_unc)
-    val, g = nlml_and_grad(Params.unpack(theta, jitter), x, y)
+    val, g = nlml_and_grad(Params.unpack(theta, jitter), x, y, variances=variances)
     return val, g * constrain_jac(theta_unc)
 
 
 # --------------------------------------------------------------------------- #
 # torch-fp64 autograd of the same expressions (independent gradient derivation)
 # --------------------------------------------------------------------------- #
-def nlml_and_grad_unc_autograd(theta_unc: np.ndarray, x, y, jitter: float):
+def nlml_and_grad_unc_autograd(theta_unc: np.ndarray, x, y, jitter: float, variances=None):
     import torch
 
     x = np.asarray(x, dtype=np.float64)
@@ -439,6 +447,8 @@ def nlml_and_grad_unc_autograd(theta_unc: np.ndarray, x, y, jitter: float):
     tt, tp = t[:, None], t[None, :]
     K = s[j] * s[k] * l * SQRT_PI * 0.5 * (hh(k, j, tp, tt) + hh(j, k, tt, tp))
     S = K + (jitter + sigma**2) * torch.eye(n, dtype=torch.float64)
+    if variances is not None:
+        S = S + torch.diag(torch.as_tensor(np.asarray(variances, dtype=np.float64).reshape(-1)))
     mu = torch.repeat_interleave(b / d, n // G) * flag
     z = yv - mu
     Lc = torch.linalg.cholesky(S)

@@ -151,6 +151,28 @@ def test_gradients_two_derivations():
         assert abs(v1 - o.nlml(o.Params.unpack(o.constrain(u), 1e-4), x, y)) < 1e-11 * abs(v1)
 
 
+def test_heteroscedastic_objective_two_derivations():
+    """sigma_matrix(variances=...): the GPyTorch twin's training convention (measurement variances on the diagonal,
+    src/gpytorch_alfi/model_alfi.py:294-299).  Closed-form gradient against torch autograd of the literal expressions;
+    the variances are constants, so only Sigma changes; zero variances reproduce the GPJax objective bit for bit."""
+    for (G, T, R, seed) in ((5, 7, 3, 3), (3, 6, 1, 4)):
+        x, y, var, _ = o.synthetic_problem(G, T, R, seed=seed)
+        u = o.unconstrain(rand_params(G, seed + 20).pack())
+        v0, g0 = o.nlml_and_grad_unc(u, x, y, 1e-4)
+        vz, gz = o.nlml_and_grad_unc(u, x, y, 1e-4, variances=np.zeros_like(var))
+        assert vz == v0 and np.array_equal(gz, g0)
+        v1, g1 = o.nlml_and_grad_unc(u, x, y, 1e-4, variances=var)
+        v2, g2 = o.nlml_and_grad_unc_autograd(u, x, y, 1e-4, variances=var)
+        assert abs(v1 - v2) < 1e-11 * abs(v2)
+        assert np.max(np.abs(g1 - g2)) < 1e-10 * np.max(np.abs(g2))
+        assert abs(v1 - o.nlml(o.Params.unpack(o.constrain(u), 1e-4), x, y, variances=var)) < 1e-11 * abs(v1)
+        assert abs(v1 - v0) > 1e-6 * abs(v0)   # the term is not a no-op
+        S = o.sigma_matrix(o.Params.unpack(o.constrain(u), 1e-4), x, var)
+        S0 = o.sigma_matrix(o.Params.unpack(o.constrain(u), 1e-4), x)
+        assert np.allclose(np.diag(S) - np.diag(S0), var.reshape(-1), rtol=0, atol=1e-15)
+        assert np.array_equal(S - np.diag(np.diag(S)), S0 - np.diag(np.diag(S0)))
+
+
 def test_reference_constants_and_bijectors():
     p = o.Params.reference_init(5)
     assert np.all(p.d == 0.4) and np.all(p.s == 1.0) and np.all(p.b == 0.05) and p.l == 2.5 and p.sigma == 1.0
