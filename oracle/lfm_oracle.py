@@ -5,13 +5,20 @@ module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker
 (or as the timed CPU arm), never as the product path.
 
-PARITY UNPINNED.  The reference (wejpurvis/DIS_project) ships no tests, no
-golden vectors and no fixtures for this path, and its stack (jax 0.4.28,
-gpjax 0.8.2, cola-ml 0.0.5, optax 0.1.9, tfp 0.22.1 -- environment.yml:48-119)
-is not installable in this container, so the restatement below cannot be run
-against the reference itself.  It is pinned instead by (tests/test_oracle.py):
-  * an independent arbitrary-precision (mpmath, 50 digits) evaluation of
-    single kernel entries written from the formulas in src/model.py:197-365,
+PARITY PINNED TO REFERENCE SOURCE EXECUTED HERE.  The reference (wejpurvis/DIS_project) ships no
+tests, no golden vectors and no fixtures for this path, and its stack (jax 0.4.28, gpjax 0.8.2,
+cola-ml 0.0.5, optax 0.1.9, tfp 0.22.1 -- environment.yml:48-119) is not installable in this
+container.  Its own source files are nevertheless executable: ``tests/refshim`` provides torch-fp64
+stand-ins for those packages, under which the UNMODIFIED ``src/{dataset,model,objectives,trainer,
+utils}.py`` run end to end (CSV loader, kernels, objective, jax.value_and_grad, the 150-step
+trainer.fit, both posteriors).  ``tests/golden/make_ref_golden.py`` writes what they return to
+``tests/golden/ref_*.json``; ``tests/test_ref_parity.py`` asserts this oracle against those files
+(NLML 1e-12, gradients 1e-10, covariance entries 1e-11, posteriors 1e-9, fit history 1e-9; with
+``LITERAL_ERF_SUMS`` the covariance entries agree to 1e-14), and the CUDA path against the same
+files.  What remains restated rather than executed is the third-party arithmetic listed below.
+Independent anchors kept from round 1 (tests/test_oracle.py):
+  * an arbitrary-precision (mpmath, 50 digits) evaluation of single kernel entries and of the
+    whole path (NLML, gradient, latent posterior) written from the formulas in src/model.py:197-365,
   * a second restatement of the GPyTorch twin's block formulas
     (src/gpytorch_alfi/model_alfi.py:302-382,414-476),
   * torch-fp64 autograd of the same expressions versus the closed-form
