@@ -57,6 +57,12 @@ SIGNATURES = {
     "lfm_nlml_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
     "lfm_nlml_grad_unc_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_het_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_het_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_unc_het_tg": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_plan_create_het": (_int, [C.POINTER(C.c_void_p), _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _int,
+                                             _ptr, _sz, _ptr, _ptr]),
+    "lfm_nlml_grad_het_host": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _int, _ptr, _ptr]),
     "lfm_latent_posterior_workspace_bytes": (_sz, [_i64, _int, _i64]),
     "lfm_latent_posterior": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _dbl, _i64, _ptr, _ptr, _sz,
                                     _ptr, _ptr, _ptr]),

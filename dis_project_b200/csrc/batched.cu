@@ -26,6 +26,7 @@
 
 
 #include "batched.cuh"
+#include <vector>
 
 template <int BT>
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -412,18 +413,12 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) 
   if (smem > 227 * 1024) return LFM_ERR_UNSUPPORTED;
   const bool small = b.max_unique <= 64 && b.N <= 128 && 3 * b.G + 2 <= 128;
   if (!small && 3 * b.G + 2 > 256) return LFM_ERR_UNSUPPORTED;
-  static size_t conf128 = 0, conf256 = 0;
+  static LfmSmemConfig conf128, conf256;
   if (small) {
-    if (smem > conf128) {
-      LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conf128 = smem;
-    }
+    LFM_CUDA_OK(lfm_ensure_smem(lfm_batched_kernel<128>, conf128, smem));
     lfm_batched_kernel<128><<<(unsigned)b.B, 128, smem, st>>>(b);
   } else {
-    if (smem > conf256) {
-      LFM_CUDA_OK(cudaFuncSetAttribute(lfm_batched_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conf256 = smem;
-    }
+    LFM_CUDA_OK(lfm_ensure_smem(lfm_batched_kernel<256>, conf256, smem));
     lfm_batched_kernel<256><<<(unsigned)b.B, 256, smem, st>>>(b);
   }
   LFM_LAUNCHED(1);
@@ -566,16 +561,26 @@ extern "C" int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G,
                             info, nullptr, nullptr);
 }
 
-// Number of distinct (time, gene, flag) rows of a HOST copy of X: the `unique_rows_hint` that lets the
-// batched kernels size their shared memory by the compressed problem.
+// Number of rows of the duplicate-row-compressed problem for a HOST copy of X: the `unique_rows_hint` that
+// lets the batched kernels size their shared memory.  Mirrors the kernels' own rule: the distinct
+// (time, gene, flag) rows when every distinct row occurs the same number of times R > 1 (replicates on a
+// shared design), otherwise N (no compression: e.g. one replicate with a missing measurement).
 extern "C" int lfm_count_unique_rows(int64_t N, const double* X_host) {
   if (N <= 0 || !X_host) return 0;
+  std::vector<int64_t> rep((size_t)N), cnt((size_t)N, 0);
   int U = 0;
   for (int64_t i = 0; i < N; ++i) {
-    bool dup = false;
-    for (int64_t j = 0; j < i && !dup; ++j)
-      dup = X_host[3 * j] == X_host[3 * i] && X_host[3 * j + 1] == X_host[3 * i + 1] && X_host[3 * j + 2] == X_host[3 * i + 2];
-    if (!dup) ++U;
+    rep[i] = i;
+    for (int64_t j = 0; j < i; ++j)
+      if (X_host[3 * j] == X_host[3 * i] && X_host[3 * j + 1] == X_host[3 * i + 1] && X_host[3 * j + 2] == X_host[3 * i + 2]) {
+        rep[i] = rep[j];
+        break;
+      }
+    if (rep[i] == i) ++U;
+    ++cnt[rep[i]];
   }
-  return U;
+  const int64_t R = cnt[0];
+  for (int64_t i = 0; i < N; ++i)
+    if (cnt[rep[i]] != R) return (int)N;
+  return R > 1 ? U : (int)N;
 }

@@ -1312,11 +1312,8 @@ size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
 // differently sized problems share it).
 template <int NW>
 static cudaError_t team_smem(size_t bytes) {
-  static size_t conf = 0;
-  if (bytes <= conf) return cudaSuccess;
-  const cudaError_t e = cudaFuncSetAttribute(lfm_batched_warp_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-  if (e == cudaSuccess) conf = bytes;
-  return e;
+  static LfmSmemConfig conf;
+  return lfm_ensure_smem(lfm_batched_warp_kernel<NW>, conf, bytes);
 }
 template <int NW>
 static int team_launch(cudaStream_t st, const BatchedArgs& a, int time_grid, size_t bytes) {
@@ -1347,13 +1344,16 @@ static int team_choice(int64_t B, size_t bytes, size_t bytes_team) {
   const char* env = getenv("LFM_BATCHED_TEAM");
   const int forced = env ? atoi(env) : 0;
   if (forced == 1 || forced == 4 || forced == 8) return forced;
-  static size_t cached_bytes = 0, cached_team = 0;
-  static int s1 = 0, s4 = 0, sms = 0;
-  if (bytes != cached_bytes || bytes_team != cached_team) {
+  // occupancy of the two instantiations for this layout: cached per host thread and device (a thread drives one device
+  // at a time; another thread, or the same thread after cudaSetDevice, re-queries)
+  thread_local size_t cached_bytes = 0, cached_team = 0;
+  thread_local int cached_dev = -2, s1 = 0, s4 = 0, sms = 0;
+  const int dev_now = lfm_current_device();
+  if (bytes != cached_bytes || bytes_team != cached_team || dev_now != cached_dev) {
     int dev = 0;
     s1 = team_slots<1>(bytes); s4 = team_slots<4>(bytes_team);
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
-    cached_bytes = bytes; cached_team = bytes_team;
+    cached_bytes = bytes; cached_team = bytes_team; cached_dev = dev_now;
   }
   if (s1 <= 0 || s4 <= 0 || sms <= 0) return 1;
   auto wave1 = [&](int64_t n) { return 1.0 + 0.11 * (double)n / (double)s1; };

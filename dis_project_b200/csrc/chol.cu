@@ -405,12 +405,9 @@ __global__ void __launch_bounds__(LEAF_THREADS, 1) lfm_potrf_leaf_kernel(double*
   if (tid == 0 && failed >= 0) atomicCAS(info, 0, pivot_base + failed + 1);
 }
 
+static LfmSmemConfig g_leaf_smem;
 static int leaf(cudaStream_t st, double* A, int64_t lda, double* W, int64_t ldw, int* info, int64_t pivot_base) {
-  static bool configured = false;
-  if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-    configured = true;
-  }
+  LFM_CUDA_OK(lfm_ensure_smem(lfm_potrf_leaf_kernel, g_leaf_smem, LEAF_SMEM));
   lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, st>>>(A, lda, W, ldw, info, (int)pivot_base, nullptr);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
@@ -548,11 +545,8 @@ __global__ void __cluster_dims__(8, 1, 1) __launch_bounds__(256, 1)
   }
 }
 static int chain_step(cudaStream_t st, double* P, int64_t ld, const double* Wkk, int64_t ldw, double* Cd) {
-  static bool configured = false;
-  if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_chain_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
-    configured = true;
-  }
+  static LfmSmemConfig smem_cfg;
+  LFM_CUDA_OK(lfm_ensure_smem(lfm_chain_step_kernel, smem_cfg, CS_SMEM));
   lfm_chain_step_kernel<<<8, 256, CS_SMEM, st>>>(P, ld, Wkk, ldw, Cd);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
@@ -919,11 +913,7 @@ int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* 
 // Debug: one leaf with clock64() stamps at its phase boundaries (16 values: start, loaded, then per
 // sub-block [diag, trailing] x 4, L stored, 3 inverse levels, W stored).
 extern "C" int lfm_debug_leaf_profile(lfm_stream_t stream, double* A, double* W, int* info, long long* stamps) {
-  static bool configured = false;
-  if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-    configured = true;
-  }
+  LFM_CUDA_OK(lfm_ensure_smem(lfm_potrf_leaf_kernel, g_leaf_smem, LEAF_SMEM));
   lfm_potrf_leaf_kernel<<<1, LEAF_THREADS, LEAF_SMEM, (cudaStream_t)stream>>>(A, NB, W, NB, info, 0, stamps);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;

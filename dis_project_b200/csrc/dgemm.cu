@@ -315,12 +315,8 @@ template <int TA, int TBN, int WM, int WN, int GM, bool SPREAD>
 static int launch(cudaStream_t st, const LfmGemm& g) {
   constexpr int BM = 8 * WM * GM, BN = 32 * WN;
   constexpr int SMEM = STAGES * (BM + BN) * LDK * 8;
-  static bool configured = false;
-  if (!configured) {
-    LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SMEM));
-    configured = true;
-  }
+  static LfmSmemConfig smem_cfg;
+  LFM_CUDA_OK(lfm_ensure_smem(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, smem_cfg, SMEM));
   const int64_t tm = g.M / BM, tn = g.N / BN;
   int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   if (g.lower_only && g.tri_skip > 0) {

@@ -13,6 +13,7 @@
 // The table entries are produced by the same lfm_pair_terms() the direct path calls.
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include "sim_math.cuh"
 
 #define GRID_EMPTY 0xFFFFFFFFFFFFFFFFull
@@ -162,18 +163,26 @@ int lfm_grid_build(cudaStream_t st, int64_t N, int G, const double* X, const dou
 // Host helper: number of distinct times in a HOST copy of X (the `time_grid` bound callers pass).
 extern "C" int64_t lfm_count_distinct_times(int64_t N, const double* X_host) {
   if (N <= 0 || !X_host) return 0;
-  double* t = (double*)malloc(sizeof(double) * (size_t)N);  // sorted distinct values found so far
+  double* t = (double*)malloc(sizeof(double) * (size_t)N);
   if (!t) return 0;
-  // insertion into a sorted prefix is O(N T); T is small whenever the answer is useful
+  // insertion into a sorted prefix: O(N log T) comparisons + O(T^2) moves while T stays small (the useful case);
+  // once more than 512 distinct values have been seen, sort the whole column instead (O(N log N), never O(N^2))
   int64_t cnt = 0;
-  for (int64_t i = 0; i < N; ++i) {
+  bool many = false;
+  for (int64_t i = 0; i < N && !many; ++i) {
     const double v = X_host[3 * i];
     int64_t lo = 0, hi = cnt;
     while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (t[mid] < v) lo = mid + 1; else hi = mid; }
     if (lo < cnt && t[lo] == v) continue;
+    if (cnt == 512) { many = true; break; }
     for (int64_t k = cnt; k > lo; --k) t[k] = t[k - 1];
     t[lo] = v;
     ++cnt;
+  }
+  if (many) {
+    for (int64_t i = 0; i < N; ++i) t[i] = X_host[3 * i];
+    std::sort(t, t + N);
+    cnt = std::unique(t, t + N) - t;
   }
   free(t);
   return cnt;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/lfm_b200.h"
 
 #define LFM_SQRT_PI 1.7724538509055160273
@@ -20,9 +21,29 @@
     if (_s != LFM_OK) return _s; \
   } while (0)
 
-// Launch accounting (bench.py's gpu_launches) and optional per-launch CUDA-event timing of the GEMM kernel.
-extern unsigned long long g_lfm_launches;
-#define LFM_LAUNCHED(n) (g_lfm_launches += (unsigned long long)(n))
+// Launch accounting (bench.py's gpu_launches): any host thread may launch.
+extern std::atomic<unsigned long long> g_lfm_launches;
+#define LFM_LAUNCHED(n) (g_lfm_launches.fetch_add((unsigned long long)(n), std::memory_order_relaxed))
+
+// Function attributes (opt-in dynamic shared memory) are per DEVICE, and one process may drive several devices from
+// several threads: every kernel keeps one of these (static storage, zero-initialised) and raises the attribute on
+// the current device the first time a launch there needs more than it has been given.  Two threads racing on the
+// same device both set the attribute, which is harmless.
+#define LFM_MAX_DEVICES 16
+struct LfmSmemConfig { std::atomic<size_t> bytes[LFM_MAX_DEVICES]; };
+static inline int lfm_current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= LFM_MAX_DEVICES) return -1;
+  return dev;
+}
+template <class Kernel>
+static inline cudaError_t lfm_ensure_smem(Kernel kernel, LfmSmemConfig& cfg, size_t bytes) {
+  const int dev = lfm_current_device();
+  if (dev >= 0 && cfg.bytes[dev].load(std::memory_order_acquire) >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0) cfg.bytes[dev].store(bytes, std::memory_order_release);
+  return e;
+}
 
 // Dense block size: every dense matrix is padded to a multiple of LFM_NB rows/cols.
 #define LFM_NB 128

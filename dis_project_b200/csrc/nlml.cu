@@ -256,28 +256,35 @@ static int check_common(int64_t N, int G, const void* X, const void* y, const vo
 
 // Shared front half: z, time-grid tables, Sigma, Cholesky.  Leaves L in ws.A and the inverted diagonal
 // blocks in ws.W; `grid` is the table view the gradient contraction reuses.
-static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* theta,
-                       double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info) {
+// `variances` (N doubles or NULL) adds diag(variances) to Sigma: the heteroscedastic objective of the GPyTorch twin
+// (src/gpytorch_alfi/model_alfi.py:294-299); it touches the diagonal tiles of the Sigma build only.
+static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* variances,
+                       const double* theta, double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info) {
   LFM_TRY(lfm_launch_residual(st, N, s.Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_grid_build(st, N, G, X, theta, s.Tu, grad, s.grid, grid));
-  LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, nullptr, jitter, 1, s.A, s.Np, grid));
+  LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, variances, jitter, 1, s.A, s.Np, grid));
   // the gradient needs W = L^-1 as well: built together with the factorisation
   return grad ? lfm_potrf_trtri(st, s.Np, s.A, s.Np, s.W, s.Np, info) : lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
 }
 
-extern "C" int lfm_nlml_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
-                           const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
-                           double* out, int* info) {
+extern "C" int lfm_nlml_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                               const double* variances, const double* theta, double jitter, int64_t time_grid,
+                               void* ws, size_t ws_bytes, double* out, int* info) {
   LFM_TRY(check_common(N, G, X, y, theta, time_grid, ws, ws_bytes, out, info));
   cudaStream_t st = (cudaStream_t)stream;
   const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
   LfmGrid grid;
-  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, false, &grid, info));
+  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, false, &grid, info));
   LFM_TRY(trsv_rec(st, s.Np, s.A, s.Np, s.W, s.Np, s.z));  // z <- L^-1 z
   lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.z, info, out);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
+}
+extern "C" int lfm_nlml_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                           const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
+                           double* out, int* info) {
+  return lfm_nlml_het_tg(stream, N, G, X, y, nullptr, theta, jitter, time_grid, ws, ws_bytes, out, info);
 }
 extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
                         const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info) {
@@ -306,11 +313,11 @@ __global__ void lfm_diag_copy_kernel(int64_t n, const double* __restrict__ A, in
   if (i < n) d[i] = A[i * lda + i];
 }
 
-static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, const double* y,
+static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* variances,
                           const double* theta, double jitter, const NlmlWs& s, double* out, int* info) {
   const int P = 3 * G + 2;
   LfmGrid grid;
-  LFM_TRY(nlml_factor(st, N, G, X, y, theta, jitter, s, true, &grid, info));
+  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, true, &grid, info));
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
   if (dev >= 0 && g_eval_side[dev].init()) {
@@ -344,12 +351,17 @@ static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, co
   return LFM_OK;
 }
 
+extern "C" int lfm_nlml_grad_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                                    const double* variances, const double* theta, double jitter, int64_t time_grid,
+                                    void* ws, size_t ws_bytes, double* out, int* info) {
+  LFM_TRY(check_common(N, G, X, y, theta, time_grid, ws, ws_bytes, out, info));
+  const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
+  return nlml_grad_impl((cudaStream_t)stream, N, G, X, y, variances, theta, jitter, s, out, info);
+}
 extern "C" int lfm_nlml_grad_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
                                 const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
                                 double* out, int* info) {
-  LFM_TRY(check_common(N, G, X, y, theta, time_grid, ws, ws_bytes, out, info));
-  const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
-  return nlml_grad_impl((cudaStream_t)stream, N, G, X, y, theta, jitter, s, out, info);
+  return lfm_nlml_grad_het_tg(stream, N, G, X, y, nullptr, theta, jitter, time_grid, ws, ws_bytes, out, info);
 }
 extern "C" int lfm_nlml_grad(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
                              const double* theta, double jitter, void* ws, size_t ws_bytes, double* out,
@@ -360,6 +372,11 @@ extern "C" int lfm_nlml_grad(lfm_stream_t stream, int64_t N, int G, const double
 extern "C" int lfm_nlml_grad_unc_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
                                     const double* theta_unc, double jitter, int64_t time_grid, void* ws,
                                     size_t ws_bytes, double* out, int* info) {
+  return lfm_nlml_grad_unc_het_tg(stream, N, G, X, y, nullptr, theta_unc, jitter, time_grid, ws, ws_bytes, out, info);
+}
+extern "C" int lfm_nlml_grad_unc_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                                        const double* variances, const double* theta_unc, double jitter,
+                                        int64_t time_grid, void* ws, size_t ws_bytes, double* out, int* info) {
   LFM_TRY(check_common(N, G, X, y, theta_unc, time_grid, ws, ws_bytes, out, info));
   cudaStream_t st = (cudaStream_t)stream;
   const NlmlWs s = nlml_ws_layout(N, G, time_grid, ws);
@@ -367,7 +384,7 @@ extern "C" int lfm_nlml_grad_unc_tg(lfm_stream_t stream, int64_t N, int G, const
   lfm_constrain_kernel<<<(P + 127) / 128, 128, 0, st>>>(1, G, theta_unc, s.theta);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
-  LFM_TRY(nlml_grad_impl(st, N, G, X, y, s.theta, jitter, s, out, info));
+  LFM_TRY(nlml_grad_impl(st, N, G, X, y, variances, s.theta, jitter, s, out, info));
   lfm_chain_kernel<<<(P + 127) / 128, 128, 0, st>>>(G, theta_unc, out + 1);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());

@@ -36,6 +36,26 @@ def _rows3(X: torch.Tensor, name: str) -> torch.Tensor:
     return X
 
 
+def _check_training_flags(X) -> None:
+    """The training covariance Sigma is built from k_xx only (every training row of the reference has flag 1,
+    dataset.py:388; objectives.py:70 would blend the other branches in for flag-0 rows).  A host copy of X is checked
+    here; a device-resident X is the caller's responsibility (include/lfm_b200.h, lfm_nlml)."""
+    if isinstance(X, torch.Tensor):
+        if X.is_cuda or X.ndim != 2 or X.shape[1] != 3:
+            return
+        bad = bool((X[:, 2] != 1).any())
+    else:
+        import numpy as np
+
+        Xh = np.asarray(X)
+        if Xh.ndim != 2 or Xh.shape[1] != 3:
+            return
+        bad = bool((Xh[:, 2] != 1).any())
+    if bad:
+        raise ValueError("training inputs must all carry flag 1 (gene expression rows): the objective and the "
+                         "posteriors build Sigma from k_xx only")
+
+
 def _theta(theta: torch.Tensor, G: int) -> torch.Tensor:
     theta = _dev(theta).reshape(-1)
     if theta.numel() != 3 * G + 2:
@@ -149,9 +169,20 @@ def distinct_times(X) -> int:
     return int(_lib.lib().lfm_count_distinct_times(Xh.shape[0], Xh.ctypes.data))
 
 
-def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int, time_grid: Optional[int] = None):
+def _variances(variances, N: int) -> Optional[torch.Tensor]:
+    if variances is None:
+        return None
+    v = _dev(variances).reshape(-1)
+    if v.numel() != N:
+        raise ValueError(f"variances has {v.numel()} values for {N} input rows")
+    return v
+
+
+def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int, time_grid: Optional[int] = None,
+               variances=None):
     if time_grid is None:
         time_grid = distinct_times(X)
+    _check_training_flags(X)
     X = _rows3(X, "x")
     y = _dev(y).reshape(-1)
     theta = _theta(theta, G)
@@ -165,8 +196,10 @@ def _nlml_call(fn_name: str, X, y, theta, jitter: float, G: int, nout: int, time
     ws = _workspace(nbytes, X.device, "nlml")
     out = torch.empty(nout, dtype=F64, device=X.device)
     info = torch.zeros(1, dtype=torch.int32, device=X.device)
-    _lib.check(getattr(l, fn_name)(_stream(), N, G, X.data_ptr(), y.data_ptr(), theta.data_ptr(), float(jitter),
-                                   int(time_grid), ws.data_ptr(), ws.numel(), out.data_ptr(), info.data_ptr()),
+    v = _variances(variances, N)
+    _lib.check(getattr(l, fn_name)(_stream(), N, G, X.data_ptr(), y.data_ptr(), v.data_ptr() if v is not None else None,
+                                   theta.data_ptr(), float(jitter), int(time_grid), ws.data_ptr(), ws.numel(),
+                                   out.data_ptr(), info.data_ptr()),
                fn_name)
     return out, info
 
@@ -180,11 +213,13 @@ class NlmlGradPlan:
 
     `out` / `info` are the plan's own buffers: copy them if they must survive the next call."""
 
-    def __init__(self, X, y, G: int, jitter: float, unconstrained: bool = False, time_grid: Optional[int] = None):
+    def __init__(self, X, y, G: int, jitter: float, unconstrained: bool = False, time_grid: Optional[int] = None,
+                 variances=None):
         import ctypes as C
 
         if time_grid is None:
             time_grid = distinct_times(X)
+        _check_training_flags(X)
         self.X = _rows3(X, "x")
         self.y = _dev(y).reshape(-1)
         self.G, self.P = int(G), 3 * int(G) + 2
@@ -193,6 +228,7 @@ class NlmlGradPlan:
             raise ValueError(f"y has {self.y.numel()} values for {N} input rows")
         if N % G:
             raise ValueError(f"{N} rows is not divisible by num_genes={G} (model.py:145-149)")
+        self.variances = _variances(variances, N)   # heteroscedastic objective (include/lfm_b200.h)
         dev = self.X.device
         l = _lib.lib()
         self.theta = torch.ones(self.P, dtype=F64, device=dev)  # a valid point for the warm-up evaluation
@@ -203,10 +239,12 @@ class NlmlGradPlan:
         self.ws = torch.empty(int(l.lfm_nlml_workspace_bytes_tg(N, G, int(time_grid))), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize(dev)
         self._plan = C.c_void_p()
-        _lib.check(l.lfm_nlml_grad_plan_create(C.byref(self._plan), N, G, self.X.data_ptr(), self.y.data_ptr(),
-                                               self.theta.data_ptr(), float(jitter), int(time_grid),
-                                               int(bool(unconstrained)), self.ws.data_ptr(), self.ws.numel(),
-                                               self.out.data_ptr(), self.info.data_ptr()), "lfm_nlml_grad_plan_create")
+        _lib.check(l.lfm_nlml_grad_plan_create_het(C.byref(self._plan), N, G, self.X.data_ptr(), self.y.data_ptr(),
+                                                   self.variances.data_ptr() if self.variances is not None else None,
+                                                   self.theta.data_ptr(), float(jitter), int(time_grid),
+                                                   int(bool(unconstrained)), self.ws.data_ptr(), self.ws.numel(),
+                                                   self.out.data_ptr(), self.info.data_ptr()),
+                   "lfm_nlml_grad_plan_create_het")
 
     def __call__(self, theta):
         t = theta if isinstance(theta, torch.Tensor) else torch.as_tensor(theta, dtype=F64)
@@ -228,24 +266,26 @@ class NlmlGradPlan:
             pass
 
 
-def nlml(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None):
-    """CustomConjMLL(negative=True) value (reference src/objectives.py:21-78).  Returns (val[1], info[1]).
-    `time_grid`: bound on the distinct times of X (None: counted from X; 0: evaluate every entry directly)."""
-    return _nlml_call("lfm_nlml_tg", X, y, theta, jitter, G, 1, time_grid)
+def nlml(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None, variances=None):
+    """CustomConjMLL(negative=True) (reference src/objectives.py:21-78): (out[1] = NLML, info[1]).
+    `variances` (N,) adds diag(variances) to Sigma: the heteroscedastic objective of the reference's GPyTorch twin
+    (src/gpytorch_alfi/model_alfi.py:294-299)."""
+    return _nlml_call("lfm_nlml_het_tg", X, y, theta, jitter, G, 1, time_grid, variances)
 
 
-def nlml_grad(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None):
-    """NLML and d NLML / d theta in constrained coordinates.  Returns (out[1+P], info[1])."""
-    return _nlml_call("lfm_nlml_grad_tg", X, y, theta, jitter, G, 3 * G + 3, time_grid)
+def nlml_grad(X, y, theta, jitter: float, G: int, time_grid: Optional[int] = None, variances=None):
+    """NLML and its gradient w.r.t. the constrained theta: out[0] = NLML, out[1:] = gradient."""
+    return _nlml_call("lfm_nlml_grad_het_tg", X, y, theta, jitter, G, 3 * G + 3, time_grid, variances)
 
 
-def nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Optional[int] = None):
+def nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Optional[int] = None, variances=None):
     """jax.value_and_grad(JaxTrainer.loss) w.r.t. the unconstrained leaves (reference src/trainer.py:126)."""
-    return _nlml_call("lfm_nlml_grad_unc_tg", X, y, theta_unc, jitter, G, 3 * G + 3, time_grid)
+    return _nlml_call("lfm_nlml_grad_unc_het_tg", X, y, theta_unc, jitter, G, 3 * G + 3, time_grid, variances)
 
 
 def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):
     """ExactLFM.latent_predict (reference src/model.py:420-463): returns (mean[T*], var[T*], info[1])."""
+    _check_training_flags(X)
     X = _rows3(X, "x")
     Xs = _rows3(Xstar, "test_inputs")
     y = _dev(y).reshape(-1)
@@ -272,6 +312,7 @@ def latent_posterior(X, y, variances, theta, jitter: float, Xstar, G: int):
 
 def gene_posterior(X, y, variances, theta, jitter: float, Xstar, G: int, full_cov: bool = True):
     """ExactLFM.multi_gene_predict (reference src/model.py:465-514): (mean[T*], cov[T*,T*] or None, var[T*], info)."""
+    _check_training_flags(X)
     X = _rows3(X, "x")
     Xs = _rows3(Xstar, "test_inputs")
     y = _dev(y).reshape(-1)
@@ -321,6 +362,7 @@ def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Opt
     `time_grid`: bound on the distinct times of X (None: counted from X; 0: one CTA per LFM, no tables)."""
     hint = unique_rows(X)
     tg = distinct_times(X) if time_grid is None else int(time_grid)
+    _check_training_flags(X)
     X = _rows3(X, "x")
     u = _dev(theta_unc)
     P = 3 * G + 2
@@ -424,6 +466,7 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     y is (N,) (multi-start: one data set, B start points) or (B, N) (one row of observations per LFM)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
+        _check_training_flags(X)
     if state.time_grid is None:
         state.time_grid = distinct_times(X)
     X = _rows3(X, "x")

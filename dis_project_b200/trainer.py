@@ -63,6 +63,7 @@ class JaxTrainer:
         n = self.training_data.n
         return (isinstance(self.objective, CustomConjMLL) and self.objective.negative
                 and isinstance(self.optim, GradientTransformation) and self.optim.name == "adam"
+                and getattr(self.objective, "variances", None) is None  # the batched kernels have no variance term
                 and n <= 128 and n % self.model.num_genes == 0 and not self.track_parameters)
 
     def fit(self, fix_params: Optional[bool] = True, num_steps_per_epoch: Optional[int] = 1000) -> tuple:
@@ -76,8 +77,11 @@ class JaxTrainer:
                                   self.model.jitter, self.num_iters, lr=self.optim.learning_rate, b1=self.optim.b1,
                                   b2=self.optim.b2, eps=self.optim.eps, fix_params=bool(fix_params),
                                   steps_per_epoch=int(num_steps_per_epoch))
-            self.model = self.model.with_leaves(st.theta[0].cpu().numpy())
-            self.history = st.hist[0].cpu().numpy()
+            theta, hist, info, _ = ops.batched_to_host(st)
+            if int(info[0]) < 0:  # the kernel refused the problem (not a numerical failure, which gives NaN like JAX)
+                raise RuntimeError(f"batched fit kernel refused the problem (info = {int(info[0])})")
+            self.model = self.model.with_leaves(theta[0])
+            self.history = hist[0]
         else:
             state = self.optim.init(self.model)
             model = self.model

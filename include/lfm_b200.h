@@ -41,7 +41,7 @@ typedef enum lfm_status {
   LFM_ERR_NO_DEVICE = -5    /* no sm_100 device: there is NO CPU fallback                       */
 } lfm_status;
 
-#define LFM_ABI_VERSION 1
+#define LFM_ABI_VERSION 2
 
 int lfm_abi_version(void);
 const char* lfm_status_string(int status);
@@ -79,7 +79,11 @@ int lfm_unconstrain(lfm_stream_t stream, int64_t B, int G, const double* theta, 
 size_t lfm_nlml_workspace_bytes(int64_t N, int G);
 
 /* CustomConjMLL(negative=True)(model, Dataset(X, y)) (src/objectives.py:21-78):
- * Sigma = K + jitter I + sigma^2 I; out[0] = 1/2 [N log 2pi + log det Sigma + z^T Sigma^-1 z]. */
+ * Sigma = K + jitter I + sigma^2 I; out[0] = 1/2 [N log 2pi + log det Sigma + z^T Sigma^-1 z].
+ * TRAINING ROWS MUST ALL CARRY FLAG 1: Sigma is built from k_xx alone (every training row of the reference has flag
+ * 1, src/dataset.py:388); for a flag-0 row objectives.py:70 would blend k_xf / k_ff in, which this path (and the
+ * posteriors' training covariance, and the batched fits) does not do.  The *_host entry points and the Python layer
+ * reject such X (LFM_ERR_UNSUPPORTED / ValueError); device-pointer callers are trusted. */
 int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
              const double* theta, double jitter, void* ws, size_t ws_bytes, double* out, int* info);
 
@@ -115,6 +119,22 @@ int lfm_nlml_grad_unc_tg(lfm_stream_t stream, int64_t N, int G, const double* X,
                          const double* theta_unc, double jitter, int64_t time_grid, void* ws, size_t ws_bytes,
                          double* out, int* info);
 
+/* ---- heteroscedastic objective ----------------------------------------------------------------
+ * Sigma = K + diag(variances) + jitter I + sigma^2 I: the measurement variances of dataset_3d
+ * (src/dataset.py:396-397) inside the training covariance, the convention of the reference's GPyTorch twin when it
+ * trains (src/gpytorch_alfi/model_alfi.py:294-299: K_xx += 1e-4 I; K_xx += self.variance).  `variances` is N doubles
+ * (device) or NULL, in which case these ARE the entry points above.  The gradient formulas do not change
+ * (d Sigma / d theta has no variance term); only the diagonal tiles of the Sigma build read `variances`. */
+int lfm_nlml_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y, const double* variances,
+                    const double* theta, double jitter, int64_t time_grid, void* ws, size_t ws_bytes, double* out,
+                    int* info);
+int lfm_nlml_grad_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                         const double* variances, const double* theta, double jitter, int64_t time_grid, void* ws,
+                         size_t ws_bytes, double* out, int* info);
+int lfm_nlml_grad_unc_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
+                             const double* variances, const double* theta_unc, double jitter, int64_t time_grid,
+                             void* ws, size_t ws_bytes, double* out, int* info);
+
 /* ---- (d) latent posterior -------------------------------------------------------------------- */
 
 size_t lfm_latent_posterior_workspace_bytes(int64_t N, int G, int64_t Tstar);
@@ -140,10 +160,11 @@ int lfm_gene_posterior(lfm_stream_t stream, int64_t N, int G, const double* X, c
 
 /* ---- batched multi-start path (many independent small LFMs per GPU) -------------------------- */
 
-/* Number of distinct rows of a HOST copy of X.  Passing it as `unique_rows_hint` lets the batched
- * kernels size their shared memory for the duplicate-row-compressed problem (the p53 layout repeats
- * each (time, gene) row once per replicate); 0 means "unknown" (sized for N).  A hint smaller than
- * the true count makes the kernels refuse with info = -1. */
+/* Rows of the duplicate-row-compressed problem for a HOST copy of X: the number of distinct rows when every distinct
+ * (time, gene, flag) row occurs the same number of times R > 1 (the p53 layout repeats each row once per replicate),
+ * else N -- the batched kernels compress only uniform multiplicities, and this mirrors their rule.  Passing it as
+ * `unique_rows_hint` lets them size their shared memory for the compressed problem; 0 means "unknown" (sized for N).
+ * A hint smaller than what the kernel finds makes it refuse with info = -1. */
 int lfm_count_unique_rows(int64_t N, const double* X_host);
 
 /* B independent value_and_grad evaluations sharing (X, y): theta_unc is B x P, out_val B,
@@ -230,6 +251,10 @@ typedef struct lfm_plan lfm_plan;
 int lfm_nlml_grad_plan_create(lfm_plan** out_plan, int64_t N, int G, const double* X, const double* y,
                               const double* theta, double jitter, int64_t time_grid, int unconstrained, void* ws,
                               size_t ws_bytes, double* out, int* info);
+/* same with the heteroscedastic objective: `variances` (N device doubles, bound like X and y) or NULL */
+int lfm_nlml_grad_plan_create_het(lfm_plan** out_plan, int64_t N, int G, const double* X, const double* y,
+                                  const double* variances, const double* theta, double jitter, int64_t time_grid,
+                                  int unconstrained, void* ws, size_t ws_bytes, double* out, int* info);
 int lfm_plan_launch(lfm_plan* plan, lfm_stream_t stream);
 int lfm_plan_destroy(lfm_plan* plan);
 
@@ -239,6 +264,9 @@ int lfm_handle_destroy(lfm_handle* h);
 
 int lfm_nlml_grad_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
                        const double* theta, double jitter, int unconstrained, double* out, int* info);
+/* heteroscedastic objective from host buffers: `variances` N host doubles or NULL (= lfm_nlml_grad_host) */
+int lfm_nlml_grad_het_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y, const double* variances,
+                           const double* theta, double jitter, int unconstrained, double* out, int* info);
 int lfm_latent_posterior_host(lfm_handle* h, int64_t N, int G, const double* X, const double* y,
                               const double* variances, const double* theta, double jitter,
                               int64_t Tstar, const double* Xstar, double* out_mean, double* out_var,

@@ -533,7 +533,7 @@ def generate_test_times(t: int = 100) -> np.ndarray:
 # --------------------------------------------------------------------------- #
 def fit(theta0: np.ndarray, x, y, jitter: float, *, num_iters: int = 150, lr: float = 0.01,
         fix_params: bool = True, num_steps_per_epoch: int = 1000, b1: float = 0.9,
-        b2: float = 0.999, eps: float = 1e-8, grad_fn=None):
+        b2: float = 0.999, eps: float = 1e-8, grad_fn=None, variances=None):
     """JaxTrainer(...).fit (trainer.py:162-228).  theta0 is CONSTRAINED; returns
     (final constrained theta, loss history (num_iters,))."""
     grad_fn = grad_fn or nlml_and_grad_unc
@@ -543,7 +543,7 @@ def fit(theta0: np.ndarray, x, y, jitter: float, *, num_iters: int = 150, lr: fl
     v = np.zeros_like(u)
     hist = np.empty(num_iters)
     for step in range(num_iters):
-        val, g = grad_fn(u, x, y, jitter)
+        val, g = grad_fn(u, x, y, jitter) if variances is None else grad_fn(u, x, y, jitter, variances=variances)
         hist[step] = val
         m = b1 * m + (1 - b1) * g
         v = b2 * v + (1 - b2) * g * g

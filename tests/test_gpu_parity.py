@@ -185,7 +185,7 @@ def test_batched_eval(cuda, G, T, R):
 
 
 @pytest.mark.parametrize("team", [1, 4])
-@pytest.mark.parametrize("R,fix", [(1, True), (3, True), (1, False)])
+@pytest.mark.parametrize("R,fix", [(1, True), (3, True), (1, False), (3, False)])   # (3, False) = notebook.py:36,73-75
 def test_batched_fit_matches_trainer(cuda, R, fix, team, monkeypatch):
     """150 Adam steps with the p21 hook (trainer.py:162-228), B restarts, split into chunks; warp-per-LFM kernel
     (register Cholesky) and four-warp team kernel (symmetric sweep)."""
@@ -298,3 +298,129 @@ def test_batched_per_lfm_observations(cuda, team, time_grid, monkeypatch):
         assert relerr(res.history, hist) < 1e-12 and res.best_id == int(np.argmin(hist[:, -1]))
     with pytest.raises(ValueError):
         ops.batched_nlml_grad_unc(x, Y[:, :-1], U, 1e-4, G)
+
+
+@pytest.mark.parametrize("team", [0, 1, 4])
+def test_batched_non_uniform_duplicate_rows(cuda, team, monkeypatch):
+    """a design with NON-uniformly duplicated rows (three replicates, one measurement missing) is not
+    compressed; the batched kernels must fit it at full size instead of refusing (info = -1, NaN)."""
+    from dis_project_b200 import ops
+    if team:
+        monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
+    G, T = 4, 5
+    x, y, var, _ = o.synthetic_problem(G, T, 2, seed=21)          # N = 40, every row twice
+    keep = np.ones(x.shape[0], dtype=bool); keep[[27, 33, 36, 39]] = False   # drop 4 rows of the second replicate
+    x, y = np.ascontiguousarray(x[keep]), np.ascontiguousarray(y[keep])      # N = 36, divisible by G
+    assert ops.unique_rows(x) == 36
+    th0 = o.Params.reference_init(G).pack()
+    TH = np.stack([th0, th0 * 1.1])
+    val, grad, info = ops.batched_nlml_grad_unc(x, y, o.unconstrain(TH), 1e-4, G, time_grid=0 if team == 0 else None)
+    assert np.all(info.cpu().numpy() == 0)
+    for b in range(2):
+        v_ref, g_ref = o.nlml_and_grad_unc(o.unconstrain(TH[b]), x, y, 1e-4)
+        assert abs(val[b].item() - v_ref) <= RTOL * abs(v_ref) and relerr(grad[b].cpu().numpy(), g_ref) < RTOL
+    st = ops.BatchedFitState(TH, G, 20)
+    if team == 0:
+        st.time_grid = 0
+    ops.batched_fit_steps(st, x, y, 1e-4, 20, fix_params=False)
+    theta, hist, info, _ = ops.batched_to_host(st)
+    assert np.all(info == 0)
+    for b in range(2):
+        th_ref, h_ref = o.fit(TH[b], x, y, 1e-4, num_iters=20, fix_params=False)
+        assert relerr(hist[b], h_ref) < 1e-9 and relerr(theta[b], th_ref) < 1e-8
+
+
+@pytest.mark.parametrize("G,T,R", [(5, 7, 1), (5, 7, 3), (6, 50, 1)])
+def test_heteroscedastic_objective(cuda, G, T, R):
+    """Sigma = K + diag(variances) + jitter I + sigma^2 I (src/gpytorch_alfi/model_alfi.py:294-299) on the device:
+    value, constrained and unconstrained gradient against the oracle's closed form AND against torch autograd of the
+    literal expressions; eager, time-grid and direct paths, the evaluation plan and the host-buffer entry point."""
+    import ctypes as C
+    from dis_project_b200 import _lib, ops
+    x, y, var, _ = o.synthetic_problem(G, T, R, seed=31)
+    var = var * np.random.default_rng(32).uniform(0.5, 20.0, var.shape)     # make the term matter
+    p = rand_params(G, 33)
+    v_ref, g_ref = o.nlml_and_grad(p, x, y, variances=var)
+    v_hom, _ = o.nlml_and_grad(p, x, y)
+    assert abs(v_ref - v_hom) > 1e-3 * abs(v_hom)
+    for tg in (None, 0):
+        v, info = ops.nlml(x, y, p.pack(), p.jitter, G, time_grid=tg, variances=var)
+        assert int(info.item()) == 0 and abs(v.item() - v_ref) <= RTOL * abs(v_ref)
+        out, info = ops.nlml_grad(x, y, p.pack(), p.jitter, G, time_grid=tg, variances=var)
+        out = out.cpu().numpy()
+        assert abs(out[0] - v_ref) <= RTOL * abs(v_ref) and relerr(out[1:], g_ref) < RTOL
+    u = o.unconstrain(p.pack())
+    vu_ref, gu_ref = o.nlml_and_grad_unc(u, x, y, p.jitter, variances=var)
+    va, ga = o.nlml_and_grad_unc_autograd(u, x, y, p.jitter, variances=var)
+    out, info = ops.nlml_grad_unc(x, y, u, p.jitter, G, variances=var)
+    out = out.cpu().numpy()
+    assert abs(out[0] - vu_ref) <= RTOL * abs(vu_ref) and relerr(out[1:], gu_ref) < RTOL
+    assert abs(out[0] - va) <= RTOL * abs(va) and relerr(out[1:], ga) < RTOL
+    plan = ops.NlmlGradPlan(x, y, G, p.jitter, unconstrained=True, variances=var)
+    pout, pinfo = plan(u)
+    assert np.array_equal(pout.cpu().numpy(), out)                              # replay == eager, bit for bit
+    plan.close()
+    lib = _lib.lib()
+    h = C.c_void_p()
+    assert lib.lfm_handle_create(C.byref(h)) == 0
+    hout = np.empty(3 * G + 3); hinfo = C.c_int(-1)
+    th = p.pack()
+    for _ in range(2):   # second call reuses the cached plan and the cached structure of X
+        assert lib.lfm_nlml_grad_het_host(h, x.shape[0], G, x.ctypes.data, y.ctypes.data, var.ctypes.data, th.ctypes.data,
+                                          p.jitter, 0, hout.ctypes.data, C.byref(hinfo)) == 0
+        assert hinfo.value == 0 and abs(hout[0] - v_ref) <= RTOL * abs(v_ref) and relerr(hout[1:], g_ref) < RTOL
+    assert lib.lfm_nlml_grad_het_host(h, x.shape[0], G, x.ctypes.data, y.ctypes.data, None, th.ctypes.data, p.jitter, 0,
+                                      hout.ctypes.data, C.byref(hinfo)) == 0
+    assert abs(hout[0] - v_hom) <= RTOL * abs(v_hom)                           # NULL variances == the plain objective
+    xbad = x.copy(); xbad[1, 2] = 0.0
+    assert lib.lfm_nlml_grad_host(h, x.shape[0], G, xbad.ctypes.data, y.ctypes.data, th.ctypes.data, p.jitter, 0,
+                                  hout.ctypes.data, C.byref(hinfo)) == -3        # flag-0 training row: refused
+    assert lib.lfm_handle_destroy(h) == 0
+
+
+def test_heteroscedastic_trainer_and_plan_cache(cuda):
+    """CustomConjMLL(variances=...) through JaxTrainer (host loop: the batched kernels have no variance term) against
+    the oracle's fit with the same objective; and the plan cache follows the CONTENTS of the data set."""
+    from dis_project_b200.gpx_compat import Dataset, adam
+    from dis_project_b200.model import ExactLFM
+    from dis_project_b200.objectives import CustomConjMLL
+    from dis_project_b200.trainer import JaxTrainer
+    x, y, var, _ = o.synthetic_problem(5, 7, 1, seed=41)
+    var = var * 10.0
+    model = ExactLFM(jitter=1e-4, num_genes=5)
+    loss = CustomConjMLL(negative=True, variances=var)
+    tr = JaxTrainer(model=model, objective=loss, training_data=Dataset(x, y.reshape(-1, 1)), optim=adam(0.01), key=None,
+                    num_iters=25)
+    trained, hist = tr.fit(fix_params=True)
+    th_ref, h_ref = o.fit(model.pack(), x, y, 1e-4, num_iters=25, fix_params=True, variances=var)
+    assert relerr(hist, h_ref) < 1e-9 and relerr(trained.pack(), th_ref) < 1e-8
+    # plan cache: same objective object, a second Dataset with other observations, then an in-place edit
+    plain = CustomConjMLL(negative=True)
+    u = model.unconstrain()
+    d1 = Dataset(x, y.reshape(-1, 1))
+    v1, _ = plain.value_and_grad(u, d1)
+    y2 = y * 1.5
+    d2 = Dataset(x, y2.reshape(-1, 1))
+    v2, _ = plain.value_and_grad(u, d2)
+    assert abs(v1 - o.nlml_and_grad_unc(o.unconstrain(model.pack()), x, y, 1e-4)[0]) <= RTOL * abs(v1)
+    assert abs(v2 - o.nlml_and_grad_unc(o.unconstrain(model.pack()), x, y2, 1e-4)[0]) <= RTOL * abs(v2)
+    d2.y[...] = y.reshape(-1, 1)            # in-place edit of the cached data set
+    v3, _ = plain.value_and_grad(u, d2)
+    assert abs(v3 - v1) <= 1e-12 * abs(v1)
+
+
+def test_bijector_kernels(cuda):
+    """lfm_constrain / lfm_unconstrain (tfp Softplus and Sigmoid(0.5, 3.5), model.py:66-111) against the oracle, B
+    vectors at once, including the tails where softplus is the identity to rounding."""
+    from dis_project_b200 import ops
+    G = 5
+    rng = np.random.default_rng(51)
+    U = rng.normal(0.0, 3.0, (7, 3 * G + 2))
+    U[0] = 0.0; U[1] = -30.0; U[2] = 30.0; U[2, 3 * G] = 12.0; U[1, 3 * G] = -12.0
+    th = ops.constrain(U, G).cpu().numpy()
+    ref = np.stack([o.constrain(u) for u in U])
+    assert relerr(th, ref) < 1e-14
+    assert np.all(th[:, 3 * G] >= 0.5) and np.all(th[:, 3 * G] <= 3.5)
+    back = ops.unconstrain(ref[3:], G).cpu().numpy()
+    assert relerr(back, np.stack([o.unconstrain(t) for t in ref[3:]])) < 1e-13
+    assert relerr(back, U[3:]) < 1e-9

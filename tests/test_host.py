@@ -4,6 +4,7 @@ import os
 import re
 
 import numpy as np
+import torch
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -25,7 +26,7 @@ def test_capi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/lfm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in dis_project_b200/_lib.py"
     l = _lib.lib()
-    assert l.lfm_abi_version() == 1
+    assert l.lfm_abi_version() == 2
     assert l.lfm_status_string(-5).decode().startswith("no sm_100")
     assert l.lfm_nlml_workspace_bytes(4000, 50) >= 2 * 4096 * 4096 * 8
     assert l.lfm_nlml_workspace_bytes(0, 5) == 0
@@ -208,6 +209,50 @@ def test_count_distinct_times():
     assert lib.lfm_count_distinct_times(0, None) == 0
     assert lib.lfm_nlml_workspace_bytes_tg(4000, 50, 80) > lib.lfm_nlml_workspace_bytes(4000, 50)
     assert lib.lfm_nlml_workspace_bytes_tg(120, 4, 120) == lib.lfm_nlml_workspace_bytes(120, 4)  # tables not worthwhile
+
+
+def test_count_distinct_times_many_values_and_unique_rows_rule():
+    """Host helpers: the distinct-time count switches to a sort beyond 512 values (never O(N^2)); the unique-row
+    hint mirrors the batched kernels' rule -- compress only when every distinct row occurs equally often."""
+    from dis_project_b200 import _lib, ops
+    lib = _lib.lib()
+    rng = np.random.default_rng(0)
+    t = rng.permutation(np.repeat(np.linspace(0, 50, 3000), 2))
+    x = np.ascontiguousarray(np.stack((t, np.zeros_like(t), np.ones_like(t)), axis=1))
+    assert lib.lfm_count_distinct_times(x.shape[0], x.ctypes.data) == 3000
+    base = np.stack((np.tile(np.linspace(0, 12, 7), 5), np.repeat(np.arange(5.0), 7), np.ones(35)), axis=1)
+    assert ops.unique_rows(base) == 35                                   # R = 1: no compression
+    assert ops.unique_rows(np.tile(base, (3, 1))) == 35                   # three replicates: 105 rows -> 35
+    ragged = np.ascontiguousarray(np.tile(base, (3, 1))[:-1])             # one replicate lost a measurement
+    assert ops.unique_rows(ragged) == 104                                 # non-uniform multiplicity: sized for N
+    assert lib.lfm_count_unique_rows(0, None) == 0
+
+
+def test_training_rows_must_carry_flag_one():
+    from dis_project_b200 import ops
+    x = np.stack((np.tile(np.linspace(0, 12, 7), 5), np.repeat(np.arange(5.0), 7), np.ones(35)), axis=1)
+    x[3, 2] = 0.0
+    with pytest.raises(ValueError, match="flag 1"):
+        ops._check_training_flags(x)
+    ops._check_training_flags(np.where(np.arange(3) == 2, 1.0, x))     # all flags 1: fine
+
+
+def test_objective_plan_key_follows_contents_not_object_ids():
+    """the CUDA-graph plan of CustomConjMLL must not be replayed for a different data set that happens to
+    live at the same address, nor after an in-place edit."""
+    from dis_project_b200.objectives import _content_token
+    a = np.arange(12.0).reshape(4, 3)
+    b = a.copy()
+    assert _content_token(a) == _content_token(b)
+    b[2, 1] = np.nextafter(b[2, 1], 100.0)
+    assert _content_token(a) != _content_token(b)
+    c = a.copy(); c[[0, 1]] = c[[1, 0]]                                  # same multiset of values, different order
+    assert _content_token(a) != _content_token(c)
+    assert _content_token(a.reshape(2, 6)) != _content_token(a)
+    t = torch.zeros(5, dtype=torch.float64)
+    k0 = _content_token(t)
+    t[1] = 3.0
+    assert _content_token(t) != k0                                        # torch version counter
 
 
 def test_loss_key_is_order_preserving():

@@ -205,9 +205,9 @@ def test_cuda_ops_match_reference_execution(cuda, name):
         out, info = ops.nlml_grad_unc(X, y, thu, jit, G)
         out = out.cpu().numpy()
         assert abs(out[0] - pt["nlml"]) <= RTOL * abs(pt["nlml"]) and rel(out[1:], pt["grad_unconstrained"]) < RTOL
-        bo, binfo = ops.batched_nlml_grad_unc(X, y, thu[None, :], jit, G)          # the batched small-N kernels
-        bo = bo.cpu().numpy()[0]
-        assert abs(bo[0] - pt["nlml"]) <= RTOL * abs(pt["nlml"]) and rel(bo[1:], pt["grad_unconstrained"]) < RTOL
+        bv, bg, binfo = ops.batched_nlml_grad_unc(X, y, thu[None, :], jit, G)      # the batched small-N kernels
+        assert int(binfo.item()) == 0 and abs(bv.item() - pt["nlml"]) <= RTOL * abs(pt["nlml"])
+        assert rel(bg.cpu().numpy()[0], pt["grad_unconstrained"]) < RTOL
         assert rel(ops.mean_function(X, th, G).cpu().numpy().reshape(-1), pt["mean_function"]) < 1e-15
         assert rel(ops.cross_covariance(rows, rows, th, G).cpu().numpy(), pt["K_block"]) < 1e-11
         assert rel(np.diag(ops.gram(X, th, G).cpu().numpy()), pt["gram_diag"]) < 1e-11
