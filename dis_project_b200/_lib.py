@@ -97,6 +97,7 @@ SIGNATURES = {
     "lfm_debug_profile_begin": (_int, []),
     "lfm_debug_profile_end": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "lfm_debug_profile_sum_ms": (C.c_double, []),
+    "lfm_debug_profile_variants": (_sz, [C.c_char_p, _sz]),
     "lfm_debug_profile_chain": (_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "lfm_debug_dgemm_nt": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "lfm_debug_potrf_potri": (_int, [_ptr, _i64, _ptr, _ptr, _ptr, _ptr]),

@@ -8,6 +8,7 @@
 // triangular Level-3 shape of the blocked Cholesky / inverse (SYRK, TRMM, LAUUM, TRSM via
 // inverted diagonal blocks) without multiplying structural zeros at tile granularity.
 #include <cstdlib>
+#include <cstring>
 #include "lfm_common.cuh"
 
 #define BK 16
@@ -222,12 +223,22 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
 
 // ---- optional per-launch timing (CUDA events on the launching stream) -----------------------------
 #include <algorithm>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
 #include <utility>
 #include <vector>
+// A process-wide DEBUG facility (bench.py's roofline pass, tools/): one profiling session at a time, serialised by a
+// mutex so that launches from several host threads stay well-defined; it is off on every product path.
 struct GemmProf {
   bool on = false;
+  std::mutex mu;
   std::vector<cudaEvent_t> ev;   // pairs
   std::vector<char> is_chain;    // per pair: launched with the 16 x 128 latency tile (look-ahead chain)
+  std::vector<int> variant;      // per pair: tile variant code TA TBN WM WN GM as decimal digits
+  std::vector<double> pair_flops;
+  std::string variants_json;     // filled by lfm_debug_profile_end
   size_t used = 0;
   double flops = 0.0;            // flops the launched tiles execute (tile-granular k-ranges), bulk launches
   double chain_flops = 0.0;
@@ -258,6 +269,8 @@ static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
 }
 
 extern "C" int lfm_debug_profile_begin(void) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  g_prof.variant.clear(); g_prof.pair_flops.clear(); g_prof.variants_json.clear();
   g_prof.on = true; g_prof.used = 0; g_prof.flops = 0.0; g_prof.launches = 0;
   g_prof.chain_flops = 0.0; g_prof.chain_launches = 0; g_prof.chain_ms = 0.0; g_prof.is_chain.clear();
   return LFM_OK;
@@ -266,8 +279,10 @@ extern "C" int lfm_debug_profile_begin(void) {
 // launches of lfm_dgemm_kernel.  The 16 x 128-tile launches of the look-ahead chain (a different template
 // instantiation, 8 CTAs, latency-bound by design) are accounted separately: lfm_debug_profile_chain.
 extern "C" int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   g_prof.on = false;
   LFM_CUDA_OK(cudaDeviceSynchronize());
+  std::map<int, std::pair<double, std::pair<double, long long>>> per;  // variant -> (ms, (flops, launches))
   // The factorisation launches on three streams, so launches overlap: the kernel time reported is the length
   // of the UNION of the launch intervals (time during which at least one bulk GEMM launch was executing), from
   // event timestamps relative to the first event; the plain sum is kept in g_prof.sum_ms.
@@ -279,6 +294,21 @@ extern "C" int lfm_debug_profile_end(double* total_ms, double* exec_flops, long 
     LFM_CUDA_OK(cudaEventElapsedTime(&t1, g_prof.ev[0], g_prof.ev[i + 1]));
     if (g_prof.is_chain[i / 2]) cms += (double)t1 - (double)t0;
     else { sum += (double)t1 - (double)t0; iv.emplace_back((double)t0, (double)t1); }
+    auto& b = per[g_prof.variant[i / 2]];
+    b.first += (double)t1 - (double)t0; b.second.first += g_prof.pair_flops[i / 2]; b.second.second += 1;
+  }
+  {
+    std::string js = "[";
+    char buf[256];
+    for (const auto& kv : per) {
+      const int v = kv.first;
+      snprintf(buf, sizeof buf, "%s{\"variant\": \"lfm_dgemm_kernel<%d,%d,%d,%d,%d>\", \"tile\": \"%dx%d\", \"launches\": %lld, "
+               "\"ms_sum\": %.6f, \"executed_flops\": %.6e}", js.size() > 1 ? ", " : "", v / 10000, v / 1000 % 10, v / 100 % 10,
+               v / 10 % 10, v % 10, 8 * (v / 100 % 10) * (v % 10), 32 * (v / 10 % 10), kv.second.second.second, kv.second.first,
+               kv.second.second.first);
+      js += buf;
+    }
+    g_prof.variants_json = js + "]";
   }
   std::sort(iv.begin(), iv.end());
   double uni = 0.0, cur_s = 0.0, cur_e = -1.0;
@@ -296,6 +326,17 @@ extern "C" int lfm_debug_profile_end(double* total_ms, double* exec_flops, long 
   return LFM_OK;
 }
 extern "C" double lfm_debug_profile_sum_ms(void) { return g_prof.sum_ms; }
+// JSON list of the last session's launches grouped by tile variant: launches, summed launch time (intervals overlap across
+// streams, so the sums can exceed the union), executed flops.  Copies at most n - 1 characters; returns the full length.
+extern "C" size_t lfm_debug_profile_variants(char* out, size_t n) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (out && n) {
+    const size_t m = g_prof.variants_json.size() < n - 1 ? g_prof.variants_json.size() : n - 1;
+    memcpy(out, g_prof.variants_json.data(), m);
+    out[m] = 0;
+  }
+  return g_prof.variants_json.size();
+}
 extern "C" int lfm_debug_profile_chain(double* total_ms, double* exec_flops, long long* launches) {
   if (total_ms) *total_ms = g_prof.chain_ms;
   if (exec_flops) *exec_flops = g_prof.chain_flops;
@@ -326,17 +367,22 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   }
   if (tiles <= 0) return LFM_OK;
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
-  if (g_prof.on) {
+  const bool prof = g_prof.on;
+  std::unique_lock<std::mutex> lock(g_prof.mu, std::defer_lock);
+  if (prof) {
+    lock.lock();
     cudaEventRecord(prof_event(), st);
     const double f = gemm_exec_flops(g, BM, BN) * (g.batch > 1 ? g.batch : 1);
     const bool chain = BM == 16;
     g_prof.is_chain.push_back(chain ? 1 : 0);
+    g_prof.variant.push_back(TA * 10000 + TBN * 1000 + WM * 100 + WN * 10 + GM);
+    g_prof.pair_flops.push_back(f);
     if (chain) { g_prof.chain_flops += f; g_prof.chain_launches += 1; }
     else { g_prof.flops += f; g_prof.launches += 1; }
   }
   const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
   lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
-  if (g_prof.on) cudaEventRecord(prof_event(), st);
+  if (prof) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;

@@ -303,6 +303,9 @@ unsigned long long lfm_debug_launch_count(void);
 int lfm_debug_profile_begin(void);
 int lfm_debug_profile_end(double* total_ms, double* exec_flops, long long* launches);
 double lfm_debug_profile_sum_ms(void);
+/* the last session grouped by tile variant, as a JSON list (launches, summed launch time, executed flops per variant);
+ * copies at most n - 1 characters into out and returns the full length */
+size_t lfm_debug_profile_variants(char* out, size_t n);
 /* the 16 x 128-tile launches of the factorisation's look-ahead chain, accounted separately (call after _end) */
 int lfm_debug_profile_chain(double* total_ms, double* exec_flops, long long* launches);
 

@@ -447,3 +447,17 @@ def test_sm_partition_is_a_scheduling_choice_only(cuda, tmp_path):
     subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
     other = np.load(tmp_path / "out.npy")
     assert np.array_equal(other, got)
+
+
+@pytest.mark.skipif(os.environ.get("LFM_FULLSIZE") != "1", reason="minutes of host time: set LFM_FULLSIZE=1 (tools/fullsize_parity.py)")
+def test_configs_3_and_5_full_size_oracle_parity(cuda, tmp_path):
+    """BASELINE configs 3 and 5 against the oracle at FULL size (N = 32768; 102 400 test times, the oracle on a sample of
+    256 of them): 1e-9 relative, north_star's tolerance.  Opt-in (about 3 minutes on 16 host cores); the record of the
+    last run is profiles/fullsize_parity_r2.json, checked by tests/test_host.py."""
+    import subprocess
+    import sys
+    out = tmp_path / "fullsize.json"
+    subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fullsize_parity.py"),
+                    "--out", str(out)], check=True)
+    res = json.load(open(out))
+    assert res["config3"]["pass"] and res["config5"]["pass"]

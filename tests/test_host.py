@@ -278,3 +278,14 @@ def test_library_links_against_the_runtime_only():
     needed = re.findall(r"\(NEEDED\)\s+Shared library: \[([^\]]+)\]", out)
     assert any(n.startswith("libcudart") for n in needed), needed
     assert not any(n.startswith("libcuda.so") for n in needed), needed
+
+
+def test_full_size_parity_record():
+    """The committed record of tools/fullsize_parity.py (run on a B200 box in round 2): configs 3 and 5 against the
+    oracle at full size, inside north_star's 1e-9."""
+    import json
+    rec = json.load(open(os.path.join(os.path.dirname(os.path.dirname(__file__)), "profiles", "fullsize_parity_r2.json")))
+    assert rec["N"] == 32768 and rec["Tstar"] == 102400 and rec["config5"]["sampled_test_points"] >= 256
+    assert rec["config3"]["rel_err_nlml"] < 1e-9 and rec["config3"]["rel_err_grad_vs_max_component"] < 1e-9
+    assert rec["config5"]["rel_err_mean"] < 1e-9 and rec["config5"]["rel_err_var"] < 1e-9
+    assert rec["config3"]["info"] == 0 and rec["config5"]["info"] == 0
