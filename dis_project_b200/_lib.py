@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "liblfm_b200.so")
 
 LFM_OK = 0
 STATUS = {0: "LFM_OK", -1: "LFM_ERR_INVALID", -2: "LFM_ERR_CUDA", -3: "LFM_ERR_UNSUPPORTED",
-          -4: "LFM_ERR_WORKSPACE", -5: "LFM_ERR_NO_DEVICE"}
+          -4: "LFM_ERR_WORKSPACE", -5: "LFM_ERR_NO_DEVICE", -6: "LFM_ERR_COMM"}
 
 
 class LfmError(RuntimeError):
@@ -80,9 +80,19 @@ SIGNATURES = {
                                                _ptr]),
     "lfm_batched_fit_multi": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                      _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    "lfm_batched_fit_trace": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
+                                     _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
     "lfm_batched_structure_bytes": (_sz, [_i64, _int, _int, _int]),
     "lfm_batched_team_size": (_int, [_i64, _i64, _int, _int, _int]),
     "lfm_batched_best": (_int, [_ptr, _i64, _int, _ptr, _i64, _i64, _ptr, _dbl, _ptr]),
+    "lfm_comm_available": (_int, []),
+    "lfm_comm_unique_id": (_int, [_ptr]),
+    "lfm_comm_create": (_int, [C.POINTER(_ptr), _int, _int, _ptr]),
+    "lfm_comm_world": (_int, [_ptr]),
+    "lfm_comm_rank": (_int, [_ptr]),
+    "lfm_comm_allreduce_min_i64": (_int, [_ptr, _ptr, _sz, _ptr]),
+    "lfm_comm_allgather_f64": (_int, [_ptr, _ptr, _ptr, _sz, _ptr]),
+    "lfm_comm_destroy": (_int, [_ptr]),
     "lfm_handle_create": (_int, [C.POINTER(_ptr)]),
     "lfm_handle_destroy": (_int, [_ptr]),
     "lfm_nlml_grad_host": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _dbl, _int, _ptr, _ptr]),

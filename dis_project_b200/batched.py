@@ -105,16 +105,56 @@ class MultiStartResult:
     best_trace: np.ndarray   # global best objective after every chunk
 
 
+_STAGE = {}
+
+
+def _stage_to_device(device, arrays):
+    """Host arrays -> device views through ONE pinned staging buffer and ONE host->device copy (cached per size)."""
+    import torch
+
+    sizes = [int(a.size) for a in arrays]
+    total = sum((n + 1) & ~1 for n in sizes)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), total)
+    bufs = _STAGE.get(key)
+    if bufs is None:
+        if len(_STAGE) > 16:
+            _STAGE.clear()
+        bufs = (torch.empty(max(total, 2), dtype=torch.float64, pin_memory=True),
+                torch.empty(max(total, 2), dtype=torch.float64, device=device))
+        _STAGE[key] = bufs
+    pinned, dbuf = bufs
+    hp = pinned.numpy()
+    views, off = [], 0
+    for a, n in zip(arrays, sizes):
+        hp[off:off + n] = np.asarray(a, dtype=np.float64).reshape(-1)
+        views.append(dbuf[off:off + n].view(*a.shape))
+        off += (n + 1) & ~1
+    dbuf.copy_(pinned, non_blocking=True)
+    return views
+
+
 def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr: float = 0.01,
-                    fix_params: bool = True, num_steps_per_epoch: int = 1000, chunk: int = 1,
-                    b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8) -> MultiStartResult:
+                    fix_params: bool = True, num_steps_per_epoch: int = 1000, chunk: Optional[int] = 1,
+                    b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, trace: bool = False,
+                    comm=None) -> MultiStartResult:
     """Fit all restarts of this rank's shard on the current CUDA device.
 
     `theta0_all` is the (B, P) array of constrained start points of the WHOLE job (every rank passes
     the same array); the function slices its own shard.  `y` is (N,) -- B restarts of one data set -- or
     (B, N): LFM b fits y[b] on the shared design X (replicas, gene subsets of equal size, candidate transcription
-    factors); the "winner" is then the LFM with the smallest final NLML over all data sets.  `chunk` optimiser steps run per kernel
-    launch; after every chunk the global best objective is all-reduced asynchronously.
+    factors); the "winner" is then the LFM with the smallest final NLML over all data sets.
+
+    Best-objective reduction across ranks (north_star: "one NCCL allreduce of best-objective ... state per step"):
+      * ``trace=False``: `chunk` optimiser steps run per kernel launch; after every launch ONE device word (the
+        atomicMin of the order-preserving image of every loss) is MIN-all-reduced on a side stream while the next
+        launch is already running.  ``chunk=1`` is the literal per-step all-reduce; ``best_trace`` has one entry
+        per chunk.
+      * ``trace=True``: the kernels record the best objective of EVERY step in a device vector (`step_keys`,
+        include/lfm_b200.h), the launches run `chunk` steps each (None: the whole fit in one launch), and the
+        per-step reduction over ranks rides in the ONE all-gather that also moves the winners: ``best_trace``
+        has one entry per step at the cost of a single collective per fit.
+    `comm`: a ``dis_project_b200.comm.LfmComm`` -- the collectives then run through the C-ABI's own NCCL communicator
+    (``lfm_comm_*``) and rank / world come from it; default: ``torch.distributed``.
     """
     import torch
     import torch.distributed as dist
@@ -123,7 +163,7 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
 
     import os
     import time
-    timing = os.environ.get("LFM_MSF_TIMING") == "1"   # debug: synchronising phase timers (tools/batched_probe3.py)
+    timing = os.environ.get("LFM_MSF_TIMING") == "1"   # debug: synchronising phase timers (tools/batched_scale.py)
     tmarks = [time.perf_counter()]
 
     def mark():
@@ -131,80 +171,107 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
             torch.cuda.synchronize()
             tmarks.append(time.perf_counter())
 
-    distributed = dist.is_available() and dist.is_initialized()
-    rank = dist.get_rank() if distributed else 0
-    world = dist.get_world_size() if distributed else 1
+    distributed = comm is not None or (dist.is_available() and dist.is_initialized())
+    if comm is not None:
+        rank, world = comm.rank, comm.world
+    else:
+        rank = dist.get_rank() if distributed else 0
+        world = dist.get_world_size() if distributed else 1
     theta0_all = np.asarray(theta0_all, dtype=np.float64)
     B, P = theta0_all.shape
     G = (P - 2) // 3
     lo, hi = shard_bounds(B, rank, world)
-    Xd = ops._rows3(X, "x")
+    if chunk is None or chunk <= 0:
+        chunk = max(num_iters, 1)
+    ops._lib.require_device()
+    device = X.device if isinstance(X, torch.Tensor) and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
     yh = y if isinstance(y, torch.Tensor) else np.asarray(y, dtype=np.float64)
-    if yh.ndim == 2 and yh.shape[0] == B and yh.shape[1] == Xd.shape[0] and B != 1:
-        yd = ops._dev(yh[lo:hi])      # one row of observations per LFM (replicas / candidate TFs): this rank's rows
+    per_lfm_y = yh.ndim == 2 and yh.shape[0] == B and yh.shape[1] == (X.shape[0]) and B != 1
+    host_inputs = not isinstance(X, torch.Tensor) and not isinstance(yh, torch.Tensor)
+    hint = tg = None
+    if host_inputs:
+        # everything this rank needs crosses PCIe in ONE copy: X, its observations, its start points
+        Xh = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        ops._check_training_flags(Xh)
+        hint, tg = ops.unique_rows(Xh), ops.distinct_times(Xh)  # from the host copy: no device->host round trip
+        ysel = np.ascontiguousarray(yh[lo:hi]) if per_lfm_y else yh.reshape(-1)
+        Xd, yd, th0 = _stage_to_device(device, [Xh, ysel, np.ascontiguousarray(theta0_all[lo:hi])])
+        Xd = ops._rows3(Xd, "x")
     else:
-        yd = ops._dev(yh).reshape(-1)  # multi-start: every LFM fits the same observations
+        Xd = ops._rows3(X, "x")
+        yd = ops._dev(yh[lo:hi]) if per_lfm_y else ops._dev(yh).reshape(-1)
+        th0 = theta0_all[lo:hi]
     nchunks = max((num_iters + chunk - 1) // chunk, 1)
-    # behind the state of the shard, in the same allocation: [loss, id, theta] of the shard's winner (P + 2), one
-    # best-objective word per chunk, and the winners of every rank (world x (P + 2)) -- read back in ONE copy
-    n_extra = (P + 2) + nchunks + world * (P + 2)
-    st = ops.BatchedFitState(theta0_all[lo:hi], G, num_iters, extra_doubles=n_extra) if hi > lo else None
-    if st is not None and not isinstance(X, torch.Tensor):
-        st.unique_hint = ops.unique_rows(X)  # from the host copy: no device->host round trip
-        st.time_grid = ops.distinct_times(X)
-    extra = st.extra if st is not None else torch.empty(n_extra, dtype=torch.float64, device=Xd.device)
-    packed = extra[:P + 2]
-    # per chunk ONE device word: the fit kernel atomic-mins the order-preserving integer image of every loss into
-    # it, the side stream MIN-all-reduces it across ranks -- no extra kernels, nothing the fit ever waits for
-    keys = extra[P + 2:P + 2 + nchunks].view(torch.int64)
+    nkeys = max(num_iters, 1) if trace else nchunks
+    # behind the state of the shard, in the same allocation: what this rank contributes to the final all-gather --
+    # [loss, id, theta] of the shard's winner (P + 2) and, with trace, the best objective of every step -- then the
+    # per-chunk best-objective words (without trace) and the gathered rows of every rank: read back in ONE copy
+    row = P + 2 + (nkeys if trace else 0)
+    n_extra = row + (0 if trace else nkeys) + world * row
+    st = ops.BatchedFitState(th0, G, num_iters, extra_doubles=n_extra) if hi > lo else None
+    if st is not None and hint is not None:
+        st.unique_hint, st.time_grid = hint, tg
+    extra = st.extra if st is not None else torch.empty(n_extra, dtype=torch.float64, device=device)
+    mine = extra[:row]
+    packed = mine[:P + 2]
+    keys = (mine[P + 2:] if trace else extra[row:row + nkeys]).view(torch.int64)
     keys.fill_(torch.iinfo(torch.int64).max)
-    allp = extra[P + 2 + nchunks:].view(world, P + 2)
+    allp = extra[n_extra - world * row:].view(world, row)
     main = torch.cuda.current_stream()
     multi = distributed and world > 1
-    side = _side_stream(Xd.device) if multi else None
+    side = _side_stream(device) if multi and not trace else None
     done = 0
     mark()
     for c in range((num_iters + chunk - 1) // chunk):
         steps = min(chunk, num_iters - done)
         if st is not None:
             ops.batched_fit_steps(st, Xd, yd, jitter, steps, lr=lr, b1=b1, b2=b2, eps=eps, fix_params=fix_params,
-                                  steps_per_epoch=num_steps_per_epoch, best_key=keys[c:c + 1])
+                                  steps_per_epoch=num_steps_per_epoch, best_key=None if trace else keys[c:c + 1],
+                                  step_keys=keys if trace else None)
         done += steps
-        if multi:
+        if side is not None:
             ev = torch.cuda.Event()
             ev.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(ev)
-                dist.all_reduce(keys[c:c + 1], op=dist.ReduceOp.MIN)
+                if comm is not None:
+                    comm.allreduce_min_i64(keys[c:c + 1], stream=side)
+                else:
+                    dist.all_reduce(keys[c:c + 1], op=dist.ReduceOp.MIN)
     mark()
-    if multi:
+    if side is not None:
         main.wait_stream(side)
     # ---- global winner: one launch packs the shard's [loss, id, theta(P)], ONE all-gather, ONE device->host copy ------
     have = st is not None and num_iters > 0
     ops.batched_best(st.hist if have else None, num_iters - 1 if have else 0, st.theta if have else None, float(lo), packed)
     gathered_on_host = None
     if multi:
-        if dist.get_backend() == "nccl":
-            dist.all_gather_into_tensor(allp.view(-1), packed)
+        if comm is not None:
+            comm.allgather_f64(mine, allp.view(-1))
+        elif dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(allp.view(-1), mine)
         else:  # gloo (CPU tests): gather on the host
-            buf = [torch.empty(P + 2, dtype=torch.float64) for _ in range(world)]
-            dist.all_gather(buf, packed.cpu())
+            buf = [torch.empty(row, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(buf, mine.cpu())
             gathered_on_host = torch.stack(buf).numpy()
     else:
-        allp[0].copy_(packed)
+        allp[0].copy_(mine)
     if st is not None:
         theta, hist, info, ex = ops.batched_to_host(st)
     else:
         theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
         ex = extra.cpu().numpy()
-    allp_h = gathered_on_host if gathered_on_host is not None else ex[P + 2 + nchunks:].reshape(world, P + 2)
-    keys_h = ex[P + 2:P + 2 + nchunks].view(np.int64)[:(num_iters + chunk - 1) // chunk]
+    allp_h = gathered_on_host if gathered_on_host is not None else ex[n_extra - world * row:].reshape(world, row)
+    if trace:
+        keys_h = allp_h[:, P + 2:].copy().view(np.int64).min(axis=0)[:num_iters]   # MIN over ranks, per step
+    else:
+        keys_h = ex[row:row + nkeys].view(np.int64)[:(num_iters + chunk - 1) // chunk]
     best = reduce_best_gathered(allp_h)
     best_id = int(best[1]) if np.isfinite(best[0]) else -1
     best_theta = None
     if best_id >= 0:
         owner = int(np.flatnonzero((allp_h[:, 0] == best[0]) & (allp_h[:, 1] == best[1]))[0])
-        best_theta = allp_h[owner, 2:].copy()
+        best_theta = allp_h[owner, 2:P + 2].copy()
     mark()
     if timing:
         global LAST_TIMING

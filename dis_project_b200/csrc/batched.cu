@@ -364,7 +364,10 @@ __global__ void __launch_bounds__(BT, (BT == 128) ? 4 : 2) lfm_batched_kernel(Ba
     if (tid == 0) {
       const double v = bad ? nan("") : nlml;
       if (eval_only) a.eval_val[bidx] = v;
-      else if (a.hist) a.hist[bidx * a.ld_hist + step] = v;
+      else {
+        if (a.hist) a.hist[bidx * a.ld_hist + step] = v;
+        if (a.step_keys && v == v) atomicMin(a.step_keys + step, lfm_loss_key(v));   // best objective of EVERY step
+      }
     }
     __syncthreads();
   }
@@ -470,6 +473,16 @@ extern "C" int lfm_batched_fit_multi(lfm_stream_t stream, int64_t B, int64_t N, 
                                      int total_steps, int fix_params, int steps_per_epoch, int unique_rows_hint,
                                      int time_grid_hint, double* out_hist, int64_t ld_hist, double* out_theta,
                                      int* info, long long* best_key, void* structure_cache) {
+  return lfm_batched_fit_trace(stream, B, N, G, X, y, y_stride, theta_unc_io, adam_state, jitter, lr, b1, b2, eps,
+                               first_step, steps, total_steps, fix_params, steps_per_epoch, unique_rows_hint,
+                               time_grid_hint, out_hist, ld_hist, out_theta, info, best_key, nullptr, structure_cache);
+}
+extern "C" int lfm_batched_fit_trace(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                                     int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter,
+                                     double lr, double b1, double b2, double eps, int first_step, int steps,
+                                     int total_steps, int fix_params, int steps_per_epoch, int unique_rows_hint,
+                                     int time_grid_hint, double* out_hist, int64_t ld_hist, double* out_theta,
+                                     int* info, long long* best_key, long long* step_keys, void* structure_cache) {
   if (steps < 0 || first_step < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
   if (first_step > 0 && !adam_state) return LFM_ERR_INVALID;
   if (N > 128) return LFM_ERR_UNSUPPORTED;
@@ -479,7 +492,7 @@ extern "C" int lfm_batched_fit_multi(lfm_stream_t stream, int64_t B, int64_t N, 
   a.jitter = jitter; a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
   a.first_step = first_step; a.steps = steps; a.total_steps = total_steps; a.fix_params = fix_params;
   a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
-  a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key;
+  a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key; a.step_keys = step_keys;
   a.struct_cache = structure_cache;
   return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }

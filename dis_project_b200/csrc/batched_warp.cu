@@ -1273,7 +1273,10 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     if (tid == 0) {
       const double v = bad ? nan("") : nlml;
       if (eval_only) a.eval_val[bidx] = v;
-      else if (a.hist) a.hist[bidx * a.ld_hist + step] = v;
+      else {
+        if (a.hist) a.hist[bidx * a.ld_hist + step] = v;
+        if (a.step_keys && v == v) atomicMin(a.step_keys + step, lfm_loss_key(v));   // best objective of EVERY step
+      }
     }
     tsync<NW>();
   }

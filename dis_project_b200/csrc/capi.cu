@@ -20,6 +20,7 @@ extern "C" const char* lfm_status_string(int status) {
     case LFM_ERR_UNSUPPORTED: return "unsupported size";
     case LFM_ERR_WORKSPACE: return "workspace too small";
     case LFM_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    case LFM_ERR_COMM: return "NCCL is not loadable or an NCCL call failed";
     default: return "unknown status";
   }
 }

@@ -461,9 +461,12 @@ def loss_key_to_float(keys):
 
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
                       b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
-                      steps_per_epoch: int = 1000, best_key: Optional[torch.Tensor] = None) -> None:
+                      steps_per_epoch: int = 1000, best_key: Optional[torch.Tensor] = None,
+                      step_keys: Optional[torch.Tensor] = None) -> None:
     """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216).
-    y is (N,) (multi-start: one data set, B start points) or (B, N) (one row of observations per LFM)."""
+    y is (N,) (multi-start: one data set, B start points) or (B, N) (one row of observations per LFM).
+    `best_key`: one int64 device word, atomicMin of the loss keys after the last step of this call; `step_keys`:
+    total_steps int64 device words, word s = atomicMin of the loss keys at step s (include/lfm_b200.h)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
         _check_training_flags(X)
@@ -477,15 +480,18 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     if state.struct_cache is None:
         nb = int(_lib.lib().lfm_batched_structure_bytes(X.shape[0], state.G, state.unique_hint, int(state.time_grid)))
         state.struct_cache = torch.zeros(max(nb, 16), dtype=torch.uint8, device=X.device)
-    _lib.check(_lib.lib().lfm_batched_fit_multi(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
+    if step_keys is not None and step_keys.numel() < state.total_steps:
+        raise ValueError("step_keys must hold one int64 word per step of the fit")
+    _lib.check(_lib.lib().lfm_batched_fit_trace(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
                                                 y_stride, state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr,
                                                 b1, b2, eps, state.step, steps, state.total_steps,
                                                 int(bool(fix_params)), int(steps_per_epoch), state.unique_hint,
                                                 int(state.time_grid), state.hist.data_ptr(), state.hist.shape[1],
                                                 state.theta.data_ptr(), state.info.data_ptr(),
                                                 best_key.data_ptr() if best_key is not None else None,
+                                                step_keys.data_ptr() if step_keys is not None else None,
                                                 state.struct_cache.data_ptr()),
-               "lfm_batched_fit_multi")
+               "lfm_batched_fit_trace")
     state.step += steps
 
 

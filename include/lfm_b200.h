@@ -38,7 +38,8 @@ typedef enum lfm_status {
   LFM_ERR_CUDA = -2,        /* a CUDA runtime call failed; cudaGetLastError has the detail      */
   LFM_ERR_UNSUPPORTED = -3, /* size outside what the kernels support (e.g. batched N > 128)     */
   LFM_ERR_WORKSPACE = -4,   /* workspace too small                                             */
-  LFM_ERR_NO_DEVICE = -5    /* no sm_100 device: there is NO CPU fallback                       */
+  LFM_ERR_NO_DEVICE = -5,   /* no sm_100 device: there is NO CPU fallback                       */
+  LFM_ERR_COMM = -6         /* NCCL is not loadable on this host, or an NCCL call failed          */
 } lfm_status;
 
 #define LFM_ABI_VERSION 2
@@ -216,6 +217,17 @@ int lfm_batched_nlml_grad_unc_multi(lfm_stream_t stream, int64_t B, int64_t N, i
                                     const double* y, int64_t y_stride, const double* theta_unc, double jitter,
                                     int unique_rows_hint, int time_grid_hint, double* out_val, double* out_grad,
                                     int* info);
+/* lfm_batched_fit_multi plus `step_keys` (may be NULL): total_steps device words, initialised to INT64_MAX by the caller;
+ * word s receives atomicMin over the batch of the order-preserving image of every LFM's loss at optimiser step s (see
+ * best_key below).  The best objective of EVERY step of a sharded fit is then ONE integer MIN all-reduce of that vector
+ * after the launch, however many steps the launch ran -- the per-step reduction of north_star without a launch boundary
+ * per step. */
+int lfm_batched_fit_trace(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                          int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter, double lr,
+                          double b1, double b2, double eps, int first_step, int steps, int total_steps,
+                          int fix_params, int steps_per_epoch, int unique_rows_hint, int time_grid_hint,
+                          double* out_hist, int64_t ld_hist, double* out_theta, int* info, long long* best_key,
+                          long long* step_keys, void* structure_cache);
 /* structure_cache (may be NULL): lfm_batched_structure_bytes() device bytes the caller keeps between the calls of ONE
  * chunked fit.  The call with first_step == 0 stores the structure of X (duplicate rows, distinct times and time
  * differences, pair table) there; calls with first_step > 0 load it instead of repeating the O(N^2) scans. */
@@ -237,6 +249,24 @@ int lfm_batched_team_size(int64_t B, int64_t N, int G, int unique_rows_hint, int
  * one CTA; what multi_start_fit all-gathers across ranks (P + 2 doubles per rank). */
 int lfm_batched_best(lfm_stream_t stream, int64_t B, int P, const double* hist, int64_t ld_hist, int64_t col,
                      const double* theta, double id0, double* out_packed);
+
+/* ---- collective of the sharded batched path --------------------------------------------------
+ * A holder of one ncclComm_t with the two collectives the path has: the integer MIN all-reduce of the best-objective
+ * keys (best_key / step_keys above; in place, stream-ordered, 8 bytes per chunk or per step) and the all-gather of the
+ * per-rank winners (lfm_batched_best, P + 2 doubles per rank).  NCCL is bound at run time (dlopen libnccl.so.2, or the
+ * path in LFM_NCCL_LIB): the library itself links against libcudart only; without NCCL these return LFM_ERR_COMM.
+ * Rank 0 calls lfm_comm_unique_id and ships the LFM_COMM_ID_BYTES bytes to the other ranks by any means (a file, a TCP
+ * store, torch.distributed); every rank then calls lfm_comm_create on its own device (collective call). */
+#define LFM_COMM_ID_BYTES 128
+typedef struct lfm_comm lfm_comm;
+int lfm_comm_available(void);
+int lfm_comm_unique_id(void* id_out);
+int lfm_comm_create(lfm_comm** out, int world, int rank, const void* id_bytes);
+int lfm_comm_world(const lfm_comm* c);
+int lfm_comm_rank(const lfm_comm* c);
+int lfm_comm_allreduce_min_i64(lfm_comm* c, long long* buf, size_t count, lfm_stream_t stream);
+int lfm_comm_allgather_f64(lfm_comm* c, const double* send, double* recv, size_t count, lfm_stream_t stream);
+int lfm_comm_destroy(lfm_comm* c);
 
 /* ---- host-buffer entry points (H2D / D2H inside; what a ctypes/cgo caller with numpy arrays
  * binds).  They allocate device scratch on first use per (N,G) and cache it in a handle. -------- */

@@ -1,0 +1,65 @@
+"""torchrun probe (also a 2-GPU correctness check): BASELINE config 4 through multi_start_fit in its three reduction modes
+-- chunk=10, chunk=1 (literal per-step all-reduce), trace (per-step keys in the kernel, one all-gather per fit) -- wall
+clock (barrier before, max over ranks, median of 7), phase timers, and agreement of the results across modes and ranks.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/msf_modes.py [B]
+"""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+rank, world = dist.get_rank(), dist.get_world_size()
+from dis_project_b200 import ops, batched, _lib
+from dis_project_b200.batched import make_restarts, multi_start_fit
+from dis_project_b200.dataset import JaxP53Data, dataset_3d
+x, y, _ = dataset_3d(JaxP53Data.synthetic()); y = y.reshape(-1)
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+TH = make_restarts(np.concatenate([np.full(5, 0.4), np.ones(5), np.full(5, 0.05), [2.5, 1.0]]), B)
+
+def once(timing, **kw):
+    os.environ["LFM_MSF_TIMING"] = "1" if timing else "0"
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = multi_start_fit(x, y, TH, 1e-4, num_iters=150, **kw)
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item(), r
+
+from dis_project_b200.comm import LfmComm
+lcomm = LfmComm.from_torch_distributed()    # the C-ABI's own communicator (lfm_comm_*), id broadcast over the process group
+modes = {"chunk10": dict(chunk=10), "chunk10_lfm_comm": dict(chunk=10, comm=lcomm), "trace_lfm_comm": dict(chunk=None, trace=True, comm=lcomm), "chunk1": dict(chunk=1), "trace": dict(chunk=None, trace=True), "trace_chunk10": dict(chunk=10, trace=True)}
+out, results = {}, {}
+for name, kw in modes.items():
+    for _ in range(2): once(False, **kw)
+    walls = [once(False, **kw)[0] for _ in range(7)]
+    _, r = once(True, **kw)
+    results[name] = r
+    out[name] = {"wall_ms_median": round(1e3 * float(np.median(walls)), 3), "wall_ms_min": round(1e3 * min(walls), 3),
+                 "wall_ms_max": round(1e3 * max(walls), 3), "phases_ms_setup_loop_tail(sync timers)": batched.LAST_TIMING,
+                 "best_nlml": r.best_loss, "best_id": r.best_id, "trace_len": int(r.best_trace.shape[0])}
+ref = results["chunk10"]
+rel = lambda a, b: float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+# launch boundaries change the rounding of Adam's running bias products: the modes agree to 1e-10, not bit for bit
+same = all(rel(r.history, ref.history) < 1e-10 and r.best_id == ref.best_id and abs(r.best_loss - ref.best_loss) < 1e-10 * abs(ref.best_loss)
+           for r in results.values())
+
+def global_colmin(r):   # minimum over ALL restarts of the job at every step: MIN all-reduce of the local column minima
+    c = torch.as_tensor(np.where(np.isfinite(r.history), r.history, np.inf).min(axis=0)).cuda()
+    dist.all_reduce(c, op=dist.ReduceOp.MIN)
+    return c.cpu().numpy()
+
+trace_ok = bool(np.array_equal(results["trace"].best_trace, global_colmin(results["trace"])))
+trace10_ok = bool(np.array_equal(results["trace_chunk10"].best_trace, global_colmin(results["trace_chunk10"])))
+chunk1_ok = bool(np.array_equal(results["chunk1"].best_trace, global_colmin(results["chunk1"])))
+chunk10_ok = bool(np.array_equal(results["chunk10"].best_trace, global_colmin(results["chunk10"])[9::10]))
+trace_ok = trace_ok and trace10_ok
+flag = torch.tensor([int(same and trace_ok and chunk1_ok and chunk10_ok)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+if rank == 0:
+    team = int(_lib.lib().lfm_batched_team_size(ref.hi - ref.lo, x.shape[0], 5, ops.unique_rows(x), ops.distinct_times(x)))
+    print(json.dumps({"world": world, "restarts": B, "restarts_per_gpu": ref.hi - ref.lo, "warps_per_lfm": team,
+                      "modes_agree_on_every_rank": bool(flag.item()), "modes": out}), flush=True)
+lcomm.close()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() else 1)
