@@ -82,6 +82,9 @@ SIGNATURES = {
                                      _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "lfm_batched_fit_trace": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                      _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "lfm_batched_queue_bytes": (_sz, [_i64, _int, _int]),
+    "lfm_batched_fit_queue": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
+                                     _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _sz]),
     "lfm_batched_structure_bytes": (_sz, [_i64, _int, _int, _int]),
     "lfm_batched_team_size": (_int, [_i64, _i64, _int, _int, _int]),
     "lfm_batched_best": (_int, [_ptr, _i64, _int, _ptr, _i64, _i64, _ptr, _dbl, _ptr]),

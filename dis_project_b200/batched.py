@@ -136,7 +136,7 @@ def _stage_to_device(device, arrays):
 def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr: float = 0.01,
                     fix_params: bool = True, num_steps_per_epoch: int = 1000, chunk: Optional[int] = 1,
                     b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, trace: bool = False,
-                    comm=None) -> MultiStartResult:
+                    comm=None, queue_chunk: int = 10) -> MultiStartResult:
     """Fit all restarts of this rank's shard on the current CUDA device.
 
     `theta0_all` is the (B, P) array of constrained start points of the WHOLE job (every rank passes
@@ -153,6 +153,9 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
         include/lfm_b200.h), the launches run `chunk` steps each (None: the whole fit in one launch), and the
         per-step reduction over ranks rides in the ONE all-gather that also moves the winners: ``best_trace``
         has one entry per step at the cost of a single collective per fit.
+    `queue_chunk`: when the whole fit is one launch (``trace=True, chunk=None``) the kernels may run as persistent workers
+    over a device-side queue of `queue_chunk`-step tasks (``lfm_batched_fit_queue``): used by the library where a static
+    one-CTA-per-LFM assignment would leave SMs unevenly loaded (e.g. 512 LFMs per GPU), ignored elsewhere; 0 = never.
     `comm`: a ``dis_project_b200.comm.LfmComm`` -- the collectives then run through the C-ABI's own NCCL communicator
     (``lfm_comm_*``) and rank / world come from it; default: ``torch.distributed``.
     """
@@ -227,7 +230,8 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
         if st is not None:
             ops.batched_fit_steps(st, Xd, yd, jitter, steps, lr=lr, b1=b1, b2=b2, eps=eps, fix_params=fix_params,
                                   steps_per_epoch=num_steps_per_epoch, best_key=None if trace else keys[c:c + 1],
-                                  step_keys=keys if trace else None)
+                                  step_keys=keys if trace else None,
+                                  queue_chunk=queue_chunk if trace and chunk >= num_iters else 0)
         done += steps
         if side is not None:
             ev = torch.cuda.Event()

@@ -412,6 +412,7 @@ static int batched_launch(cudaStream_t st, const BatchedArgs& a, int time_grid) 
     const int st2 = lfm_batched_warp_launch(st, b, time_grid);
     if (st2 != LFM_ERR_UNSUPPORTED) return st2;
   }
+  b.queue = nullptr;   // the CTA-per-LFM kernel has no queue mode: plain launch over all the steps it was given
   const size_t smem = batched_smem_bytes(b.N, b.G, b.max_unique);
   if (smem > 227 * 1024) return LFM_ERR_UNSUPPORTED;
   const bool small = b.max_unique <= 64 && b.N <= 128 && 3 * b.G + 2 <= 128;
@@ -476,6 +477,36 @@ extern "C" int lfm_batched_fit_multi(lfm_stream_t stream, int64_t B, int64_t N, 
   return lfm_batched_fit_trace(stream, B, N, G, X, y, y_stride, theta_unc_io, adam_state, jitter, lr, b1, b2, eps,
                                first_step, steps, total_steps, fix_params, steps_per_epoch, unique_rows_hint,
                                time_grid_hint, out_hist, ld_hist, out_theta, info, best_key, nullptr, structure_cache);
+}
+// Whole fit in ONE launch with persistent workers and a device-side task queue (batched_warp.cu): see the header.
+extern "C" size_t lfm_batched_queue_bytes(int64_t B, int total_steps, int chunk_steps) {
+  if (B <= 0 || total_steps <= 0 || chunk_steps <= 0) return 0;
+  const int64_t nchunks = (total_steps + chunk_steps - 1) / chunk_steps;
+  if (B * nchunks > 0x7fffffff) return 0;
+  return (size_t)(4 + B + B * nchunks) * sizeof(int);
+}
+extern "C" int lfm_batched_fit_queue(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                                     int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter,
+                                     double lr, double b1, double b2, double eps, int total_steps, int fix_params,
+                                     int steps_per_epoch, int unique_rows_hint, int time_grid_hint, double* out_hist,
+                                     int64_t ld_hist, double* out_theta, int* info, long long* best_key,
+                                     long long* step_keys, void* structure_cache, int chunk_steps, void* queue_ws,
+                                     size_t queue_bytes) {
+  if (total_steps < 0 || steps_per_epoch <= 0) return LFM_ERR_INVALID;
+  if (N > 128) return LFM_ERR_UNSUPPORTED;
+  if (queue_ws && (chunk_steps <= 0 || queue_bytes < lfm_batched_queue_bytes(B, total_steps, chunk_steps) ||
+                   lfm_batched_queue_bytes(B, total_steps, chunk_steps) == 0 || !adam_state))
+    return queue_bytes ? LFM_ERR_WORKSPACE : LFM_ERR_INVALID;
+  BatchedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.N = (int)N; a.G = G; a.X = X; a.y = y; a.y_stride = y_stride; a.u_io = theta_unc_io; a.adam = adam_state;
+  a.jitter = jitter; a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps;
+  a.first_step = 0; a.steps = total_steps; a.total_steps = total_steps; a.fix_params = fix_params;
+  a.steps_per_epoch = steps_per_epoch; a.hist = out_hist; a.ld_hist = ld_hist; a.theta_out = out_theta;
+  a.info = info; a.max_unique = unique_rows_hint; a.best_key = best_key; a.step_keys = step_keys;
+  a.struct_cache = structure_cache;
+  a.queue = (int*)queue_ws; a.queue_chunk = chunk_steps;
+  return batched_launch((cudaStream_t)stream, a, time_grid_hint);
 }
 extern "C" int lfm_batched_fit_trace(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
                                      int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter,

@@ -245,7 +245,9 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   (void)wid;
-  const int64_t bidx = blockIdx.x;
+  // queue mode (a.queue != NULL): the CTA is a WORKER that takes (LFM, chunk of steps) tasks from a device-side queue
+  // until the fit is done; bidx / first_step / task_steps are then per task (see the task loop below)
+  int64_t bidx = a.queue ? (int64_t)(blockIdx.x % a.B) : (int64_t)blockIdx.x;
   const int MU = a.max_unique;
   const WarpLayout L = warp_layout(N, G, MU, MT, NW > 1);
   double* base = reinterpret_cast<double*>(smem_raw);
@@ -275,12 +277,6 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   unsigned* itab = reinterpret_cast<unsigned*>(smem_raw + L.itab);
   (void)itab;
 
-  for (int p = tid; p < P; p += NT) {
-    u[p] = a.u_io[bidx * P + p];
-    const bool have = a.adam != nullptr && a.first_step > 0;
-    am[p] = have ? a.adam[bidx * 2 * P + p] : 0.0;
-    av[p] = have ? a.adam[bidx * 2 * P + P + p] : 0.0;
-  }
   int fail = 0;
   const int blk = N / G;  // rows per positional mean block (model.py:145)
   // ---- structure of X (duplicate rows, distinct times, distinct time differences, pair table): identical for every
@@ -475,7 +471,44 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   }
   }
   const bool eval_only = a.eval_val != nullptr;
-  const int nsteps = eval_only ? 1 : a.steps;
+  // ---- task loop.  Without a queue: one pass, this CTA's LFM, the launch's steps.  With a queue: pop tasks until the
+  // ticket counter passes the number of tasks of the fit.  The structure above is the same for every LFM and stays in
+  // shared memory; only the iterate, the Adam moments and (with per-LFM observations) y are per task.
+  const int fail_struct = fail;
+  int first_step = a.first_step, task_steps = a.steps;
+  __shared__ int task_sh[2];
+  for (;;) {
+  if (a.queue) {
+    LfmQueue Q = lfm_queue_view(a.queue, a.B);
+    if (tid == 0) {
+      const int t = atomicAdd(Q.head, 1);
+      int b = -1;
+      if (t < Q.total(a.total_steps, a.queue_chunk)) {
+        volatile int* slot = Q.ring + t;
+        while ((b = *slot) < 0) __nanosleep(200);   // published by the worker that ran this LFM's previous chunk
+        __threadfence();
+      }
+      task_sh[0] = b;
+      task_sh[1] = b >= 0 ? *(volatile int*)(Q.done + b) : 0;
+    }
+    __syncthreads();
+    if (task_sh[0] < 0) break;
+    bidx = task_sh[0];
+    first_step = task_sh[1] * a.queue_chunk;
+    task_steps = min(a.queue_chunk, a.total_steps - first_step);
+    if (a.y_stride != 0)
+      for (int i = tid; i < N; i += NT) ys[i] = __ldcg(a.y + bidx * a.y_stride + i);
+    fail = fail_struct;
+  }
+  for (int p = tid; p < P; p += NT) {
+    // (__ldcg: in queue mode the previous chunk of this LFM may have run on another SM; L1 is not coherent)
+    u[p] = __ldcg(a.u_io + bidx * P + p);
+    const bool have = a.adam != nullptr && first_step > 0;
+    am[p] = have ? __ldcg(a.adam + bidx * 2 * P + p) : 0.0;
+    av[p] = have ? __ldcg(a.adam + bidx * 2 * P + P + p) : 0.0;
+  }
+  tsync<NW>();
+  const int nsteps = eval_only ? 1 : task_steps;
   const double dR = (double)R;
   const int ex = U > 32 ? U - 32 : 0;  // rows [0, ex) are the "extra" rows: lane -> rows {lane < ex, ex + lane}
   const int TT = Tu * Tu;
@@ -486,7 +519,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   if constexpr (NW > 1) wpair_decode(tid < (GJN / 3) * (GJN / 3 + 1) / 2 ? tid : 0, sweep_ti, sweep_tj);
   (void)flip;
   // Adam bias corrections b^(step+1), carried multiplicatively (pow once per launch, not twice per step per leaf)
-  double b1t = pow(a.b1, (double)a.first_step), b2t = pow(a.b2, (double)a.first_step);
+  double b1t = pow(a.b1, (double)first_step), b2t = pow(a.b2, (double)first_step);
 #define WSTAMP() do { if (a.stamps && bidx == 0 && sidx == 1 && tid == 0) a.stamps[nstamp++] = clock64(); } while (0)
   // finer stamps inside a phase (slots 16..31 of the same buffer; tools/team_quick.py prints them)
 #define WSTAMPX(i) do { if (a.stamps && bidx == 0 && sidx == 1 && tid == 0) a.stamps[16 + (i)] = clock64(); } while (0)
@@ -494,7 +527,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
   // different threads, so that a team spreads the transcendentals of a stage over all of its lanes
 #define TEAM_ITEMS(e, n, base) for (int e = (tid + NT - ((base) % NT)) % NT; e < (n); e += NT)
   for (int sidx = 0; sidx < nsteps; ++sidx) {
-    const int step = a.first_step + sidx;
+    const int step = first_step + sidx;
     WSTAMP();
     // ---- A. constrain -----------------------------------------------------------------------
     for (int p = tid; p < P; p += NT) th[p] = (p == 3 * G) ? lfm_l_forward(u[p]) : lfm_softplus(u[p]);
@@ -1285,7 +1318,7 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     for (int p = tid; p < P; p += NT) {
       a.u_io[bidx * P + p] = u[p];
       if (a.adam) { a.adam[bidx * 2 * P + p] = am[p]; a.adam[bidx * 2 * P + P + p] = av[p]; }
-      if (a.theta_out && a.first_step + a.steps >= a.total_steps) {
+      if (a.theta_out && first_step + task_steps >= a.total_steps) {
         double t = (p == 3 * G) ? lfm_l_forward(u[p]) : lfm_softplus(u[p]);  // trainer.py:218
         if (a.fix_params && G > 3) {                                         // trainer.py:219-220
           if (p == G + 3) t = 1.0;
@@ -1296,13 +1329,29 @@ __global__ void __launch_bounds__(32 * NW, NW == 1 ? 1 : (NW <= 4 ? 4 : 2)) lfm_
     }
   }
   if (tid == 0 && a.info) {
-    if (a.first_step == 0 || eval_only) a.info[bidx] = fail;
+    if (first_step == 0 || eval_only) a.info[bidx] = fail;
     else if (fail) a.info[bidx] = fail;
   }
-  if (tid == 0 && a.best_key && !eval_only && a.hist && a.steps > 0) {
-    const double v = a.hist[bidx * a.ld_hist + a.first_step + a.steps - 1];
+  // (queue mode: the launch covers the whole fit, so "after the launch's last step" is the task that reaches total_steps)
+  if (tid == 0 && a.best_key && !eval_only && a.hist && task_steps > 0 && (!a.queue || first_step + task_steps >= a.total_steps)) {
+    const double v = a.hist[bidx * a.ld_hist + first_step + task_steps - 1];
     if (v == v) atomicMin(a.best_key, lfm_loss_key(v));
   }
+  if (!a.queue) break;
+  // publish the LFM's next chunk: every thread's stores of the iterate / moments precede the barrier, thread 0's fence
+  // makes them visible device-wide before the ring slot is
+  __syncthreads();
+  if (tid == 0) {
+    LfmQueue Q = lfm_queue_view(a.queue, a.B);
+    const int c = task_sh[1] + 1;
+    Q.done[bidx] = c;
+    if (c * a.queue_chunk < a.total_steps) {
+      const int slot = atomicAdd(Q.tail, 1);
+      __threadfence();
+      atomicExch(Q.ring + slot, (int)bidx);
+    }
+  }
+  }   // task loop
 }
 
 size_t lfm_batched_warp_structure_bytes(int N, int G, int MU, int MT) {
@@ -1318,10 +1367,45 @@ static cudaError_t team_smem(size_t bytes) {
   static LfmSmemConfig conf;
   return lfm_ensure_smem(lfm_batched_warp_kernel<NW>, conf, bytes);
 }
+template <int NW> static int team_slots(size_t bytes);
+__global__ void lfm_queue_init_kernel(int* base, int64_t B, int total) {
+  const LfmQueue q = lfm_queue_view(base, B);
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i == 0) { *q.head = 0; *q.tail = (int)B; base[2] = 0; base[3] = 0; }
+  if (i < B) q.done[i] = 0;
+  if (i < total) q.ring[i] = i < B ? (int)i : -1;
+}
 template <int NW>
 static int team_launch(cudaStream_t st, const BatchedArgs& a, int time_grid, size_t bytes) {
   LFM_CUDA_OK(team_smem<NW>(bytes));
-  lfm_batched_warp_kernel<NW><<<(unsigned)a.B, 32 * NW, bytes, st>>>(a, time_grid);
+  BatchedArgs b = a;
+  unsigned grid = (unsigned)a.B;
+  if (a.queue) {
+    // Persistent workers + task queue: worth it only when a static assignment is UNBALANCED -- more LFMs than SMs, fewer
+    // than resident CTA slots, and not a whole number per SM (512 LFMs on 148 SMs: 68 SMs would carry 4 teams for the
+    // whole fit and 80 SMs 3; with the queue an LFM moves to a free slot after every chunk and the loads average out).
+    int dev = 0, sms = 0;
+    const int slots = team_slots<NW>(bytes);
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    const char* env = getenv("LFM_BATCHED_QUEUE");   // 0: never, 1: whenever a workspace is given (measurements)
+    const int forced = env ? atoi(env) : -1;
+    // Measured on B200 (profiles/batched_queue_r2.md): at 512 LFMs the loads a random hop produces are no better than the
+    // static 4 / 3 split (4.11 vs 4.14 ms) and below one LFM per slot the hops cost (3.25 vs 2.74 ms at 148); the queue
+    // pays when there are MORE LFMs than resident team slots (1024 LFMs, four warps each: 7.07 vs 8.03 ms), which is
+    // the only case it is used in unless LFM_BATCHED_QUEUE=1 forces it.
+    (void)sms;
+    const bool use = forced == 1 || (forced != 0 && NW > 1 && slots > 0 && a.B > slots);
+    if (use && slots > 0 && a.first_step == 0 && a.steps == a.total_steps && a.queue_chunk > 0) {
+      const LfmQueue q = lfm_queue_view(a.queue, a.B);
+      const int total = q.total(a.total_steps, a.queue_chunk);
+      lfm_queue_init_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a.queue, a.B, total);
+      LFM_LAUNCHED(1);
+      grid = (unsigned)(slots < total ? slots : total);
+    } else {
+      b.queue = nullptr;
+    }
+  }
+  lfm_batched_warp_kernel<NW><<<grid, 32 * NW, bytes, st>>>(b, time_grid);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;

@@ -411,6 +411,7 @@ class BatchedFitState:
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
         self.struct_cache = None  # device bytes that carry the structure of X from the first launch to the later ones
+        self.queue_ws = None      # task queue of the persistent mode (batched_fit_steps(queue_chunk=...))
 
 
 _PINNED: Dict[int, torch.Tensor] = {}
@@ -462,11 +463,13 @@ def loss_key_to_float(keys):
 def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *, lr: float = 0.01,
                       b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, fix_params: bool = True,
                       steps_per_epoch: int = 1000, best_key: Optional[torch.Tensor] = None,
-                      step_keys: Optional[torch.Tensor] = None) -> None:
+                      step_keys: Optional[torch.Tensor] = None, queue_chunk: int = 0) -> None:
     """Advance every fit in `state` by `steps` optimiser steps (reference src/trainer.py:201-216).
     y is (N,) (multi-start: one data set, B start points) or (B, N) (one row of observations per LFM).
     `best_key`: one int64 device word, atomicMin of the loss keys after the last step of this call; `step_keys`:
-    total_steps int64 device words, word s = atomicMin of the loss keys at step s (include/lfm_b200.h)."""
+    total_steps int64 device words, word s = atomicMin of the loss keys at step s (include/lfm_b200.h).
+    `queue_chunk` > 0 with the whole fit in this one call: lfm_batched_fit_queue (persistent workers, tasks of
+    `queue_chunk` steps)."""
     if state.unique_hint == 0:
         state.unique_hint = unique_rows(X)
         _check_training_flags(X)
@@ -482,6 +485,25 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
         state.struct_cache = torch.zeros(max(nb, 16), dtype=torch.uint8, device=X.device)
     if step_keys is not None and step_keys.numel() < state.total_steps:
         raise ValueError("step_keys must hold one int64 word per step of the fit")
+    if queue_chunk > 0 and state.step == 0 and steps == state.total_steps:
+        # the whole fit in one launch: persistent workers + task queue where a static assignment would be unbalanced
+        # (lfm_batched_fit_queue, include/lfm_b200.h); the library ignores the queue where it does not pay
+        l = _lib.lib()
+        qb = int(l.lfm_batched_queue_bytes(state.B, state.total_steps, int(queue_chunk)))
+        if qb > 0:
+            if state.queue_ws is None or state.queue_ws.numel() < qb:
+                state.queue_ws = torch.empty(qb, dtype=torch.uint8, device=X.device)
+            _lib.check(l.lfm_batched_fit_queue(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(), y_stride,
+                                               state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr, b1, b2, eps,
+                                               state.total_steps, int(bool(fix_params)), int(steps_per_epoch),
+                                               state.unique_hint, int(state.time_grid), state.hist.data_ptr(),
+                                               state.hist.shape[1], state.theta.data_ptr(), state.info.data_ptr(),
+                                               best_key.data_ptr() if best_key is not None else None,
+                                               step_keys.data_ptr() if step_keys is not None else None,
+                                               state.struct_cache.data_ptr(), int(queue_chunk), state.queue_ws.data_ptr(), qb),
+                       "lfm_batched_fit_queue")
+            state.step += steps
+            return
     _lib.check(_lib.lib().lfm_batched_fit_trace(_stream(), state.B, X.shape[0], state.G, X.data_ptr(), y.data_ptr(),
                                                 y_stride, state.u.data_ptr(), state.adam.data_ptr(), float(jitter), lr,
                                                 b1, b2, eps, state.step, steps, state.total_steps,

@@ -228,6 +228,21 @@ int lfm_batched_fit_trace(lfm_stream_t stream, int64_t B, int64_t N, int G, cons
                           int fix_params, int steps_per_epoch, int unique_rows_hint, int time_grid_hint,
                           double* out_hist, int64_t ld_hist, double* out_theta, int* info, long long* best_key,
                           long long* step_keys, void* structure_cache);
+/* The WHOLE fit (steps 0 .. total_steps) in one launch, with `queue_ws` (lfm_batched_queue_bytes() device bytes, may be
+ * NULL = plain launch): the CTAs become persistent workers that take "the next chunk_steps steps of LFM b" tasks from a
+ * device-side queue, so an LFM moves to whichever resident slot is free after every chunk.  The library uses the queue
+ * when a static one-CTA-per-LFM assignment would be unbalanced (more LFMs than SMs, fewer than resident team slots, not
+ * a whole number per SM -- e.g. the 512-LFM shard of 4096 restarts over 8 GPUs: 4 teams on 68 SMs and 3 on 80 for the
+ * whole fit otherwise) and ignores it elsewhere; results do not depend on it beyond the rounding of Adam's running bias
+ * products at chunk boundaries.  adam_state is required with a queue (the moments travel between workers through it);
+ * the CTA-per-LFM fallback kernel ignores the queue.  LFM_BATCHED_QUEUE = 0 | 1 in the environment forces it off / on. */
+size_t lfm_batched_queue_bytes(int64_t B, int total_steps, int chunk_steps);
+int lfm_batched_fit_queue(lfm_stream_t stream, int64_t B, int64_t N, int G, const double* X, const double* y,
+                          int64_t y_stride, double* theta_unc_io, double* adam_state, double jitter, double lr,
+                          double b1, double b2, double eps, int total_steps, int fix_params, int steps_per_epoch,
+                          int unique_rows_hint, int time_grid_hint, double* out_hist, int64_t ld_hist,
+                          double* out_theta, int* info, long long* best_key, long long* step_keys,
+                          void* structure_cache, int chunk_steps, void* queue_ws, size_t queue_bytes);
 /* structure_cache (may be NULL): lfm_batched_structure_bytes() device bytes the caller keeps between the calls of ONE
  * chunked fit.  The call with first_step == 0 stores the structure of X (duplicate rows, distinct times and time
  * differences, pair table) there; calls with first_step > 0 load it instead of repeating the O(N^2) scans. */

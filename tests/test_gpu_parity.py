@@ -424,3 +424,35 @@ def test_bijector_kernels(cuda):
     back = ops.unconstrain(ref[3:], G).cpu().numpy()
     assert relerr(back, np.stack([o.unconstrain(t) for t in ref[3:]])) < 1e-13
     assert relerr(back, U[3:]) < 1e-9
+
+
+@pytest.mark.parametrize("team,B", [(4, 20), (1, 9), (4, 333)])
+def test_batched_queue_mode_matches_chunked_launches(cuda, team, B, monkeypatch):
+    """lfm_batched_fit_queue: persistent workers + device-side task queue (an LFM changes SM after every chunk).  Forced
+    on here (LFM_BATCHED_QUEUE=1; the library otherwise only uses it where the static assignment is unbalanced): the fit
+    must equal the same fit run as separate launches of the same chunk length, bit for bit -- same arithmetic, only the
+    placement differs -- including per-LFM observations and the per-step best-objective keys."""
+    from dis_project_b200 import ops
+    monkeypatch.setenv("LFM_BATCHED_TEAM", str(team))
+    G, T, R = 5, 7, 3
+    x, y, var, _ = o.synthetic_problem(G, T, R, seed=61)
+    rng = np.random.default_rng(62)
+    th0 = o.Params.reference_init(G).pack()
+    TH = o.constrain(o.unconstrain(th0)[None, :] + 0.3 * rng.standard_normal((B, th0.shape[0])))
+    Y = y[None, :] + 0.05 * rng.standard_normal((B, y.shape[0]))
+    steps, chunk = 23, 5
+    for yy in (y, Y):
+        ref = ops.BatchedFitState(TH, G, steps)
+        kref = torch.full((steps,), torch.iinfo(torch.int64).max, dtype=torch.int64, device="cuda")
+        for c0 in range(0, steps, chunk):
+            ops.batched_fit_steps(ref, x, yy, 1e-4, min(chunk, steps - c0), step_keys=kref)
+        monkeypatch.setenv("LFM_BATCHED_QUEUE", "1")
+        st = ops.BatchedFitState(TH, G, steps)
+        keys = torch.full((steps,), torch.iinfo(torch.int64).max, dtype=torch.int64, device="cuda")
+        ops.batched_fit_steps(st, x, yy, 1e-4, steps, step_keys=keys, queue_chunk=chunk)
+        monkeypatch.delenv("LFM_BATCHED_QUEUE")
+        assert st.queue_ws is not None and st.step == steps
+        assert torch.equal(st.hist, ref.hist) and torch.equal(st.theta, ref.theta) and torch.equal(st.u, ref.u)
+        assert torch.equal(st.adam, ref.adam) and torch.equal(st.info, ref.info) and torch.equal(keys, kref)
+    th_ref, h_ref = o.fit(TH[1], x, Y[1], 1e-4, num_iters=steps)
+    assert relerr(st.hist[1].cpu().numpy(), h_ref) < 1e-9
