@@ -82,6 +82,7 @@ SIGNATURES = {
                                      _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
     "lfm_batched_fit_trace": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                      _int, _int, _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "lfm_batched_fit_init": (_int, [_ptr, _i64, _int, _ptr, _ptr, _ptr, _ptr, _i64, _ptr, _ptr, _i64]),
     "lfm_batched_queue_bytes": (_sz, [_i64, _int, _int]),
     "lfm_batched_fit_queue": (_int, [_ptr, _i64, _i64, _int, _ptr, _ptr, _i64, _ptr, _ptr, _dbl, _dbl, _dbl, _dbl, _dbl,
                                      _int, _int, _int, _int, _int, _ptr, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _sz]),

@@ -211,14 +211,16 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     # per-chunk best-objective words (without trace) and the gathered rows of every rank: read back in ONE copy
     row = P + 2 + (nkeys if trace else 0)
     n_extra = row + (0 if trace else nkeys) + world * row
-    st = ops.BatchedFitState(th0, G, num_iters, extra_doubles=n_extra) if hi > lo else None
+    key_off = (P + 2) if trace else row
+    st = ops.BatchedFitState(th0, G, num_iters, extra_doubles=n_extra, n_keys=nkeys, keys_offset=key_off) if hi > lo else None
     if st is not None and hint is not None:
         st.unique_hint, st.time_grid = hint, tg
     extra = st.extra if st is not None else torch.empty(n_extra, dtype=torch.float64, device=device)
     mine = extra[:row]
     packed = mine[:P + 2]
     keys = (mine[P + 2:] if trace else extra[row:row + nkeys]).view(torch.int64)
-    keys.fill_(torch.iinfo(torch.int64).max)
+    if st is None:
+        keys.fill_(torch.iinfo(torch.int64).max)   # (with a shard the state's initialisation launch has done it)
     allp = extra[n_extra - world * row:].view(world, row)
     main = torch.cuda.current_stream()
     multi = distributed and world > 1

@@ -177,6 +177,40 @@ __global__ void lfm_unconstrain_kernel(int64_t B, int G, const double* __restric
   const int p = (int)(idx % P);
   u[idx] = (p == 3 * G) ? lfm_l_inverse(th[idx]) : lfm_softplus_inv(th[idx]);
 }
+// One launch that prepares the device state of B fits (lfm_batched_fit_init): u = unconstrain(theta0), zero Adam moments,
+// NaN loss history, zero info words, INT64_MAX best-objective keys.
+__global__ void lfm_fit_init_kernel(int64_t B, int G, const double* __restrict__ th0, double* __restrict__ u,
+                                    double* __restrict__ adam, double* __restrict__ hist, int64_t n_hist,
+                                    int* __restrict__ info, long long* __restrict__ keys, int64_t n_keys) {
+  const int P = 3 * G + 2;
+  const int64_t n_u = B * P;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_u + 2 * n_u + n_hist + B + n_keys; i += stride) {
+    int64_t j = i;
+    if (j < n_u) { const int p = (int)(j % P); u[j] = (p == 3 * G) ? lfm_l_inverse(th0[j]) : lfm_softplus_inv(th0[j]); continue; }
+    j -= n_u;
+    if (j < 2 * n_u) { if (adam) adam[j] = 0.0; continue; }
+    j -= 2 * n_u;
+    if (j < n_hist) { if (hist) hist[j] = nan(""); continue; }
+    j -= n_hist;
+    if (j < B) { if (info) info[j] = 0; continue; }
+    j -= B;
+    if (keys) keys[j] = 0x7fffffffffffffffLL;
+  }
+}
+extern "C" int lfm_batched_fit_init(lfm_stream_t stream, int64_t B, int G, const double* theta0, double* theta_unc,
+                                    double* adam_state, double* hist, int64_t n_hist, int* info, long long* keys,
+                                    int64_t n_keys) {
+  if (B <= 0 || G <= 0 || !theta0 || !theta_unc || n_hist < 0 || n_keys < 0) return LFM_ERR_INVALID;
+  const int64_t total = 3 * B * (3 * (int64_t)G + 2) + n_hist + B + n_keys;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  lfm_fit_init_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, G, theta0, theta_unc, adam_state, hist, n_hist,
+                                                                         info, keys, n_keys);
+  LFM_LAUNCHED(1);
+  LFM_CUDA_OK(cudaGetLastError());
+  return LFM_OK;
+}
 // grad_unc = grad_con * d(constrained)/d(unconstrained)
 __global__ void lfm_chain_kernel(int G, const double* __restrict__ u, double* __restrict__ grad) {
   const int P = 3 * G + 2;

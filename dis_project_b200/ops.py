@@ -383,9 +383,12 @@ def batched_nlml_grad_unc(X, y, theta_unc, jitter: float, G: int, time_grid: Opt
 
 
 class BatchedFitState:
-    """Device-resident state of B independent fits (iterates, Adam moments, loss history)."""
+    """Device-resident state of B independent fits (iterates, Adam moments, loss history).
 
-    def __init__(self, theta0, G: int, total_steps: int, extra_doubles: int = 0):
+    ONE device allocation [u | adam | theta | hist | info | extra] and ONE initialisation launch
+    (lfm_batched_fit_init); `n_keys` int64 words at the start of `extra` are set to INT64_MAX (best-objective keys)."""
+
+    def __init__(self, theta0, G: int, total_steps: int, extra_doubles: int = 0, n_keys: int = 0, keys_offset: int = 0):
         theta0 = _dev(theta0)
         self.G, self.P = G, 3 * G + 2
         if theta0.ndim != 2 or theta0.shape[1] != self.P:
@@ -393,20 +396,28 @@ class BatchedFitState:
         self.B = theta0.shape[0]
         self.total_steps = int(total_steps)
         dev = theta0.device
-        self.u = unconstrain(theta0, G)  # trainer.py:75
-        self.adam = torch.zeros((self.B, 2 * self.P), dtype=F64, device=dev)
-        # everything a caller reads back lives in ONE device allocation (theta | hist | info | extra), so that the
-        # results of a fit cross PCIe as one copy (to_host)
+        # everything a caller reads back lives behind the iterate and the moments (theta | hist | info | extra), so that
+        # the results of a fit cross PCIe as one copy (batched_to_host)
         S = max(1, self.total_steps)
-        n_theta, n_hist, n_info = self.B * self.P, self.B * S, (self.B + 1) // 2
+        n_u = self.B * self.P
+        n_theta, n_hist, n_info = n_u, self.B * S, (self.B + 1) // 2
         self._cuts = (n_theta, n_theta + n_hist, n_theta + n_hist + n_info)
-        self.blob = torch.empty(self._cuts[2] + int(extra_doubles), dtype=F64, device=dev)
+        whole = torch.empty(3 * n_u + self._cuts[2] + int(extra_doubles), dtype=F64, device=dev)
+        self.u = whole[:n_u].view(self.B, self.P)
+        self.adam = whole[n_u:3 * n_u].view(self.B, 2 * self.P)
+        self.blob = whole[3 * n_u:]
         self.theta = self.blob[:n_theta].view(self.B, self.P)
         self.hist = self.blob[n_theta:self._cuts[1]].view(self.B, S)
-        self.hist.fill_(float("nan"))
         self.info = self.blob[self._cuts[1]:self._cuts[2]].view(torch.int32)[:self.B]
-        self.info.zero_()
         self.extra = self.blob[self._cuts[2]:]
+        if n_keys > int(extra_doubles) - int(keys_offset):
+            raise ValueError("the best-objective keys live inside `extra`")
+        keys = self.extra[keys_offset:keys_offset + n_keys].view(torch.int64) if n_keys else None
+        if self.B:
+            _lib.check(_lib.lib().lfm_batched_fit_init(_stream(), self.B, G, theta0.data_ptr(), self.u.data_ptr(),
+                                                       self.adam.data_ptr(), self.hist.data_ptr(), n_hist,
+                                                       self.info.data_ptr(), keys.data_ptr() if n_keys else None, n_keys),
+                       "lfm_batched_fit_init")
         self.step = 0
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
@@ -482,7 +493,7 @@ def batched_fit_steps(state: BatchedFitState, X, y, jitter: float, steps: int, *
     steps = min(steps, state.total_steps - state.step)
     if state.struct_cache is None:
         nb = int(_lib.lib().lfm_batched_structure_bytes(X.shape[0], state.G, state.unique_hint, int(state.time_grid)))
-        state.struct_cache = torch.zeros(max(nb, 16), dtype=torch.uint8, device=X.device)
+        state.struct_cache = torch.empty(max(nb, 16), dtype=torch.uint8, device=X.device)  # written by the first launch
     if step_keys is not None and step_keys.numel() < state.total_steps:
         raise ValueError("step_keys must hold one int64 word per step of the fit")
     if queue_chunk > 0 and state.step == 0 and steps == state.total_steps:

@@ -189,6 +189,12 @@ int lfm_batched_fit(lfm_stream_t stream, int64_t B, int64_t N, int G, const doub
                     int steps_per_epoch, int unique_rows_hint, double* out_hist, int64_t ld_hist,
                     double* out_theta, int* info);
 
+/* Device state of B fits in ONE launch: theta_unc = unconstrain(theta0) (src/trainer.py:75), adam_state (B x 2P, may be
+ * NULL) = 0, hist (n_hist doubles, may be NULL) = NaN, info (B ints, may be NULL) = 0, keys (n_keys int64 words for
+ * best_key / step_keys, may be NULL) = INT64_MAX. */
+int lfm_batched_fit_init(lfm_stream_t stream, int64_t B, int G, const double* theta0, double* theta_unc,
+                         double* adam_state, double* hist, int64_t n_hist, int* info, long long* keys, int64_t n_keys);
+
 /* Time-grid variants of the two batched entry points: `time_grid_hint` is an upper bound on the number of
  * DISTINCT times among the rows of X (lfm_count_distinct_times; 0 = unknown).  With both hints set and
  * the problem inside the limits of the one-warp-per-LFM kernel (unique rows <= 36, G T^2 <= 2048), every
