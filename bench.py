@@ -346,22 +346,36 @@ def main():
         xb, yb, _ = dataset_3d(data)
         TH = make_restarts(np.concatenate([np.full(5, 0.4), np.ones(5), np.full(5, 0.05), [2.5, 1.0]]), 4096)
         secondary["batched"] = {}
+        # the collectives of the sharded path run through the C-ABI's own NCCL communicator (lfm_comm_*, include/lfm_b200.h),
+        # its id broadcast over the process group; measured at 8 GPUs (tools/msf_modes.py): 4.59 ms against 4.79 ms through
+        # torch.distributed for the same fit
+        lcomm = None
+        if world > 1:
+            from dis_project_b200.comm import LfmComm
+            lcomm = LfmComm.from_torch_distributed()
         # chunk = 10: best-objective all-reduce every 10 optimiser steps; chunk = 1: every step (north_star: "one NCCL
         # allreduce of best-objective ... state per step").  Median of 7 after a full-size warm-up each.
-        for chunk in (10, 1):
-            multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, chunk=chunk)   # allocator, pinned buffers, NCCL
+        modes = (("chunk10", dict(chunk=10), "best-objective MIN all-reduce (8 bytes, side stream) every 10 optimiser steps"),
+                 ("chunk1", dict(chunk=1), "best-objective MIN all-reduce every optimiser step (north_star's literal wording): "
+                                           "one launch + one collective per step"),
+                 ("trace", dict(chunk=None, trace=True), "best objective of EVERY step recorded by the kernels (step_keys), whole "
+                                                         "fit in one launch, the per-step reduction over ranks rides in the ONE "
+                                                         "all-gather that moves the winners"))
+        for name, kw, what in modes:
+            multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, comm=lcomm, **kw)   # allocator, pinned buffers, NCCL
             times = []
             for _ in range(7):
                 barrier()
                 t0 = time.perf_counter()
-                res = multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, chunk=chunk)
+                res = multi_start_fit(xb, yb.reshape(-1), TH, JITTER, num_iters=150, comm=lcomm, **kw)
                 times.append(max_over_ranks(time.perf_counter() - t0))
             st_ = stats(times)
-            secondary["batched"][f"chunk{chunk}"] = {
+            secondary["batched"][name] = {
                 "workload": "config 4: 4096 p53-shaped restarts (N=105, G=5) x 150 Adam steps, sharded over "
-                            f"{world} GPU(s), best-objective MIN all-reduce every {chunk} optimiser step(s)",
+                            f"{world} GPU(s); {what}",
                 "seconds": st_, "restarts_per_s": 4096 / st_["median"], "evals_per_s": 4096 * 150 / st_["median"],
-                "best_nlml": res.best_loss, "restarts_per_gpu": res.hi - res.lo,
+                "best_nlml": res.best_loss, "restarts_per_gpu": res.hi - res.lo, "best_trace_entries": int(res.best_trace.shape[0]),
+                "collectives": "lfm_comm_* (C-ABI, NCCL)" if lcomm is not None else "none (one GPU)",
                 "warps_per_lfm": int(_lib.lib().lfm_batched_team_size(
                     res.hi - res.lo, xb.shape[0], 5, ops.unique_rows(xb), ops.distinct_times(xb))),
                 "timed": "host wall clock around multi_start_fit (host buffers in, numpy results out, barrier before, "
@@ -370,6 +384,8 @@ def main():
         secondary["batched"].update({k: secondary["batched"]["chunk10"][k] for k in ("restarts_per_s", "evals_per_s", "best_nlml",
                                                                                      "restarts_per_gpu", "warps_per_lfm")})
         secondary["batched"]["seconds"] = secondary["batched"]["chunk10"]["seconds"]["median"]
+        if lcomm is not None:
+            lcomm.close()
         if rank == 0:
             try:
                 X3h, y3h, th3h = _Inputs.make_problem(G_C3, T_C3)

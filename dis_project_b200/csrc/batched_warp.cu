@@ -1421,7 +1421,7 @@ static int team_slots(size_t bytes) {   // LFMs of team size NW resident on the 
 }
 
 // Team size for a batch of B LFMs.  The kernel time is the sum over waves of resident LFMs of the time of one wave;
-// measured on B200 for the p53 shape (tools/team_probe.py, gpurun_out/team5.log), in units of one warp-per-LFM fit:
+// measured on B200 for the p53 shape (round 1; tools/team_quick.py reproduces it), in units of one warp-per-LFM fit:
 //   team 1 (warp per LFM, 7 per SM):   1.00 alone, 1.11 with every slot taken -- no contention to speak of;
 //   team 4 (four warps per LFM, 4 per SM): 0.42 up to one LFM per SM, 0.71 with every slot taken (issue contention).
 // A full GPU keeps the warp-per-LFM kernel (most LFMs resident per wave); a shard that leaves lanes idle -- the

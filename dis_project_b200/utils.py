@@ -21,8 +21,8 @@ def generate_test_times_pred(t: Optional[int] = 100, num_genes: int = 5) -> np.n
 
 
 class GeneExpressionPredictor:
-    """Gene-expression predictions of a trained model (reference utils.py:40-234), without the
-    matplotlib part: `predict()` returns what `plot_predictions` would draw."""
+    """Gene-expression predictions of a trained model (reference utils.py:40-234): `predict()` returns what
+    `plot_predictions` draws; the drawing itself is `plotter.plot_gene_predictions` (SVG, no matplotlib here)."""
 
     def __init__(self, model, p53_data, t: Optional[int] = 100):
         self.model = model
@@ -49,6 +49,14 @@ class GeneExpressionPredictor:
         dist = self.model.multi_gene_predict(xpr_times, self.p53_data)
         split = self.decompose_predictions2 if self.num_genes == 5 else self.decompose_predictions
         return xpr_times, split(dist.mean()), split(dist.stddev())
+
+
+    def plot_predictions(self, p53_data, stddev: Optional[int] = 2, save: Optional[bool] = True,
+                         save_name: Optional[str] = None):
+        """Plot gene expression predictions (reference utils.py:143-234): gpjax_gxpr[_<save_name>]."""
+        from .plotter import plot_gene_predictions
+
+        return plot_gene_predictions(self, p53_data, stddev=stddev, save=save, save_name=save_name)
 
 
 def print_hyperparams(model, dataset, file: Optional[str] = None) -> list:

@@ -4,8 +4,9 @@ Same steps, same names: load p53 data -> dataset_3d -> Dataset -> ExactLFM(jitte
 -> adam(0.01) -> JaxTrainer(...).fit(num_steps_per_epoch=1000) -> print_hyperparams -> latent_predict ->
 GeneExpressionPredictor.  Two differences, both forced by this image: the Barenco CSVs are not part of the reference
 checkout, so without `--data-dir` the p53-shaped synthetic set (`JaxP53Data.synthetic`, ground-truth kinetics of
-dataset.py:201-203) is fitted; matplotlib is absent, so the three figures of main.py:67-78 are written as CSV columns
-(what `plot_lf` / `plot_predictions` / `plot_comparison_gpjax` would draw) instead of PNGs.
+dataset.py:201-203) is fitted; matplotlib is absent, so the three figures of main.py:67-78 (`plot_lf`,
+`plot_predictions`, `plot_comparison_gpjax`) are written as SVG by dis_project_b200/plotter.py, next to the same
+numbers as CSV columns.
 
   python examples/main.py [--data-dir data] [--replicate 0] [--out-dir out]
 """
@@ -26,6 +27,8 @@ from dis_project_b200.model import ExactLFM  # noqa: E402
 from dis_project_b200.objectives import CustomConjMLL  # noqa: E402
 from dis_project_b200.trainer import JaxTrainer  # noqa: E402
 from dis_project_b200.utils import GeneExpressionPredictor, generate_test_times, print_hyperparams  # noqa: E402
+from dis_project_b200 import plotter  # noqa: E402
+from dis_project_b200.plotter import plot_comparison_gpjax, plot_lf  # noqa: E402
 
 
 def main() -> None:
@@ -52,6 +55,7 @@ def main() -> None:
     print(f"NLML {training_history[0]:.6f} -> {training_history[-1]:.6f} in {len(training_history)} steps")
 
     os.makedirs(args.out_dir, exist_ok=True)
+    plotter.PLOTS_DIR = os.path.join(args.out_dir, "plots")
     print_hyperparams(trained_model, p53_data, file=os.path.join(args.out_dir, "hyperparams.csv"))
 
     print("Making predictions...")
@@ -63,7 +67,14 @@ def main() -> None:
         w.writerow(["t", "mean", "stddev", "lower_2sd", "upper_2sd"])
         for t, m, sd in zip(testing_times[:, 0], mean, std):
             w.writerow([t, m, sd, m - 2 * sd, m + 2 * sd])
+    # Plot latent force (main.py:67-69)
+    f = np.asarray(p53_data.f_observed).squeeze()
+    plot_lf(testing_times, latent_dist, y_scatter=f, stddev=2)
+    # Plot gene expression predictions (main.py:71-73)
     gene_predictor = GeneExpressionPredictor(trained_model, p53_data)
+    gene_predictor.plot_predictions(p53_data)
+    # Plot hyperparameter comparison (main.py:75-76)
+    plot_comparison_gpjax(trained_model, p53_data)
     xpr_times, means, stds = gene_predictor.predict()
     t100 = xpr_times[:gene_predictor.t, 0]
     with open(os.path.join(args.out_dir, "gene_expression.csv"), "w", newline="") as fh:   # utils.py:173-234

@@ -330,3 +330,40 @@ def test_jax_ffi_shim_refuses_cleanly_without_jax():
         pass
     with pytest.raises(ImportError, match="jax"):
         import dis_project_b200.jax_ffi  # noqa: F401
+
+
+def test_plotter_writes_the_reference_figures(tmp_path):
+    """plotter.py: the three figures of src/main.py:67-76 (plot_lf, plot_predictions, plot_comparison_gpjax) with the
+    reference's signatures and file names, drawn by the dependency-free SVG writer (host-side; fake predictive
+    distributions stand in for the CUDA results here)."""
+    from dis_project_b200 import plotter
+    from dis_project_b200.dataset import JaxP53Data
+    from dis_project_b200.gpx_compat import GaussianDistribution
+    from dis_project_b200.utils import GeneExpressionPredictor, generate_test_times
+
+    plotter.PLOTS_DIR = str(tmp_path)
+    data = JaxP53Data.synthetic(replicate=0)
+    tt = generate_test_times(50)
+    dist = GaussianDistribution(np.sin(tt[:, 0] / 2.0), 0.01 + 0.05 * np.cos(tt[:, 0] / 5.0) ** 2)
+    plotter.plot_lf(tt, dist, y_scatter=data.f_observed.squeeze(), stddev=2)
+    plotter.plot_lf(tt, dist, stddev=1, title="Replicate 3", save_name="replicate3")
+
+    class FakeModel:
+        true_b, true_s, true_d = np.full(5, 0.05), np.ones(5), np.full(5, 0.4)
+
+        def multi_gene_predict(self, x, d):
+            n = x.shape[0]
+            return GaussianDistribution(np.linspace(0, 1, n), np.full(n, 0.04))
+
+    plotter.plot_comparison_gpjax(FakeModel(), data)
+    gp = GeneExpressionPredictor(FakeModel(), data, t=20)
+    gp.plot_predictions(data)
+    files = sorted(os.listdir(tmp_path))
+    assert files == ["gpjax_comparison.svg", "gpjax_gxpr.svg", "gpjax_lf.svg", "gpjax_lf_replicate3.svg"]
+    lf = open(tmp_path / "gpjax_lf.svg").read()
+    assert lf.startswith("<svg") and "Latent Force Model (GPJax)" in lf and "Predictive mean" in lf and "True values" in lf
+    assert lf.count("<path") == 7            # Barenco's seven measured points as crosses
+    assert "Replicate 3" in open(tmp_path / "gpjax_lf_replicate3.svg").read()
+    cmp_svg = open(tmp_path / "gpjax_comparison.svg").read()
+    assert all(g in cmp_svg for g in data.gene_names) and cmp_svg.count("<rect") >= 30
+    assert open(tmp_path / "gpjax_gxpr.svg").read().count("Expression Over Time") == 5

@@ -28,7 +28,7 @@ def once(timing, **kw):
 
 from dis_project_b200.comm import LfmComm
 lcomm = LfmComm.from_torch_distributed()    # the C-ABI's own communicator (lfm_comm_*), id broadcast over the process group
-modes = {"chunk10": dict(chunk=10), "chunk10_lfm_comm": dict(chunk=10, comm=lcomm), "trace_lfm_comm": dict(chunk=None, trace=True, comm=lcomm), "chunk1": dict(chunk=1), "trace": dict(chunk=None, trace=True), "trace_chunk10": dict(chunk=10, trace=True)}
+modes = {"chunk10": dict(chunk=10), "chunk10_lfm_comm": dict(chunk=10, comm=lcomm), "trace_lfm_comm": dict(chunk=None, trace=True, comm=lcomm), "chunk1_lfm_comm": dict(chunk=1, comm=lcomm), "chunk1": dict(chunk=1), "trace": dict(chunk=None, trace=True), "trace_chunk10": dict(chunk=10, trace=True)}
 out, results = {}, {}
 for name, kw in modes.items():
     for _ in range(2): once(False, **kw)
