@@ -103,6 +103,8 @@ class MultiStartResult:
     best_id: int             # global restart id
     best_theta: Optional[np.ndarray]  # global winner, broadcast to every rank
     best_trace: np.ndarray   # global best objective after every chunk
+    device_ms: float = float("nan")   # CUDA-event time on this rank from the first enqueued operation (the input copy)
+                                      # to the last (the read-back of the results): the fit as the device saw it
 
 
 _STAGE = {}
@@ -188,6 +190,8 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
         chunk = max(num_iters, 1)
     ops._lib.require_device()
     device = X.device if isinstance(X, torch.Tensor) and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     yh = y if isinstance(y, torch.Tensor) else np.asarray(y, dtype=np.float64)
     per_lfm_y = yh.ndim == 2 and yh.shape[0] == B and yh.shape[1] == (X.shape[0]) and B != 1
     host_inputs = not isinstance(X, torch.Tensor) and not isinstance(yh, torch.Tensor)
@@ -263,7 +267,7 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     else:
         allp[0].copy_(mine)
     if st is not None:
-        theta, hist, info, ex = ops.batched_to_host(st)
+        theta, hist, info, ex = ops.batched_to_host(st, after_copy=ev1)
     else:
         theta, hist, info = np.zeros((0, P)), np.zeros((0, num_iters)), np.zeros(0, dtype=np.int32)
         ex = extra.cpu().numpy()
@@ -282,5 +286,6 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
     if timing:
         global LAST_TIMING
         LAST_TIMING = [round(1e3 * (b - a), 3) for a, b in zip(tmarks[:-1], tmarks[1:])]
+    device_ms = float(ev0.elapsed_time(ev1)) if st is not None else float("nan")
     return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
-                            ops.loss_key_to_float(keys_h))
+                            ops.loss_key_to_float(keys_h), device_ms)

@@ -436,10 +436,13 @@ def _pinned(n: int) -> torch.Tensor:
     return buf
 
 
-def batched_to_host(state: "BatchedFitState"):
-    """(theta, hist, info, extra) of a fit as numpy arrays: ONE device->host copy through a cached pinned buffer."""
+def batched_to_host(state: "BatchedFitState", after_copy=None):
+    """(theta, hist, info, extra) of a fit as numpy arrays: ONE device->host copy through a cached pinned buffer.
+    `after_copy`: a torch.cuda.Event recorded right behind the copy (device-side timing of a whole fit)."""
     host = _pinned(state.blob.numel())
     host.copy_(state.blob, non_blocking=True)
+    if after_copy is not None:
+        after_copy.record()
     torch.cuda.current_stream().synchronize()
     a = host.numpy()
     c0, c1, c2 = state._cuts
