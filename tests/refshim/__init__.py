@@ -28,6 +28,8 @@ What is real and what is a stand-in:
     optax 0.1.9         -> ``shim_misc``   adam (b1 .9, b2 .999, eps 1e-8, bias corrected), apply_updates
     tfp bijectors       -> ``shim_misc``   Softplus, Sigmoid(low, high)
     jaxtyping, matplotlib -> inert placeholders (annotations / plotting are never exercised)
+    gpytorch            -> ``shim_gpytorch`` (on real torch) for the reference's GPyTorch twin,
+                           ``src/gpytorch_alfi/{dataset_alfi,model_alfi}.py`` (tests/golden/make_ref_twin_golden.py)
 
 ``install()`` registers the stand-ins in ``sys.modules`` and puts the reference's ``src`` directory
 on ``sys.path`` (the reference modules import each other by bare name).

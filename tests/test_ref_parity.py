@@ -274,3 +274,68 @@ def test_reference_call_sequence_on_cuda_matches_reference_execution(cuda, name)
     dec = gp.decompose_predictions2(gene.mean()) if G == 5 else gp.decompose_predictions(gene.mean())
     for a, b in zip(dec, c["fit"]["gene_mean_decomposed"]):
         assert rel(a, b) < RTOL
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's GPyTorch twin (src/gpytorch_alfi), executed under tests/refshim/shim_gpytorch.py: the heteroscedastic
+# training objective K_xx + 1e-4 I + diag(variances) + noise I (model_alfi.py:294-299) and its block-structured Gram.
+# The twin keeps its kernel parameters in float32 (model_alfi.py:191), so its numbers carry ~1e-7 relative rounding:
+# tolerances here are 1e-5 (value, entries) and 1e-4 of the largest gradient component.
+# ------------------------------------------------------------------------------------------------
+TWIN_CASES = ("rep0", "rep2")
+
+
+def _twin(name):
+    with open(os.path.join(GOLD, f"ref_twin_{name}.json")) as fh:
+        c = json.load(fh)
+    G = c["G"]
+    t, y, var = np.array(c["train_t"]), np.array(c["train_y"]), np.array(c["variances"])
+    N = t.size
+    X = np.stack((t, np.repeat(np.arange(G), N // G).astype(np.float64), np.ones(N)), axis=1)   # the twin's block layout
+    return c, G, N, X, y, var
+
+
+def _twin_theta_and_grad(pt, G, N):
+    """theta = [d, s, b, l, sigma] of include/lfm_b200.h and d(NLML)/d(theta) from the twin's d(loss)/d(raw): loss =
+    NLML / N; Positive = softplus (derivative sigmoid), Interval(0.5, 3.5) = 0.5 + 3 sigmoid, noise = softplus(raw) + 1e-4
+    = sigma^2."""
+    sig = lambda r: 1.0 / (1.0 + np.exp(-np.asarray(r, dtype=np.float64)))
+    sigma = float(np.sqrt(pt["noise"]))
+    theta = np.concatenate([pt["decay"], pt["sensitivity"], pt["basal"], [pt["lengthscale"], sigma]])
+    sl = sig(pt["raw"]["lengthscale"])
+    g = np.concatenate([np.array(pt["grad_raw"]["decay"]) / sig(pt["raw"]["decay"]),
+                        np.array(pt["grad_raw"]["sensitivity"]) / sig(pt["raw"]["sensitivity"]),
+                        np.array(pt["grad_raw"]["basal"]) / sig(pt["raw"]["basal"]),
+                        np.array(pt["grad_raw"]["lengthscale"]) / (3.0 * sl * (1.0 - sl)),
+                        np.array(pt["grad_raw"]["noise"]) / sig(pt["raw"]["noise"]) * 2.0 * sigma]) * N
+    return theta, g
+
+
+@pytest.mark.parametrize("name", TWIN_CASES)
+def test_oracle_heteroscedastic_objective_matches_the_gpytorch_twin(name):
+    c, G, N, X, y, var = _twin(name)
+    assert c["provenance"].startswith("reference GPyTorch twin executed")
+    for pt in c["points"]:
+        theta, g_twin = _twin_theta_and_grad(pt, G, N)
+        p = o.Params.unpack(theta, c["kernel_jitter"])
+        val, g = o.nlml_and_grad(p, X, y, variances=var)
+        assert abs(val / N - pt["loss"]) <= 1e-5 * abs(pt["loss"])                       # trainer_alfi.py:173
+        K = o.gram(p, X) + np.diag(var) + c["kernel_jitter"] * np.eye(N)                # model_alfi.py:282-299
+        assert rel(K, pt["K_xx"]) < 1e-6
+        assert rel(o.mean_function(p, X), pt["mean"]) < 1e-7                             # model_alfi.py:540-546
+        assert np.max(np.abs(g - g_twin)) <= 1e-4 * np.max(np.abs(g_twin))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", TWIN_CASES)
+def test_cuda_heteroscedastic_objective_matches_the_gpytorch_twin(cuda, name):
+    from dis_project_b200 import ops
+    c, G, N, X, y, var = _twin(name)
+    for pt in c["points"]:
+        theta, g_twin = _twin_theta_and_grad(pt, G, N)
+        out, info = ops.nlml_grad(X, y, theta, c["kernel_jitter"], G, variances=var)
+        out = out.cpu().numpy()
+        assert int(info.item()) == 0 and abs(out[0] / N - pt["loss"]) <= 1e-5 * abs(pt["loss"])
+        assert np.max(np.abs(out[1:] - g_twin)) <= 1e-4 * np.max(np.abs(g_twin))
+        K = ops.gram(X, theta, G).cpu().numpy() + np.diag(var) + c["kernel_jitter"] * np.eye(N)
+        assert rel(K, pt["K_xx"]) < 1e-6
