@@ -13,6 +13,14 @@
 
 #define BK 16
 #define STAGES 4
+// k4-steps of a unit (of 8) over which the next unit's cp.async are issued in the SPREAD instantiations.  Spreading
+// them over all 8 steps issued the last eighth one k4-step (~300 cycles) before the barrier that needs it -- less than
+// an L2 round trip, so every unit boundary stalled on its latest loads; over the first 4 steps every load has at least
+// half a unit to land.  Measured on B200 (N = 4000 evaluation, ms per step): 8 steps 3.40, 6: 3.35, 5: 3.33, 4: 3.33,
+// 3: 3.34, 2: 3.34, one burst behind the barrier (no SPREAD) 3.50; largest rank-128 update 23.7 -> 24.6 TF/s.
+#ifndef SPREAD_STEPS
+#define SPREAD_STEPS 4
+#endif
 #define LDK (BK + 4)    // [row][k] layout: 20 doubles per row, == 4 (mod 16) -> conflict-free fragment reads
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -108,8 +116,8 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   // Two k-tiles (32 deep) per barrier: the four stages form two units; unit u is computed while unit u+1 streams
   // in, so there is one wait_group + one __syncthreads per 256 DMMAs of every warp.  The cp.async of unit u+1 are
   // issued from per-thread pointers computed once; with SPREAD (short and medium K, where unit boundaries are a
-  // visible share of a tile) not in one burst behind the barrier but in PIECES, one eighth after each k4-step of
-  // unit u (measured: +4..6 % on K <= 4096 shapes, -3 % on K >= 8192, hence the switch).
+  // visible share of a tile) not in one burst behind the barrier but in PIECES after each of the first SPREAD_STEPS
+  // k4-steps of unit u (measured: +4..6 % on K <= 4096 shapes, -3 % on K >= 8192, hence the switch).
   constexpr int PA = (BM * 8 + NT - 1) / NT;   // 16-byte chunks per thread and k-tile, operand A
   constexpr int PB = (BN * 8 + NT - 1) / NT;   //                                         operand B
   constexpr int PP = 2 * (PA + PB);            // chunks per thread and unit
@@ -209,8 +217,11 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
         if (spread) {
           // this step's share of the next unit's loads (slot (u+1)&1 was last read before this iteration's barrier)
 #pragma unroll
-          for (int q = step * PP / 8; q < (step + 1) * PP / 8; ++q) issue_piece((u + 1) & 1, 2 * (u + 1), q);
-          if (step == 7) cp_async_commit();
+          if (step < SPREAD_STEPS) {
+#pragma unroll
+            for (int q = step * PP / SPREAD_STEPS; q < (step + 1) * PP / SPREAD_STEPS; ++q) issue_piece((u + 1) & 1, 2 * (u + 1), q);
+            if (step == SPREAD_STEPS - 1) cp_async_commit();
+          }
         }
       }
     }
