@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   // in, so there is one wait_group + one __syncthreads per 256 DMMAs of every warp.  The cp.async of unit u+1 are
   // issued from per-thread pointers computed once; with SPREAD (short and medium K, where unit boundaries are a
   // visible share of a tile) not in one burst behind the barrier but in PIECES after each of the first SPREAD_STEPS
-  // k4-steps of unit u (measured: +4..6 % on K <= 4096 shapes, -3 % on K >= 8192, hence the switch).
+  // k4-steps of unit u.
   constexpr int PA = (BM * 8 + NT - 1) / NT;   // 16-byte chunks per thread and k-tile, operand A
   constexpr int PB = (BN * 8 + NT - 1) / NT;   //                                         operand B
   constexpr int PP = 2 * (PA + PB);            // chunks per thread and unit
@@ -426,7 +426,10 @@ static int dispatch2(cudaStream_t st, const LfmGemm& g) {
 }
 static int64_t spread_max_k() {
   static int64_t v = -1;
-  if (v < 0) { const char* e = getenv("LFM_GEMM_SPREAD_K"); v = e ? atoll(e) : 4096; }
+  // (with the loads of a unit spread over all 8 of its k4-steps, spreading lost to one burst for K >= 8192 and the switch
+  // sat at 4096; over the first SPREAD_STEPS = 4 steps it wins at every K: plain 8192^3 product 32.4 -> 34.8 TF/s = 0.98 of
+  // cuBLAS Dgemm, N = 32768 evaluation 1.116 -> 1.056 s.  LFM_GEMM_SPREAD_K = K above which one burst is used instead.)
+  if (v < 0) { const char* e = getenv("LFM_GEMM_SPREAD_K"); v = e ? atoll(e) : ((int64_t)1 << 62); }
   return v;
 }
 template <int WM, int WN, int GM>
