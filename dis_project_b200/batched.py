@@ -135,6 +135,209 @@ def _stage_to_device(device, arrays):
     return views
 
 
+_PLANS = {}
+
+
+class _MsfPlan:
+    """Everything of one rank's share of a multi-start fit that depends on SHAPES only, built once and reused by every
+    later fit of the same shape: the pinned staging buffer and its device twin ([X | y | start points], one copy), the
+    fit state with the result rows behind it (one allocation, one read-back), the structure cache and task queue of
+    the kernels, the events, and every pointer the C-ABI calls take.  What is left per fit on the host is three numpy
+    copies into the staging buffer and five stream-ordered calls -- the fit kernel is in flight ~30 us after
+    `multi_start_fit` is entered instead of ~200 us (`tools/msf_timeline.py`: the device used to wait for the host)."""
+
+    def __init__(self, device, N, G, Bl, per_lfm_y, num_iters, chunk, trace, world):
+        import torch
+
+        from . import ops
+
+        P = 3 * G + 2
+        ev = lambda n: (int(n) + 1) & ~1
+        ny = Bl * N if per_lfm_y else N
+        self.N, self.G, self.P, self.Bl, self.ny, self.num_iters, self.chunk, self.trace = N, G, P, Bl, ny, num_iters, chunk, trace
+        self.oy, self.oth = ev(3 * N), ev(3 * N) + ev(ny)
+        total = self.oth + ev(Bl * P)
+        self.pin_in = torch.empty(total, dtype=torch.float64, pin_memory=True)
+        self.h_in = self.pin_in.numpy()
+        self.d_in = torch.empty(total, dtype=torch.float64, device=device)
+        self.Xd = self.d_in[:3 * N].view(N, 3)
+        self.yd = self.d_in[self.oy:self.oy + ny]
+        self.th0 = self.d_in[self.oth:self.oth + Bl * P].view(Bl, P)
+        self.y_stride = N if per_lfm_y else 0
+        self.nchunks = max((num_iters + chunk - 1) // chunk, 1)
+        nkeys = max(num_iters, 1) if trace else self.nchunks
+        row = P + 2 + (nkeys if trace else 0)
+        self.row, self.nkeys = row, nkeys
+        self.n_extra = row + (0 if trace else nkeys) + world * row
+        key_off = (P + 2) if trace else row
+        self.st = st = ops.BatchedFitState(None, G, num_iters, extra_doubles=self.n_extra, n_keys=nkeys, keys_offset=key_off,
+                                           B=Bl, device=device)
+        extra = st.extra
+        self.mine = extra[:row]
+        self.packed = self.mine[:P + 2]
+        self.keys = (self.mine[P + 2:] if trace else extra[row:row + nkeys]).view(torch.int64)
+        self.key_views = None if trace else [self.keys[c:c + 1] for c in range(self.nchunks)]
+        self.allp = extra[self.n_extra - world * row:].view(world, row)
+        self.allp_flat = self.allp.view(-1)
+        self.ev0, self.ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.chunk_events = [torch.cuda.Event() for _ in range(self.nchunks)] if world > 1 and not trace else None
+        self.X_bytes = None
+        self.hint = self.tg = 0
+        self.struct = None
+        self.queue_ws, self.qb = None, 0
+
+    def stage_X(self, Xh):
+        """X into the staging buffer; the checks and counts that depend on its contents run once per distinct X."""
+        import torch
+
+        from . import ops
+
+        b = Xh.tobytes()
+        if b == self.X_bytes:
+            return
+        ops._check_training_flags(Xh)
+        self.hint, self.tg = ops.unique_rows(Xh), int(ops.distinct_times(Xh))
+        self.h_in[:3 * self.N] = Xh.reshape(-1)
+        l = ops._lib.lib()
+        nb = int(l.lfm_batched_structure_bytes(self.N, self.G, self.hint, self.tg))
+        if self.struct is None or self.struct.numel() < max(nb, 16):
+            self.struct = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.d_in.device)
+        self.X_bytes = b
+
+    def queue(self, queue_chunk):
+        import torch
+
+        from . import ops
+
+        qb = int(ops._lib.lib().lfm_batched_queue_bytes(self.Bl, self.num_iters, int(queue_chunk)))
+        if qb > 0 and (self.queue_ws is None or self.queue_ws.numel() < qb):
+            self.queue_ws = torch.empty(qb, dtype=torch.uint8, device=self.d_in.device)
+        self.qb = qb
+        return qb
+
+
+def _msf_planned(Xh, yh, theta0_all, lo, hi, per_lfm_y, jitter, num_iters, lr, fix_params, num_steps_per_epoch, chunk,
+                 b1, b2, eps, trace, comm, queue_chunk, dist, rank, world, device, timing):
+    """The host-buffer path of `multi_start_fit` over a cached `_MsfPlan` (same results, same collectives)."""
+    import time
+
+    import torch
+
+    from . import ops
+
+    B, P = theta0_all.shape
+    G = (P - 2) // 3
+    N = Xh.shape[0]
+    Bl = hi - lo
+    tmarks = [time.perf_counter()]
+
+    def mark():
+        if timing:
+            torch.cuda.synchronize()
+            tmarks.append(time.perf_counter())
+
+    key = (device.index if device.index is not None else torch.cuda.current_device(), N, G, Bl, per_lfm_y, num_iters, chunk,
+           trace, world)
+    plan = _PLANS.get(key)
+    if plan is None:
+        if len(_PLANS) > 8:
+            _PLANS.clear()
+        plan = _PLANS[key] = _MsfPlan(device, N, G, Bl, per_lfm_y, num_iters, chunk, trace, world)
+    lib = ops._lib.lib()
+    check = ops._lib.check
+    st = plan.st
+    plan.stage_X(Xh)
+    h = plan.h_in
+    h[plan.oy:plan.oy + plan.ny] = (yh[lo:hi] if per_lfm_y else yh).reshape(-1)
+    h[plan.oth:plan.oth + Bl * P] = theta0_all[lo:hi].reshape(-1)
+    main = torch.cuda.current_stream()
+    s = main.cuda_stream
+    plan.ev0.record(main)
+    plan.d_in.copy_(plan.pin_in, non_blocking=True)
+    check(lib.lfm_batched_fit_init(s, Bl, G, plan.th0.data_ptr(), *st._init_tail), "lfm_batched_fit_init")
+    mark()
+    multi = world > 1
+    side = _side_stream(device) if multi and not trace else None
+    keys_ptr = plan.keys.data_ptr()
+    common = (Bl, N, G, plan.Xd.data_ptr(), plan.yd.data_ptr(), plan.y_stride, st.u.data_ptr(), st.adam.data_ptr(),
+              float(jitter), float(lr), float(b1), float(b2), float(eps))
+    tail = (int(bool(fix_params)), int(num_steps_per_epoch), plan.hint, plan.tg, st.hist.data_ptr(), st.hist.shape[1],
+            st.theta.data_ptr(), st.info.data_ptr())
+    done = 0
+    for c in range((num_iters + chunk - 1) // chunk):
+        steps = min(chunk, num_iters - done)
+        best_key = None if trace else keys_ptr + 8 * c
+        step_keys = keys_ptr if trace else None
+        qb = plan.queue(queue_chunk) if (trace and chunk >= num_iters and queue_chunk > 0 and done == 0) else 0
+        if qb > 0:
+            check(lib.lfm_batched_fit_queue(s, *common, num_iters, *tail, best_key, step_keys, plan.struct.data_ptr(),
+                                            int(queue_chunk), plan.queue_ws.data_ptr(), qb), "lfm_batched_fit_queue")
+        else:
+            check(lib.lfm_batched_fit_trace(s, *common, done, steps, num_iters, *tail, best_key, step_keys,
+                                            plan.struct.data_ptr()), "lfm_batched_fit_trace")
+        done += steps
+        if side is not None:
+            e = plan.chunk_events[c]
+            e.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(e)
+                if comm is not None:
+                    comm.allreduce_min_i64(plan.key_views[c], stream=side)
+                else:
+                    dist.all_reduce(plan.key_views[c], op=dist.ReduceOp.MIN)
+    mark()
+    if side is not None:
+        main.wait_stream(side)
+    if num_iters > 0:
+        check(lib.lfm_batched_best(s, Bl, P, st.hist.data_ptr(), st.hist.stride(0), num_iters - 1, st.theta.data_ptr(),
+                                   float(lo), plan.packed.data_ptr()), "lfm_batched_best")
+    else:
+        check(lib.lfm_batched_best(s, 0, P, None, 1, 0, None, float(lo), plan.packed.data_ptr()), "lfm_batched_best")
+    gathered_on_host = None
+    if multi:
+        if comm is not None:
+            comm.allgather_f64(plan.mine, plan.allp_flat)
+        elif dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(plan.allp_flat, plan.mine)
+        else:  # gloo: gather on the host
+            buf = [torch.empty(plan.row, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(buf, plan.mine.cpu())
+            gathered_on_host = torch.stack(buf).numpy()
+    else:
+        plan.allp[0].copy_(plan.mine)
+    # ONE device->host copy of [theta | history | info | extra] into a pinned block of torch's caching host allocator;
+    # the arrays handed back are views of it (they keep it alive), nothing is copied again on the host
+    out = torch.empty(st.blob.numel(), dtype=torch.float64, pin_memory=True)
+    out.copy_(st.blob, non_blocking=True)
+    plan.ev1.record(main)
+    main.synchronize()
+    a = out.numpy()
+    c0, c1, c2 = st._cuts
+    theta = a[:c0].reshape(Bl, P)
+    hist = a[c0:c1].reshape(Bl, -1)
+    info = a[c1:c2].view("int32")[:Bl]
+    ex = a[c2:]
+    n_extra, row, nkeys = plan.n_extra, plan.row, plan.nkeys
+    allp_h = gathered_on_host if gathered_on_host is not None else ex[n_extra - world * row:].reshape(world, row)
+    if trace:
+        keys_h = allp_h[:, P + 2:].copy().view(np.int64).min(axis=0)[:num_iters]   # MIN over ranks, per step
+    else:
+        keys_h = ex[row:row + nkeys].view(np.int64)[:(num_iters + chunk - 1) // chunk]
+    best = reduce_best_gathered(allp_h)
+    best_id = int(best[1]) if np.isfinite(best[0]) else -1
+    best_theta = None
+    if best_id >= 0:
+        owner = int(np.flatnonzero((allp_h[:, 0] == best[0]) & (allp_h[:, 1] == best[1]))[0])
+        best_theta = allp_h[owner, 2:P + 2].copy()
+    mark()
+    if timing:
+        global LAST_TIMING
+        LAST_TIMING = [round(1e3 * (b - a_), 3) for a_, b in zip(tmarks[:-1], tmarks[1:])]
+    device_ms = float(plan.ev0.elapsed_time(plan.ev1))
+    return MultiStartResult(theta, hist, info, lo, hi, float(best[0]), best_id, best_theta,
+                            ops.loss_key_to_float(keys_h), device_ms)
+
+
 def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr: float = 0.01,
                     fix_params: bool = True, num_steps_per_epoch: int = 1000, chunk: Optional[int] = 1,
                     b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8, trace: bool = False,
@@ -190,12 +393,19 @@ def multi_start_fit(X, y, theta0_all, jitter: float, *, num_iters: int = 150, lr
         chunk = max(num_iters, 1)
     ops._lib.require_device()
     device = X.device if isinstance(X, torch.Tensor) and X.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
     yh = y if isinstance(y, torch.Tensor) else np.asarray(y, dtype=np.float64)
     per_lfm_y = yh.ndim == 2 and yh.shape[0] == B and yh.shape[1] == (X.shape[0]) and B != 1
     host_inputs = not isinstance(X, torch.Tensor) and not isinstance(yh, torch.Tensor)
     hint = tg = None
+    if host_inputs and hi > lo and os.environ.get("LFM_MSF_PLAN", "1") != "0":
+        Xh = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+        if Xh.ndim != 2 or Xh.shape[1] != 3:
+            raise ValueError(f"x must have shape (n, 3) = [time, gene_index, flag] (dataset.py:391), got {Xh.shape}")
+        return _msf_planned(Xh, yh, theta0_all, lo, hi, per_lfm_y, jitter, num_iters, lr, fix_params, num_steps_per_epoch,
+                            chunk, b1, b2, eps, trace, comm, queue_chunk, dist if distributed and comm is None else None,
+                            rank, world, device, timing)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
     if host_inputs:
         # everything this rank needs crosses PCIe in ONE copy: X, its observations, its start points
         Xh = np.ascontiguousarray(np.asarray(X, dtype=np.float64))

@@ -388,14 +388,18 @@ class BatchedFitState:
     ONE device allocation [u | adam | theta | hist | info | extra] and ONE initialisation launch
     (lfm_batched_fit_init); `n_keys` int64 words at the start of `extra` are set to INT64_MAX (best-objective keys)."""
 
-    def __init__(self, theta0, G: int, total_steps: int, extra_doubles: int = 0, n_keys: int = 0, keys_offset: int = 0):
-        theta0 = _dev(theta0)
+    def __init__(self, theta0, G: int, total_steps: int, extra_doubles: int = 0, n_keys: int = 0, keys_offset: int = 0,
+                 B: Optional[int] = None, device=None):
+        """`theta0` None with `B` and `device`: allocate only (a cached state that `reset` re-initialises per fit)."""
         self.G, self.P = G, 3 * G + 2
-        if theta0.ndim != 2 or theta0.shape[1] != self.P:
-            raise ValueError(f"theta0 must be (B, {self.P}) constrained start points")
-        self.B = theta0.shape[0]
+        if theta0 is not None:
+            theta0 = _dev(theta0)
+            if theta0.ndim != 2 or theta0.shape[1] != self.P:
+                raise ValueError(f"theta0 must be (B, {self.P}) constrained start points")
+            B, device = theta0.shape[0], theta0.device
+        self.B = int(B)
         self.total_steps = int(total_steps)
-        dev = theta0.device
+        dev = device
         # everything a caller reads back lives behind the iterate and the moments (theta | hist | info | extra), so that
         # the results of a fit cross PCIe as one copy (batched_to_host)
         S = max(1, self.total_steps)
@@ -413,16 +417,23 @@ class BatchedFitState:
         if n_keys > int(extra_doubles) - int(keys_offset):
             raise ValueError("the best-objective keys live inside `extra`")
         keys = self.extra[keys_offset:keys_offset + n_keys].view(torch.int64) if n_keys else None
-        if self.B:
-            _lib.check(_lib.lib().lfm_batched_fit_init(_stream(), self.B, G, theta0.data_ptr(), self.u.data_ptr(),
-                                                       self.adam.data_ptr(), self.hist.data_ptr(), n_hist,
-                                                       self.info.data_ptr(), keys.data_ptr() if n_keys else None, n_keys),
-                       "lfm_batched_fit_init")
-        self.step = 0
+        # arguments of lfm_batched_fit_init behind (stream, B, G, theta0)
+        self._init_tail = (self.u.data_ptr(), self.adam.data_ptr(), self.hist.data_ptr(), n_hist, self.info.data_ptr(),
+                           keys.data_ptr() if n_keys else None, n_keys)
         self.unique_hint = 0  # filled from X on the first batched_fit_steps call
         self.time_grid = None  # distinct-time bound, counted from X on the first call (0: CTA-per-LFM kernel)
         self.struct_cache = None  # device bytes that carry the structure of X from the first launch to the later ones
         self.queue_ws = None      # task queue of the persistent mode (batched_fit_steps(queue_chunk=...))
+        self.step = 0
+        if theta0 is not None:
+            self.reset(theta0)
+
+    def reset(self, theta0: torch.Tensor) -> None:
+        """(Re-)initialise the state for a fit from the constrained start points `theta0` (B x P, device): ONE launch."""
+        self.step = 0
+        if self.B:
+            _lib.check(_lib.lib().lfm_batched_fit_init(_stream(), self.B, self.G, theta0.data_ptr(), *self._init_tail),
+                       "lfm_batched_fit_init")
 
 
 _PINNED: Dict[int, torch.Tensor] = {}

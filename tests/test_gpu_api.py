@@ -180,6 +180,36 @@ def test_multi_start_per_step_trace(cuda):
     assert np.array_equal(res2.history, res.history) and np.array_equal(res2.best_trace, res.best_trace)
 
 
+def test_multi_start_cached_plan_matches_the_uncached_path(cuda, monkeypatch):
+    """Host inputs go through a cached per-shape plan (staging buffers, state, pointers built once); the results are those
+    of the uncached path bit for bit, a second fit on the same plan with another X / y / start points is not polluted by
+    the first, and the arrays handed back stay valid after later fits (they are not views of a reused buffer)."""
+    from dis_project_b200 import batched
+    from dis_project_b200.batched import make_restarts, multi_start_fit
+    TH = make_restarts(o.Params.reference_init(5).pack(), 12)
+    sets = [o.synthetic_problem(5, 7, 3, seed=s)[:2] for s in (6, 9)]
+    for kw in ({"chunk": 7}, {"chunk": None, "trace": True}, {"chunk": 10, "trace": True}):
+        monkeypatch.setenv("LFM_MSF_PLAN", "0")
+        refs = [multi_start_fit(x, y, TH, 1e-4, num_iters=30, **kw) for x, y in sets]
+        monkeypatch.setenv("LFM_MSF_PLAN", "1")
+        batched._PLANS.clear()
+        got = [multi_start_fit(x, y, TH, 1e-4, num_iters=30, **kw) for x, y in sets]
+        got.append(multi_start_fit(sets[0][0], sets[0][1], TH[::-1].copy(), 1e-4, num_iters=30, **kw))
+        assert len(batched._PLANS) == 1
+        for r, g in zip(refs, got):
+            assert np.array_equal(r.theta, g.theta) and np.array_equal(r.history, g.history) and np.array_equal(r.info, g.info)
+            assert np.array_equal(r.best_trace, g.best_trace) and r.best_id == g.best_id and r.best_loss == g.best_loss
+            assert np.array_equal(r.best_theta, g.best_theta)
+        assert np.array_equal(got[2].history[::-1], got[0].history)   # same data set, start points reversed
+    # per-LFM observations through the plan
+    Y = np.stack([sets[0][1] + 0.01 * b for b in range(12)])
+    monkeypatch.setenv("LFM_MSF_PLAN", "0")
+    r = multi_start_fit(sets[0][0], Y, TH, 1e-4, num_iters=20, chunk=None, trace=True)
+    monkeypatch.setenv("LFM_MSF_PLAN", "1")
+    g = multi_start_fit(sets[0][0], Y, TH, 1e-4, num_iters=20, chunk=None, trace=True)
+    assert np.array_equal(r.history, g.history) and np.array_equal(r.theta, g.theta)
+
+
 def test_examples_main_runs_the_reference_script(cuda, tmp_path):
     """examples/main.py = the reference's src/main.py call sequence: runs end to end on the synthetic p53 set and
     writes the tables behind the reference's three figures; p21 stays pinned (trainer.py:218-220)."""
