@@ -86,7 +86,12 @@ static int plan_capture(lfm_plan* p, int64_t N, int G, const double* X, const do
   cudaStreamDestroy(cap);
   if (st != LFM_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return st != LFM_OK ? st : LFM_ERR_CUDA; }
   p->graph = g;
-  if (cudaGraphInstantiate(&p->exec, g, 0) != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return LFM_ERR_CUDA; }
+  // per-node priorities (the GEMM launches carry their stream's priority as a launch attribute, dgemm.cu): without this
+  // flag every node of the graph runs at the priority of the stream the graph is launched into
+  if (cudaGraphInstantiate(&p->exec, g, cudaGraphInstantiateFlagUseNodePriority) != cudaSuccess) {
+    cudaGetLastError();
+    if (cudaGraphInstantiate(&p->exec, g, 0) != cudaSuccess) { cudaGraphDestroy(g); cudaGetLastError(); return LFM_ERR_CUDA; }
+  }
   return LFM_OK;
 }
 

@@ -426,6 +426,27 @@ static LfmGemm mk(int ta, int tb, int64_t M, int64_t N, int64_t K, const double*
   return g;
 }
 
+// Low-priority products of the interleaved inverse, K-CHUNKED: one launch per `chunk` of the k-range (the first with the
+// caller's beta, the rest accumulating).  A 64 x 64-tile CTA of a node product with K = 1024 lives for ~75 us; a dozen of
+// such launches had every CTA slot of the bulk partition taken just when a trailing update of the chain-bound half became
+// ready, and stream priority only acts when a slot frees (CUPTI timeline: the update waited 67 us, the chain behind it).
+// In chunks the CTAs live ~20-40 us and the high-priority stream gets the next free slot.
+static int64_t tri_kchunk() {
+  static int64_t v = -1;
+  if (v < 0) { const char* e = getenv("LFM_TRI_KCHUNK"); v = e ? atoll(e) : 512; }
+  return v;
+}
+static int gemm_kchunked(cudaStream_t st, LfmGemm g, int64_t chunk) {
+  if (chunk <= 0 || g.K <= chunk) return lfm_dgemm(st, g);
+  for (int64_t k0 = 0; k0 < g.K; k0 += chunk) {
+    g.k_lo = k0;
+    g.k_hi = k0 + chunk;
+    LFM_TRY(lfm_dgemm(st, g));
+    g.beta = 1.0;
+  }
+  return LFM_OK;
+}
+
 // X L^T = B in place; B is m x n (ldb), L n x n lower with inverted diagonal blocks in Wd.
 static int trsm_rec(cudaStream_t st, int64_t m, int64_t n, double* B, int64_t ldb, const double* L, int64_t ldl,
                     const double* Wd, int64_t ldw) {
@@ -568,10 +589,13 @@ static int chain_fused_mode() {
 // stream is a high-priority stream and the bulk stream is the caller's.
 struct LookAhead {
   cudaStream_t chain = nullptr, tri = nullptr;
+  cudaStream_t pan = nullptr;    // panel stream: rows >= k+2 of panel k, underneath the trailing update of step k-1 (highest priority)
+  cudaStream_t ua = nullptr;     // early part of a trailing update (block column k+1): beside the late part, not in front of it
   cudaStream_t bulk = nullptr;   // SM partition only: the bulk stream of the large partition (else the caller's stream)
   cudaStream_t tri2 = nullptr;   // SM partition only: a SUBSET of the large partition for the one long product of the inverse
   cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr, bulk_join = nullptr, tri_mid = nullptr, tri2_join = nullptr;
   cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
+  cudaEvent_t ua_done[2] = {nullptr, nullptr}, ud_done[2] = {nullptr, nullptr}, pan_done[2] = {nullptr, nullptr}, pan_join = nullptr, ua_join = nullptr;
   bool ok = false;
   int chain_sms = 0;             // SMs of the chain partition (0: no partition, priorities only)
   // SM partition (green contexts, driver API >= 12.4, reached through cudaGetDriverEntryPoint so that the library
@@ -593,9 +617,11 @@ struct LookAhead {
       bulk = nullptr; tri2 = nullptr; chain_sms = 0;
       if (cudaStreamCreateWithPriority(&chain, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
       if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
+      if (cudaStreamCreateWithPriority(&pan, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+      if (cudaStreamCreateWithPriority(&ua, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
     }
     cudaEvent_t* all[] = {&fork, &join, &tri_join, &bulk_join, &tri_mid, &tri2_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1],
-                          &bulk_done[0], &bulk_done[1]};
+                          &bulk_done[0], &bulk_done[1], &ua_done[0], &ua_done[1], &ud_done[0], &ud_done[1], &pan_done[0], &pan_done[1], &pan_join, &ua_join};
     for (cudaEvent_t* e : all)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
     ok = true;
@@ -673,11 +699,16 @@ bool LookAhead::init_partition(int dev, int prio_lo, int prio_hi) {
   SmPartition& P = g_sm_partition[dev];
   std::call_once(P.once, sm_partition_create, std::ref(P), dev);
   if (!P.ok) return false;
-  CUstream sc, sb, stri, st2;
+  CUstream sc, sb, stri, st2, sp;
+  // priorities inside the large partition: panel stream > trailing updates > inverse (numerically lower = higher)
+  const int prio_bulk = (prio_hi + 1 < prio_lo) ? prio_hi + 1 : prio_hi;
   if (P.stream_create(&sc, P.chain_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
-  if (P.stream_create(&sb, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+  if (P.stream_create(&sb, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_bulk) != CUDA_SUCCESS) return false;
   if (P.stream_create(&stri, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
-  chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri;
+  if (P.stream_create(&sp, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+  CUstream sua;
+  if (P.stream_create(&sua, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
+  chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri; pan = (cudaStream_t)sp; ua = (cudaStream_t)sua;
   chain_sms = P.chain_sms;
   if (P.have_sub && P.stream_create(&st2, P.sub_ctx, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS) tri2 = (cudaStream_t)st2;
   return true;
@@ -737,16 +768,20 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
       s1 = la.tri2;
       tri2_used = true;
     }
-    return lfm_dgemm(s1, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
-                            1.0, 0.0, 0, LFM_K_GE_ROW));
+    return gemm_kchunked(s1, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
+                                1.0, 0.0, 0, LFM_K_GE_ROW), tri_kchunk());
   };
   auto tri_g2 = [&](cudaStream_t s2, int64_t ob, int64_t mb) -> int {  // W21 = -W22 T
     const int64_t o = ob * NB, m = mb * NB;
-    return lfm_dgemm(s2, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
-                            W + (o + m) * ldw + o, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW));
+    // (the serial tail after the join runs on the whole device with nothing to yield to: one launch)
+    return gemm_kchunked(s2, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
+                                W + (o + m) * ldw + o, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW), s2 == st ? 0 : tri_kchunk());
   };
   int step = 0;
-  bool bulk_used = false;
+  bool ua_used = false, ub_used = false;
+  cudaStream_t pn = la.pan, ua_s = la.ua;
+  LFM_CUDA_OK(cudaStreamWaitEvent(pn, la.fork, 0));
+  LFM_CUDA_OK(cudaStreamWaitEvent(ua_s, la.fork, 0));
   for (int64_t k = 0; k < n; k += NB, ++step) {
     const int e = step & 1;
     double* Akk = A + k * lda + k;
@@ -764,8 +799,12 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     }
     if (m <= 0) break;
     double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
-    // ---- chain: first 128 rows of the panel, then the next diagonal block
-    if (bulk_used) LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.bulk_done[e ^ 1], 0));
+    // ---- chain: first 128 rows of the panel, then the next diagonal block.  Block column k below the diagonal block is
+    // final once the EARLY part U_a of the previous trailing update is (below), not the whole update.
+    if (ua_used) {
+      LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.ua_done[e ^ 1], 0));
+      LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.ud_done[e ^ 1], 0));
+    }
     if (chain_fused_mode()) {
       LFM_TRY(chain_step(ch, P, lda, Wkk, ldw, P + NB));
     } else {
@@ -778,30 +817,52 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     }
     LFM_CUDA_OK(cudaEventRecord(la.p1_done[e], ch));
     // nodes whose LEFT half ends at block `step`: W11 is complete and, once this step's panel is final, so is L21
-    auto tri_front = [&](bool wait_bulk) -> int {
+    auto tri_front = [&](bool wait_panel) -> int {
       if (!with_trtri) return LFM_OK;
       LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.p1_done[e], 0));
-      if (wait_bulk) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.bulk_done[e], 0));
+      if (wait_panel) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.pan_done[e], 0));
       for (int64_t mb = 1; 2 * mb <= nb; mb *= 2)
         if ((step + 1) % (2 * mb) == mb) LFM_TRY(tri_g1(step + 1 - mb, mb));
       return LFM_OK;
     };
     if (m <= NB) { LFM_TRY(tri_front(false)); continue; }
-    // ---- bulk (caller's stream)
+    // ---- panel stream: rows >= k+2 of the panel, concurrently with the chain step AND with the late part U_b of the
+    // previous trailing update (highest priority in the partition: its CTAs take the slots U_b's CTAs free)
     double* P2 = P + NB * lda;  // rows >= k+2 of the panel, (m - 128) x 128
     const int64_t m2 = m - NB;
-    LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.leaf_done[e], 0));
-    LFM_TRY(lfm_dgemm(bk, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
-    LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.p1_done[e], 0));
-    // trailing update A(k+1:, k+1:) -= L(k+1:, k) L(k+1:, k)^T on the lower tiles, minus the diagonal block
-    // (k+1, k+1) that the chain has already updated: one launch over a trapezoid of tiles
-    {
-      LfmGemm u = mk(0, 1, m, m, NB, P, lda, P, lda, P + NB, lda, -1.0, 1.0, 1, LFM_K_FULL);
-      u.tri_skip = NB;
+    LFM_CUDA_OK(cudaStreamWaitEvent(pn, la.leaf_done[e], 0));
+    if (ua_used) LFM_CUDA_OK(cudaStreamWaitEvent(pn, la.ua_done[e ^ 1], 0));
+    LFM_TRY(lfm_dgemm(pn, mk(0, 1, m2, NB, NB, P2, lda, Wkk, ldw, P2, lda, 1.0, 0.0, 0, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaEventRecord(la.pan_done[e], pn));
+    // ---- the trailing update A(k+1:, k+1:) -= L(k+1:, k) L(k+1:, k)^T in four parts on four streams.  The chain has
+    // done block (k+1, k+1).  The EARLY parts -- U_a: block column k+1 below it (stream ua), U_d: block (k+2, k+2)
+    // (panel stream) -- are everything step k+1 needs for its panel, its chain step and, after that, its leaf; the
+    // chain and the panel stream wait for THEM.  The LATE part U_b -- the rest, one trapezoid launch on the bulk stream
+    // -- starts at the same moment and runs underneath chain step k+1, panel k+1 and leaf(k+2); the early parts of
+    // step k+1 wait for it (they accumulate into blocks it writes).  While the updates are the longer side, the bulk
+    // stream therefore runs U_b(k-1), U_b(k), ... back to back (before: chain step + panel sat BETWEEN two updates,
+    // ~15 us of an idle partition per step for 17 steps of an N = 4096 sweep).
+    const bool have_ub = m2 > NB;
+    LFM_CUDA_OK(cudaStreamWaitEvent(ua_s, la.p1_done[e], 0));
+    LFM_CUDA_OK(cudaStreamWaitEvent(ua_s, la.pan_done[e], 0));
+    if (ub_used) LFM_CUDA_OK(cudaStreamWaitEvent(ua_s, la.bulk_done[e ^ 1], 0));
+    LFM_TRY(lfm_dgemm(ua_s, mk(0, 1, m2, NB, NB, P2, lda, P, lda, P2 + NB, lda, -1.0, 1.0, 0, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaEventRecord(la.ua_done[e], ua_s));
+    LFM_CUDA_OK(cudaStreamWaitEvent(pn, la.p1_done[e], 0));
+    if (ub_used) LFM_CUDA_OK(cudaStreamWaitEvent(pn, la.bulk_done[e ^ 1], 0));
+    LFM_TRY(lfm_dgemm(pn, mk(0, 1, NB, NB, NB, P2, lda, P2, lda, P2 + 2 * NB, lda, -1.0, 1.0, 1, LFM_K_FULL)));
+    LFM_CUDA_OK(cudaEventRecord(la.ud_done[e], pn));
+    ua_used = true;
+    if (have_ub) {
+      LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.p1_done[e], 0));
+      LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.pan_done[e], 0));
+      LfmGemm u = mk(0, 1, m2, m2, NB, P2, lda, P2, lda, P2 + 2 * NB, lda, -1.0, 1.0, 1, LFM_K_FULL);
+      u.tri_skip = NB;   // block (k+2, k+2) is U_d's
       LFM_TRY(lfm_dgemm(bk, u));
+      LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], bk));
     }
-    LFM_CUDA_OK(cudaEventRecord(la.bulk_done[e], bk));
-    bulk_used = true;
+    // (bulk_done[e] of a step without a late part is never waited for: every later step is without one too)
+    ub_used = have_ub;
     LFM_TRY(tri_front(true));
   }
   // join: everything after the factorisation is ordered behind the chain (and the inverse)
@@ -811,6 +872,10 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     LFM_CUDA_OK(cudaEventRecord(la.bulk_join, bk));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.bulk_join, 0));
   }
+  LFM_CUDA_OK(cudaEventRecord(la.pan_join, pn));
+  LFM_CUDA_OK(cudaStreamWaitEvent(st, la.pan_join, 0));
+  LFM_CUDA_OK(cudaEventRecord(la.ua_join, ua_s));
+  LFM_CUDA_OK(cudaStreamWaitEvent(st, la.ua_join, 0));
   if (with_trtri) {
     LFM_CUDA_OK(cudaEventRecord(la.tri_join, tr));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.tri_join, 0));

@@ -101,7 +101,10 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     case LFM_K_GE_ROWCOL: kb = max(row0, col0); break;
     default: break;
   }
-  const int nk = (int)((ke - kb) / BK);
+  kb = max(kb, g.k_lo);
+  ke = min(ke, g.k_hi);
+  const int nk = ke > kb ? (int)((ke - kb) / BK) : 0;
+  if (nk == 0 && g.beta == 1.0) return;   // K-chunked accumulation: nothing of this chunk falls into the tile's k-range
 
   double acc[WM][WN][2];
 #pragma unroll
@@ -291,6 +294,8 @@ static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
         case LFM_K_GE_ROWCOL: kb = row0 > col0 ? row0 : col0; break;
         default: break;
       }
+      if (kb < g.k_lo) kb = g.k_lo;
+      if (ke > g.k_hi) ke = g.k_hi;
       if (ke > kb) f += 2.0 * BM * BN * (double)(ke - kb);
     }
   }
@@ -386,6 +391,17 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   constexpr int BM = 8 * WM * GM, BN = 32 * WN;
   constexpr int SMEM = STAGES * (BM + BN) * LDK * 8;
   static LfmSmemConfig smem_cfg;
+  {
+    // Every tile variant asks for the LARGEST shared-memory carveout, whatever its own footprint: CTAs of two variants
+    // can only share an SM if the SM does not have to be re-partitioned between L1 and shared memory for the newcomer
+    // (that needs a drained SM).  With per-variant carveouts a 102 KB panel CTA of the highest-priority stream sat
+    // behind a whole 64 x 64-tile trailing update (2 x 80 KB per SM) although slots freed every ~13 us (CUPTI
+    // timeline, round 2).  The kernels read global memory through cp.async.cg / ld.cg only, so L1 size is irrelevant.
+    const int dev = lfm_current_device();
+    if (dev < 0 || smem_cfg.bytes[dev].load(std::memory_order_acquire) < (size_t)SMEM)
+      LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  }
   LFM_CUDA_OK(lfm_ensure_smem(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, smem_cfg, SMEM));
   const int64_t tm = g.M / BM, tn = g.N / BN;
   int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
@@ -410,7 +426,25 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
     else { g_prof.flops += f; g_prof.launches += 1; }
   }
   const dim3 grid((unsigned)tiles, (unsigned)(g.batch > 1 ? g.batch : 1));
-  lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD><<<grid, 128 * GM, SMEM, st>>>(g, (int)tn);
+  {
+    // The launch carries its stream's priority as a launch attribute: inside a captured graph (the evaluation plans) the
+    // kernel nodes otherwise run without one, and the panel stream's CTAs queued behind every pending CTA of a trailing
+    // update instead of taking the next free slot (CUPTI timelines, eager vs graph, round 2).
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(128 * GM); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    int prio = 0;
+    unsigned nattr = 0;
+    if (cudaStreamGetPriority(st, &prio) == cudaSuccess) {
+      attr[0].id = cudaLaunchAttributePriority;
+      attr[0].val.priority = prio;
+      nattr = 1;
+    } else {
+      cudaGetLastError();
+    }
+    cfg.attrs = attr; cfg.numAttrs = nattr;
+    LFM_CUDA_OK(cudaLaunchKernelEx(&cfg, lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, g, (int)tn));
+  }
   if (prof) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());

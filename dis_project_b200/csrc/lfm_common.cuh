@@ -93,6 +93,8 @@ struct LfmGemm {
   int64_t strideA, strideB, strideC;
   int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain)
   int tri_skip = 0;    // lower_only: skip the output tiles of the first `tri_skip` rows of C (the look-ahead chain owns them)
+  int64_t k_lo = 0, k_hi = ((int64_t)1 << 62);   // k-window: a tile's k-range (after kmode) is clipped to [k_lo, k_hi), multiples of 16;
+                       // with beta == 1 a tile whose clipped range is empty is left untouched (K-chunked accumulation)
 };
 int lfm_dgemm(cudaStream_t st, const LfmGemm& g);
 

@@ -31,7 +31,7 @@ ev.sort(key=lambda e: e["ts"])
 cut = len(ev) // 2
 ev = ev[cut:]
 t0 = ev[0]["ts"]
-rows = [[e["name"][:60], e["args"].get("stream"), round(e["ts"] - t0, 2), round(e["dur"], 2)] for e in ev]
+rows = [[e["name"][:60], e["args"].get("stream"), round(e["ts"] - t0, 2), round(e["dur"], 2), (e["args"].get("grid") or [0])[0]] for e in ev]
 json.dump(rows, open(f"gpurun_out/timeline_{tag}.json", "w"))
 os.remove(path)
 end = max(r[2] + r[3] for r in rows)
