@@ -433,7 +433,17 @@ static LfmGemm mk(int ta, int tb, int64_t M, int64_t N, int64_t K, const double*
 // In chunks the CTAs live ~20-40 us and the high-priority stream gets the next free slot.
 static int64_t tri_kchunk() {
   static int64_t v = -1;
-  if (v < 0) { const char* e = getenv("LFM_TRI_KCHUNK"); v = e ? atoll(e) : 512; }
+  if (v < 0) { const char* e = getenv("LFM_TRI_KCHUNK"); v = e ? atoll(e) : 0; }
+  return v;
+}
+// Low-priority launches of the bulk partition (inverse products, early W11^T W11) take at most ONE CTA slot per SM: a
+// 64 x 64-tile CTA (80 KB of shared memory, two per SM) is launched with 40 KB of padding, so that two of them do not fit
+// on an SM but one of them and one CTA of a trailing update / panel do.  Priority only decides who gets a slot that
+// frees; with both slots of every SM held by 40-150 us CTAs of the inverse, the short kernels of the chain-bound half
+// waited for slots (CUPTI timeline: leaf-to-leaf periods of 60-170 us instead of 42).
+static int low_pad() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LFM_LOW_PAD"); v = e ? atoi(e) : 0; }
   return v;
 }
 static int gemm_kchunked(cudaStream_t st, LfmGemm g, int64_t chunk) {
@@ -591,11 +601,12 @@ struct LookAhead {
   cudaStream_t chain = nullptr, tri = nullptr;
   cudaStream_t pan = nullptr;    // panel stream: rows >= k+2 of panel k, underneath the trailing update of step k-1 (highest priority)
   cudaStream_t ua = nullptr;     // early part of a trailing update (block column k+1): beside the late part, not in front of it
+  cudaStream_t fill = nullptr;   // lowest priority: work that only fills idle SMs of the chain-bound half (early W11^T W11)
   cudaStream_t bulk = nullptr;   // SM partition only: the bulk stream of the large partition (else the caller's stream)
   cudaStream_t tri2 = nullptr;   // SM partition only: a SUBSET of the large partition for the one long product of the inverse
   cudaEvent_t fork = nullptr, join = nullptr, tri_join = nullptr, bulk_join = nullptr, tri_mid = nullptr, tri2_join = nullptr;
   cudaEvent_t leaf_done[2] = {nullptr, nullptr}, p1_done[2] = {nullptr, nullptr}, bulk_done[2] = {nullptr, nullptr};
-  cudaEvent_t ua_done[2] = {nullptr, nullptr}, ud_done[2] = {nullptr, nullptr}, pan_done[2] = {nullptr, nullptr}, pan_join = nullptr, ua_join = nullptr;
+  cudaEvent_t ua_done[2] = {nullptr, nullptr}, ud_done[2] = {nullptr, nullptr}, pan_done[2] = {nullptr, nullptr}, pan_join = nullptr, ua_join = nullptr, w11_done = nullptr, fill_join = nullptr;
   bool ok = false;
   int chain_sms = 0;             // SMs of the chain partition (0: no partition, priorities only)
   // SM partition (green contexts, driver API >= 12.4, reached through cudaGetDriverEntryPoint so that the library
@@ -619,9 +630,10 @@ struct LookAhead {
       if (cudaStreamCreateWithPriority(&tri, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
       if (cudaStreamCreateWithPriority(&pan, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
       if (cudaStreamCreateWithPriority(&ua, cudaStreamNonBlocking, hi) != cudaSuccess) return false;
+      if (cudaStreamCreateWithPriority(&fill, cudaStreamNonBlocking, lo) != cudaSuccess) return false;
     }
     cudaEvent_t* all[] = {&fork, &join, &tri_join, &bulk_join, &tri_mid, &tri2_join, &leaf_done[0], &leaf_done[1], &p1_done[0], &p1_done[1],
-                          &bulk_done[0], &bulk_done[1], &ua_done[0], &ua_done[1], &ud_done[0], &ud_done[1], &pan_done[0], &pan_done[1], &pan_join, &ua_join};
+                          &bulk_done[0], &bulk_done[1], &ua_done[0], &ua_done[1], &ud_done[0], &ud_done[1], &pan_done[0], &pan_done[1], &pan_join, &ua_join, &w11_done, &fill_join};
     for (cudaEvent_t* e : all)
       if (cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) return false;
     ok = true;
@@ -704,13 +716,20 @@ bool LookAhead::init_partition(int dev, int prio_lo, int prio_hi) {
   const int prio_bulk = (prio_hi + 1 < prio_lo) ? prio_hi + 1 : prio_hi;
   if (P.stream_create(&sc, P.chain_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
   if (P.stream_create(&sb, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_bulk) != CUDA_SUCCESS) return false;
-  if (P.stream_create(&stri, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
+  // the inverse sits one level above the lowest priority, which belongs to the filler stream
+  const int prio_tri = (prio_lo - 1 > prio_bulk) ? prio_lo - 1 : prio_lo;
+  if (P.stream_create(&stri, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_tri) != CUDA_SUCCESS) return false;
+  CUstream sfill;
+  if (P.stream_create(&sfill, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_lo) != CUDA_SUCCESS) return false;
+  fill = (cudaStream_t)sfill;
   if (P.stream_create(&sp, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
   CUstream sua;
   if (P.stream_create(&sua, P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_hi) != CUDA_SUCCESS) return false;
   chain = (cudaStream_t)sc; bulk = (cudaStream_t)sb; tri = (cudaStream_t)stri; pan = (cudaStream_t)sp; ua = (cudaStream_t)sua;
   chain_sms = P.chain_sms;
-  if (P.have_sub && P.stream_create(&st2, P.sub_ctx, CU_STREAM_NON_BLOCKING, prio_lo) == CUDA_SUCCESS) tri2 = (cudaStream_t)st2;
+  // the one long product of the inverse: its own stream (it must not sit in front of the later node products of `tri`),
+  // inside the sub-partition if there is one, else on the whole bulk partition
+  if (P.stream_create(&st2, P.have_sub ? P.sub_ctx : P.bulk_ctx, CU_STREAM_NON_BLOCKING, prio_tri) == CUDA_SUCCESS) tri2 = (cudaStream_t)st2;
   return true;
 }
 
@@ -740,13 +759,34 @@ static int potrf_right_looking_serial(cudaStream_t st, int64_t n, double* A, int
 // [o, o + 2 m) needs  T = W11^T-product with L21  as soon as its left half is inverted and the panels of its
 // columns are final, and  W21 = -W22 T  as soon as its right half is inverted; in the second half of the
 // factorisation, where the dependent chain leaves most SMs idle, these products are free.
+__global__ void lfm_chol_diag_copy_kernel(int64_t n, const double* __restrict__ A, int64_t lda, double* __restrict__ d) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) d[i] = A[i * lda + i];
+}
+static int early_lauum_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LFM_EARLY_LAUUM"); v = e ? atoi(e) : 0; }
+  return v;
+}
+// `ldiag` (with_trtri only, may be NULL): n doubles that receive diag(L).  When it is given and the sweep has at least 16
+// blocks, the first half of Sigma^-1 = W^T W is started EARLY: as soon as W11 = L11^-1 is complete (half-way through the
+// sweep) diag(L11) is copied out and  S11' = W11^T W11  overwrites the lower triangle of the (dead) L11 block, on the
+// lowest-priority stream of the bulk partition, i.e. in the SM time the chain-bound second half leaves idle (~50 % of
+// the partition).  *early_done = 1 then, and the caller finishes with lfm_lauum_late (S11 = S11' + W21^T W21, the other
+// blocks as usual) instead of lfm_lauum.
 static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                               int64_t pivot_base, bool with_trtri = false) {
+                               int64_t pivot_base, bool with_trtri = false, double* ldiag = nullptr, int* early_done = nullptr) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
   if (!lookahead_mode() || n < 4 * NB || dev < 0 || !g_la_dev[dev].init()) {
     LFM_TRY(potrf_right_looking_serial(st, n, A, lda, W, ldw, info, pivot_base));
-    return with_trtri ? lfm_trtri(st, n, A, lda, W, ldw) : LFM_OK;
+    LFM_TRY(with_trtri ? lfm_trtri(st, n, A, lda, W, ldw) : LFM_OK);
+    if (ldiag) {
+      lfm_chol_diag_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A, lda, ldiag);
+      LFM_LAUNCHED(1);
+      LFM_CUDA_OK(cudaGetLastError());
+    }
+    return LFM_OK;
   }
   LookAhead& la = g_la_dev[dev];
   cudaStream_t ch = la.chain;
@@ -768,15 +808,22 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
       s1 = la.tri2;
       tri2_used = true;
     }
-    return gemm_kchunked(s1, mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw,
-                                1.0, 0.0, 0, LFM_K_GE_ROW), tri_kchunk());
+    LfmGemm g = mk(1, 1, m, m, m, W + o * ldw + o, ldw, A + (o + m) * lda + o, lda, W + o * ldw + o + m, ldw, 1.0, 0.0, 0,
+                   LFM_K_GE_ROW);
+    g.tile = 3; g.smem_pad = low_pad();
+    return gemm_kchunked(s1, g, tri_kchunk());
   };
   auto tri_g2 = [&](cudaStream_t s2, int64_t ob, int64_t mb) -> int {  // W21 = -W22 T
     const int64_t o = ob * NB, m = mb * NB;
     // (the serial tail after the join runs on the whole device with nothing to yield to: one launch)
-    return gemm_kchunked(s2, mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw,
-                                W + (o + m) * ldw + o, ldw, -1.0, 0.0, 0, LFM_K_LE_ROW), s2 == st ? 0 : tri_kchunk());
+    LfmGemm g = mk(0, 1, m, m, m, W + (o + m) * ldw + o + m, ldw, W + o * ldw + o + m, ldw, W + (o + m) * ldw + o, ldw, -1.0,
+                   0.0, 0, LFM_K_LE_ROW);
+    if (s2 != st) { g.tile = 3; g.smem_pad = low_pad(); }
+    return gemm_kchunked(s2, g, s2 == st ? 0 : tri_kchunk());
   };
+  const bool early = with_trtri && ldiag != nullptr && early_done != nullptr && nb >= 16 && nb % 2 == 0 && la.fill != nullptr &&
+                     early_lauum_mode() != 0;
+  if (early) LFM_CUDA_OK(cudaStreamWaitEvent(la.fill, la.fork, 0));
   int step = 0;
   bool ua_used = false, ub_used = false;
   cudaStream_t pn = la.pan, ua_s = la.ua;
@@ -796,6 +843,19 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
       LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.leaf_done[e], 0));
       for (int64_t mb = 1; 2 * mb <= nb && m > 0; mb *= 2)
         if ((step + 1) % (2 * mb) == 0) LFM_TRY(tri_g2(tr, step + 1 - 2 * mb, mb));
+      if (early && 2 * (step + 1) == nb) {
+        // W11 is complete behind everything `tr` has been given so far; every product that reads L11 precedes it there
+        const int64_t h = n / 2;
+        LFM_CUDA_OK(cudaEventRecord(la.w11_done, tr));
+        LFM_CUDA_OK(cudaStreamWaitEvent(la.fill, la.w11_done, 0));
+        lfm_chol_diag_copy_kernel<<<(unsigned)((h + 255) / 256), 256, 0, la.fill>>>(h, A, lda, ldiag);
+        LFM_LAUNCHED(1);
+        LFM_CUDA_OK(cudaGetLastError());
+        LfmGemm g = mk(1, 0, h, h, h, W, ldw, W, ldw, A, lda, 1.0, 0.0, 1, LFM_K_GE_ROWCOL);
+        g.tile = 3;   // 64 x 64 tiles: they share an SM with the trailing updates' CTAs (a 128 x 128 tile takes a whole SM)
+        g.smem_pad = low_pad();
+        LFM_TRY(gemm_kchunked(la.fill, g, 512));
+      }
     }
     if (m <= 0) break;
     double* P = Akk + NB * lda;  // panel below the diagonal block, m x 128
@@ -885,6 +945,19 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
     }
     for (int64_t mb = 1; 2 * mb <= nb; mb *= 2) LFM_TRY(tri_g2(st, nb - 2 * mb, mb));
   }
+  if (early) {
+    LFM_CUDA_OK(cudaEventRecord(la.fill_join, la.fill));
+    LFM_CUDA_OK(cudaStreamWaitEvent(st, la.fill_join, 0));
+    const int64_t h = n / 2;   // diag(L22); diag(L11) went out before S11' overwrote it
+    lfm_chol_diag_copy_kernel<<<(unsigned)((h + 255) / 256), 256, 0, st>>>(h, A + h * lda + h, lda, ldiag + h);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+    *early_done = 1;
+  } else if (ldiag) {
+    lfm_chol_diag_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A, lda, ldiag);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+  }
   return LFM_OK;
 }
 
@@ -912,17 +985,28 @@ static int potrf_rec(cudaStream_t st, int64_t n, double* A, int64_t lda, double*
 
 // Cholesky and W = L^-1 together: for a single right-looking sweep (n <= threshold, power-of-two block count)
 // the inverse is interleaved with the factorisation, otherwise the two run back to back.
-int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {
+int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
+                         double* ldiag, int* early_done) {
   if (n <= 0 || n % NB) return LFM_ERR_INVALID;
+  if (early_done) *early_done = 0;
   const int64_t nblk = n / NB;
   static int fuse = -1;
   if (fuse < 0) { const char* e = getenv("LFM_FUSE_TRTRI"); fuse = e ? atoi(e) : 1; }
   if (fuse && nblk >= 4 && (nblk & (nblk - 1)) == 0 && lda == ldw && n <= rl_threshold()) {
     LFM_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
-    return potrf_right_looking(st, n, A, lda, W, ldw, info, 0, true);
+    return potrf_right_looking(st, n, A, lda, W, ldw, info, 0, true, ldiag, early_done);
   }
   LFM_TRY(lfm_potrf(st, n, A, lda, W, ldw, info));
-  return lfm_trtri(st, n, A, lda, W, ldw);
+  LFM_TRY(lfm_trtri(st, n, A, lda, W, ldw));
+  if (ldiag) {
+    lfm_chol_diag_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, A, lda, ldiag);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+  }
+  return LFM_OK;
+}
+int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {
+  return lfm_potrf_trtri_diag(st, n, A, lda, W, ldw, info, nullptr, nullptr);
 }
 
 int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {
@@ -973,6 +1057,19 @@ static int trtri_levels(cudaStream_t st, int64_t n, const double* L, int64_t ld,
 // the diagonal, and the scratch that lfm_trtri leaves in W's strict upper blocks is never read).
 int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds) {
   return lfm_dgemm(st, mk(1, 0, n, n, n, W, ldw, W, ldw, S, lds, 1.0, 0.0, 1, LFM_K_GE_ROWCOL));
+}
+// The rest of S = W^T W when the top-left half block already holds S11' = W11^T W11 (lfm_potrf_trtri_diag, early_done):
+// S11 += W21^T W21 (full k-range over the second half's rows, beta = 1) and the tiles of the block rows >= n/2 as in
+// lfm_lauum.  Two launches of 128 x 128 tiles, the second on `side` (may equal st) so that both fill the device together.
+int lfm_lauum_late(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds) {
+  const int64_t h = n / 2;
+  LfmGemm lo = mk(1, 0, n, n, n, W, ldw, W, ldw, S, lds, 1.0, 0.0, 1, LFM_K_GE_ROWCOL);
+  lo.tri_skip = (int)h;
+  lo.tile = 2;
+  LFM_TRY(lfm_dgemm(st, lo));
+  LfmGemm tl = mk(1, 0, h, h, h, W + h * ldw, ldw, W + h * ldw, ldw, S, lds, 1.0, 1.0, 1, LFM_K_FULL);
+  tl.tile = 2;
+  return lfm_dgemm(st, tl);
 }
 
 // Debug: one leaf with clock64() stamps at its phase boundaries (16 values: start, loaded, then per

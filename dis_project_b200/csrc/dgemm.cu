@@ -402,7 +402,8 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
       LFM_CUDA_OK(cudaFuncSetAttribute(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>,
                                        cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   }
-  LFM_CUDA_OK(lfm_ensure_smem(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, smem_cfg, SMEM));
+  const size_t smem_total = (size_t)SMEM + (size_t)(g.smem_pad > 0 ? g.smem_pad : 0);
+  LFM_CUDA_OK(lfm_ensure_smem(lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, smem_cfg, smem_total));
   const int64_t tm = g.M / BM, tn = g.N / BN;
   int64_t tiles = g.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   if (g.lower_only && g.tri_skip > 0) {
@@ -431,7 +432,7 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
     // kernel nodes otherwise run without one, and the panel stream's CTAs queued behind every pending CTA of a trailing
     // update instead of taking the next free slot (CUPTI timelines, eager vs graph, round 2).
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(128 * GM); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+    cfg.gridDim = grid; cfg.blockDim = dim3(128 * GM); cfg.dynamicSmemBytes = smem_total; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     int prio = 0;
     unsigned nattr = 0;
@@ -490,6 +491,8 @@ int lfm_dgemm(cudaStream_t st, const LfmGemm& g) {
     if (g.N % 128 || g.lower_only) return LFM_ERR_INVALID;
     return dispatch<1, 4, 2>(st, g);
   }
+  if (g.tile == 2 && !inplace) return dispatch<4, 4, 4>(st, g);   // 128 x 128 tiles whatever the tile count
+  if (g.tile == 3 && !inplace) return dispatch<4, 2, 2>(st, g);   // 64 x 64 tiles (two CTAs per SM)
   if (inplace) {
     if (g.N != 128) return LFM_ERR_INVALID;
     if (t128 >= 148) return dispatch<8, 4, 2>(st, g);

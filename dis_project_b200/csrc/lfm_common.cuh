@@ -91,8 +91,10 @@ struct LfmGemm {
   int kmode;
   int batch;           // > 1: blockIdx.y-th problem uses A + y*strideA, B + y*strideB, C + y*strideC
   int64_t strideA, strideB, strideC;
-  int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain)
+  int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain);
+                       // 2: 128 x 128 tiles; 3: 64 x 64 tiles
   int tri_skip = 0;    // lower_only: skip the output tiles of the first `tri_skip` rows of C (the look-ahead chain owns them)
+  int smem_pad = 0;    // extra dynamic shared memory (bytes) the launch asks for and never touches: caps the CTAs of this launch per SM
   int64_t k_lo = 0, k_hi = ((int64_t)1 << 62);   // k-window: a tile's k-range (after kmode) is clipped to [k_lo, k_hi), multiples of 16;
                        // with beta == 1 a tile whose clipped range is empty is left untouched (K-chunked accumulation)
 };
@@ -106,5 +108,10 @@ int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int
 int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info);
 // W = L^-1 (lower) given L and the inverse diagonal blocks already in W's diagonal.
 int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw);
+// lfm_potrf_trtri that also returns diag(L) in `ldiag` (n doubles) and may start S = W^T W early: *early_done = 1 means the
+// top-left half block of A (lower) holds W11^T W11 instead of L11 and the caller must finish with lfm_lauum_late(S = A).
+int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
+                         double* ldiag, int* early_done);
+int lfm_lauum_late(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds);
 // S(lower) = W^T W, out of place.
 int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds);

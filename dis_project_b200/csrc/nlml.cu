@@ -293,12 +293,14 @@ static int check_common(int64_t N, int G, const void* X, const void* y, const vo
 // `variances` (N doubles or NULL) adds diag(variances) to Sigma: the heteroscedastic objective of the GPyTorch twin
 // (src/gpytorch_alfi/model_alfi.py:294-299); it touches the diagonal tiles of the Sigma build only.
 static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* variances,
-                       const double* theta, double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info) {
+                       const double* theta, double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info,
+                       double* ldiag = nullptr, int* early_done = nullptr) {
   LFM_TRY(lfm_launch_residual(st, N, s.Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_grid_build(st, N, G, X, theta, s.Tu, grad, s.grid, grid));
   LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, variances, jitter, 1, s.A, s.Np, grid));
   // the gradient needs W = L^-1 as well: built together with the factorisation
-  return grad ? lfm_potrf_trtri(st, s.Np, s.A, s.Np, s.W, s.Np, info) : lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
+  return grad ? lfm_potrf_trtri_diag(st, s.Np, s.A, s.Np, s.W, s.Np, info, ldiag, early_done)
+              : lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
 }
 
 extern "C" int lfm_nlml_het_tg(lfm_stream_t stream, int64_t N, int G, const double* X, const double* y,
@@ -342,26 +344,20 @@ struct EvalSide {
 };
 static thread_local EvalSide g_eval_side[16];  // per host thread and device
 
-__global__ void lfm_diag_copy_kernel(int64_t n, const double* __restrict__ A, int64_t lda, double* __restrict__ d) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < n) d[i] = A[i * lda + i];
-}
-
 static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* variances,
                           const double* theta, double jitter, const NlmlWs& s, double* out, int* info) {
   const int P = 3 * G + 2;
   LfmGrid grid;
-  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, true, &grid, info));
+  // the diagonal of L moves out of the way during the factorisation (the gradient scratch is idle until the contraction):
+  // Sigma^-1 overwrites L -- its first half block possibly before the factorisation is over (early_done)
+  double* ldiag = s.gscratch;
+  int early_done = 0;
+  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, true, &grid, info, ldiag, &early_done));
+  auto lauum = [&]() { return early_done ? lfm_lauum_late(st, s.Np, s.W, s.Np, s.A, s.Np) : lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np); };
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
   if (dev >= 0 && g_eval_side[dev].init()) {
     EvalSide& es = g_eval_side[dev];
-    // the diagonal of L moves out of the way first (the gradient scratch is idle until the contraction): Sigma^-1
-    // overwrites L while the side stream is still reducing
-    double* ldiag = s.gscratch;
-    lfm_diag_copy_kernel<<<(unsigned)((s.Np + 255) / 256), 256, 0, st>>>(s.Np, s.A, s.Np, ldiag);
-    LFM_LAUNCHED(1);
-    LFM_CUDA_OK(cudaGetLastError());
     LFM_CUDA_OK(cudaEventRecord(es.fork, st));
     LFM_CUDA_OK(cudaStreamWaitEvent(es.side, es.fork, 0));
     LFM_TRY(lfm_launch_alpha(es.side, s.Np, s.W, s.z, s.w, s.part, s.alpha));
@@ -369,14 +365,14 @@ static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, co
     LFM_LAUNCHED(1);
     LFM_CUDA_OK(cudaGetLastError());
     LFM_CUDA_OK(cudaEventRecord(es.join, es.side));
-    LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
+    LFM_TRY(lauum());  // Sigma^-1 (lower) overwrites L
     LFM_CUDA_OK(cudaStreamWaitEvent(st, es.join, 0));
   } else {
     LFM_TRY(lfm_launch_alpha(st, s.Np, s.W, s.z, s.w, s.part, s.alpha));
-    lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, s.A, s.Np, s.w, info, out);
+    lfm_nlml_reduce_kernel<<<1, 1024, 0, st>>>(N, s.Np, ldiag, 0, s.w, info, out);
     LFM_LAUNCHED(1);
     LFM_CUDA_OK(cudaGetLastError());
-    LFM_TRY(lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np));  // Sigma^-1 (lower) overwrites L
+    LFM_TRY(lauum());  // Sigma^-1 (lower) overwrites L
   }
   LFM_TRY(lfm_launch_grad_contract(st, N, X, G, theta, s.A, s.Np, s.alpha, s.gscratch, out + 1, &grid));
   lfm_poison_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, info, out + 1);

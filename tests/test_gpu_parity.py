@@ -88,6 +88,26 @@ def test_nlml_and_grad(cuda, G, T, R):
     assert relerr(out2[1:], g2) < RTOL
 
 
+def test_nlml_grad_half_sweep_sizes(cuda):
+    """N = 2048 (16 blocks of 128) is the smallest problem whose factorisation starts Sigma^-1 = W^T W early (W11^T W11 into
+    the dead L11 block half-way through the sweep, diag(L11) copied out first; chol.cu); N = 1920 (15 blocks) and N = 3200
+    (25 blocks) take the plain recursion.  Value (log-determinant from the copied diagonal) and gradient (the whole of
+    Sigma^-1) against the oracle."""
+    from dis_project_b200 import ops
+    for G, T in ((16, 128), (15, 128), (25, 128)):
+        x, y, var, _ = o.synthetic_problem(G, T, 1, seed=8)
+        p = rand_params(G, 9)
+        val_ref, g_ref = o.nlml_and_grad(p, x, y)
+        out, info = ops.nlml_grad(x, y, p.pack(), p.jitter, G)
+        out = out.cpu().numpy()
+        assert int(info.item()) == 0
+        assert abs(out[0] - val_ref) <= RTOL * abs(val_ref), (G, T)
+        assert relerr(out[1:], g_ref) < RTOL, (G, T)
+        plan = ops.NlmlGradPlan(torch.as_tensor(x).cuda(), torch.as_tensor(y).cuda(), G, p.jitter)
+        out2, info2 = plan(torch.as_tensor(p.pack()).cuda())
+        assert np.array_equal(out2.cpu().numpy(), out)   # the captured graph replays the same arithmetic
+
+
 def test_nlml_grad_vs_autograd(cuda):
     from dis_project_b200 import ops
     x, y, var, _ = o.synthetic_problem(5, 7, 3, seed=6)
