@@ -693,7 +693,7 @@ static void sm_partition_create(SmPartition& P, int dev) {
   // factorisation.  On the whole partition it took every slot for 280 us and the (short) trailing updates of the
   // chain-bound second half queued behind it; confined to half of the SMs it runs underneath that half instead.
   const char* e2 = getenv("LFM_TRI2_SMS");
-  const int want = e2 ? atoi(e2) : 72;
+  const int want = e2 ? atoi(e2) : 88;
   CUdevResource resB, sub[1], rem2;
   unsigned nb2 = 1;
   CUdevResourceDesc dC;
@@ -765,15 +765,18 @@ __global__ void lfm_chol_diag_copy_kernel(int64_t n, const double* __restrict__ 
 }
 static int early_lauum_mode() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("LFM_EARLY_LAUUM"); v = e ? atoi(e) : 0; }
+  if (v < 0) { const char* e = getenv("LFM_EARLY_LAUUM"); v = e ? atoi(e) : 2; }
   return v;
 }
 // `ldiag` (with_trtri only, may be NULL): n doubles that receive diag(L).  When it is given and the sweep has at least 16
-// blocks, the first half of Sigma^-1 = W^T W is started EARLY: as soon as W11 = L11^-1 is complete (half-way through the
-// sweep) diag(L11) is copied out and  S11' = W11^T W11  overwrites the lower triangle of the (dead) L11 block, on the
-// lowest-priority stream of the bulk partition, i.e. in the SM time the chain-bound second half leaves idle (~50 % of
-// the partition).  *early_done = 1 then, and the caller finishes with lfm_lauum_late (S11 = S11' + W21^T W21, the other
-// blocks as usual) instead of lfm_lauum.
+// blocks, the first half of Sigma^-1 = W^T W is started EARLY: diag(L11) is copied out and  S11' = W11^T W11  overwrites
+// the lower triangle of the (dead) L11 block on the lowest-priority stream of the bulk partition.  *early_done = 1 then,
+// and the caller finishes with lfm_lauum_late (S11 = S11' + W21^T W21, the other blocks as usual) instead of lfm_lauum.
+// LFM_EARLY_LAUUM = 2 (default): S11' starts when the chain is through, beside the serial tail of the inverse (four
+// short dependent launches on a mostly idle device): N = 4000 evaluation 3.238 -> 3.222 ms.  1: as soon as W11 is complete,
+// half-way through the sweep -- measured SLOWER (3.31 vs 3.25 ms): the 64 x 64-tile CTAs of the filler hold slots of the
+// partition for 40-170 us and the short kernels the chain-bound half waits for queue behind them (priority only
+// decides who gets a slot that frees).  0: off.
 static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
                                int64_t pivot_base, bool with_trtri = false, double* ldiag = nullptr, int* early_done = nullptr) {
   int dev = 0;
@@ -843,10 +846,10 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
       LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.leaf_done[e], 0));
       for (int64_t mb = 1; 2 * mb <= nb && m > 0; mb *= 2)
         if ((step + 1) % (2 * mb) == 0) LFM_TRY(tri_g2(tr, step + 1 - 2 * mb, mb));
-      if (early && 2 * (step + 1) == nb) {
+      if (early && 2 * (step + 1) == nb) LFM_CUDA_OK(cudaEventRecord(la.w11_done, tr));
+      if (early && early_lauum_mode() == 1 && 2 * (step + 1) == nb) {
         // W11 is complete behind everything `tr` has been given so far; every product that reads L11 precedes it there
         const int64_t h = n / 2;
-        LFM_CUDA_OK(cudaEventRecord(la.w11_done, tr));
         LFM_CUDA_OK(cudaStreamWaitEvent(la.fill, la.w11_done, 0));
         lfm_chol_diag_copy_kernel<<<(unsigned)((h + 255) / 256), 256, 0, la.fill>>>(h, A, lda, ldiag);
         LFM_LAUNCHED(1);
@@ -928,6 +931,19 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
   // join: everything after the factorisation is ordered behind the chain (and the inverse)
   LFM_CUDA_OK(cudaEventRecord(la.join, ch));
   LFM_CUDA_OK(cudaStreamWaitEvent(st, la.join, 0));
+  if (early && early_lauum_mode() == 2) {
+    // mode 2: S11' starts when the chain is through -- beside the serial tail of the inverse, whose first levels are
+    // four short dependent launches that leave most of the device idle
+    const int64_t h = n / 2;
+    LFM_CUDA_OK(cudaStreamWaitEvent(la.fill, la.w11_done, 0));
+    LFM_CUDA_OK(cudaStreamWaitEvent(la.fill, la.join, 0));
+    lfm_chol_diag_copy_kernel<<<(unsigned)((h + 255) / 256), 256, 0, la.fill>>>(h, A, lda, ldiag);
+    LFM_LAUNCHED(1);
+    LFM_CUDA_OK(cudaGetLastError());
+    LfmGemm g = mk(1, 0, h, h, h, W, ldw, W, ldw, A, lda, 1.0, 0.0, 1, LFM_K_GE_ROWCOL);
+    g.tile = 3;
+    LFM_TRY(gemm_kchunked(la.fill, g, 512));
+  }
   if (bk != st) {
     LFM_CUDA_OK(cudaEventRecord(la.bulk_join, bk));
     LFM_CUDA_OK(cudaStreamWaitEvent(st, la.bulk_join, 0));
