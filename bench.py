@@ -47,7 +47,7 @@ CONFIG = {"workload": "config 2: synthetic LFM 50 genes x 80 time points (N=4000
           "parallelism": "replicas only (one independent LFM per GPU; a single large-N Cholesky does not shard)",
           "l2": "256 MB buffer written between timed iterations (L2 flush); working set 268 MB > 126 MB L2",
           "scheduling": "factorisation streams in green contexts when the driver exports them (8-SM chain partition, 140-SM "
-                        "bulk partition, 72-SM sub-partition for the top-node product of the inverse; LFM_SM_PARTITION=0 "
+                        "bulk partition with panel, early-update, late-update, inverse and filler streams at three priorities, 88-SM sub-partition for the top-node product of the inverse; LFM_SM_PARTITION=0 "
                         "= stream priorities only)"}
 
 
@@ -205,7 +205,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     # the public API for repeated evaluations at fixed (X, y): a CUDA-graph evaluation plan (what JaxTrainer's
-    # objective uses); every step writes theta into the bound buffer and replays ~140 kernel launches
+    # objective uses); every step writes theta into the bound buffer and replays ~270 kernel launches
     plan = ops.NlmlGradPlan(X, y, G_C2, JITTER)
 
     def step():
@@ -324,7 +324,7 @@ def main():
                 "launches_per_eval": nl.value / args.steps, "kernel_s_per_eval": gemm_s,
                 "kernel_share_of_step": gemm_s / prof_step_s,
                 "kernel_s_per_eval_summed": lib.lfm_debug_profile_sum_ms() * 1e-3 / args.steps,
-                "note": "the factorisation launches on three streams and launches overlap: kernel_s_per_eval is the "
+                "note": "the factorisation launches on several streams and launches overlap: kernel_s_per_eval is the "
                         "length of the union of the launch intervals (CUDA-event timestamps), the plain sum is beside it",
                 "chain_tile_launches": {"kernel": "lfm_dgemm_kernel<.,.,1,4,2> (16 x 128 tiles; only with LFM_CHAIN_FUSED=0 -- by "
                                                   "default the chain step is lfm_chain_step_kernel, one 8-CTA cluster "
