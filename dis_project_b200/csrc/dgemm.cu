@@ -70,6 +70,13 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   double* sB = smem + STAGES * A_STAGE;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
+  long long* const stamp = (g.stamps && tid == 0) ? g.stamps + 8 * (int64_t)blockIdx.x : nullptr;
+  if (stamp) {
+    unsigned smid; long long gt;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    stamp[0] = smid; stamp[1] = clock64(); stamp[5] = gt;
+  }
   int tm, tn;
   if (g.lower_only) {
     // blockIdx.x enumerates lower-triangle tiles, longest k-range first: row tiles descending, except
@@ -80,7 +87,10 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     const int64_t total = (int64_t)gridDim.x;
     const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL);
     const int64_t t = skipped + (asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x);
-    int64_t i = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+    // row of triangular index t: single-precision estimate, exact integer correction.  (A double-precision sqrt here is
+    // ~14 dependent FP64 instructions that queue behind the DMMAs of the other CTA on the SM: `tools/tile_life.py` had a
+    // tile spend 2.2 k cycles -- a tenth of its life at K = 128 -- before its first memory request.)
+    int64_t i = (int64_t)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
     while ((i + 1) * (i + 2) / 2 <= t) ++i;
     while (i * (i + 1) / 2 > t) --i;
     tm = (int)i;
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   kb = max(kb, g.k_lo);
   ke = min(ke, g.k_hi);
   const int nk = ke > kb ? (int)((ke - kb) / BK) : 0;
-  if (nk == 0 && g.beta == 1.0) return;   // K-chunked accumulation: nothing of this chunk falls into the tile's k-range
+  if (nk == 0 && g.c_mode >= 2) return;   // K-chunked accumulation: nothing of this chunk falls into the tile's k-range
 
   double acc[WM][WN][2];
 #pragma unroll
@@ -163,12 +173,16 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     for (int q = 0; q < PP; ++q) issue_piece(uslot, kt0, q);
     cp_async_commit();
   };
+  if (stamp) stamp[7] = clock64();   // address set-up done, nothing requested yet
   issue_unit(0, 0);
   // beta = 1, alpha = +-1 (the trailing updates C -= P P^T of the factorisation, K = 128: eight k-tiles, where the
   // read-modify-write of C at the end was a visible share of a tile's life): the C tile is loaded into the accumulators
   // NOW, behind the first unit's cp.async, so both latencies overlap and the epilogue only stores.  out = alpha * acc
   // with acc initialised to alpha * C gives C + alpha * A B exactly (alpha^2 = 1).
-  const bool c_in_acc = g.beta == 1.0 && (g.alpha == 1.0 || g.alpha == -1.0) && nk > 0;
+  const bool c_in_acc = g.c_mode >= 2 && nk > 0;
+  // alpha = -1 as a flip of the sign bit (an integer instruction): the DMULs it replaces waited for the FP64 pipe too
+  const int sgn = g.c_mode == 3 ? (int)0x80000000 : 0;
+  auto flip = [&](double x) { return __hiloint2double(__double2hiint(x) ^ sgn, __double2loint(x)); };
   if (c_in_acc) {
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
@@ -177,14 +191,15 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
       for (int j = 0; j < WN; ++j) {
         const int64_t c = col0 + wn + j * 8 + fc * 2;
         const double2 old = __ldcg(reinterpret_cast<const double2*>(gC + r * g.ldc + c));
-        acc[i][j][0] = g.alpha * old.x;
-        acc[i][j][1] = g.alpha * old.y;
+        acc[i][j][0] = flip(old.x);
+        acc[i][j][1] = flip(old.y);
       }
     }
   }
   for (int u = 0; 2 * u < nk; ++u) {
     cp_async_wait<0>();
     __syncthreads();
+    if (stamp && u == 0) stamp[2] = clock64();
     // the unit's (up to) 8 k4-steps with explicitly double-buffered fragments: the LDS of step s+1
     // are issued before the 32 DMMAs of step s
     const int nsteps = (2 * u + 1 < nk) ? 8 : 4;
@@ -230,6 +245,7 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     }
   }
   cp_async_wait<0>();
+  if (stamp) stamp[3] = clock64();
 
   // epilogue: thread holds C[row = 8i + lane/4][col = 8j + 2*(lane%4) + {0,1}]
   const double alpha = g.alpha, beta = g.beta;
@@ -241,15 +257,25 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
       const int64_t c = col0 + wn + j * 8 + fc * 2;
       double2* p = reinterpret_cast<double2*>(gC + r * g.ldc + c);
       double2 o;
-      o.x = alpha * acc[i][j][0];
-      o.y = alpha * acc[i][j][1];
-      if (beta != 0.0 && !c_in_acc) {
+      if (c_in_acc) {
+        o.x = flip(acc[i][j][0]);
+        o.y = flip(acc[i][j][1]);
+      } else {
+        o.x = alpha * acc[i][j][0];
+        o.y = alpha * acc[i][j][1];
+      }
+      if (g.c_mode != 0 && !c_in_acc) {
         const double2 old = *p;
         o.x += beta * old.x;
         o.y += beta * old.y;
       }
       *p = o;
     }
+  }
+  if (stamp) {
+    long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    stamp[4] = clock64(); stamp[6] = gt;
   }
 }
 
@@ -413,6 +439,8 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
   }
   if (tiles <= 0) return LFM_OK;
   if (tiles > 0x7fffffff) return LFM_ERR_UNSUPPORTED;
+  LfmGemm gk = g;
+  gk.c_mode = g.beta == 0.0 ? 0 : ((g.beta == 1.0 && g.alpha == 1.0) ? 2 : ((g.beta == 1.0 && g.alpha == -1.0) ? 3 : 1));
   const bool prof = g_prof.on;
   std::unique_lock<std::mutex> lock(g_prof.mu, std::defer_lock);
   if (prof) {
@@ -444,7 +472,7 @@ static int launch(cudaStream_t st, const LfmGemm& g) {
       cudaGetLastError();
     }
     cfg.attrs = attr; cfg.numAttrs = nattr;
-    LFM_CUDA_OK(cudaLaunchKernelEx(&cfg, lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, g, (int)tn));
+    LFM_CUDA_OK(cudaLaunchKernelEx(&cfg, lfm_dgemm_kernel<TA, TBN, WM, WN, GM, SPREAD>, gk, (int)tn));
   }
   if (prof) cudaEventRecord(prof_event(), st);
   LFM_LAUNCHED(1);

@@ -94,6 +94,10 @@ struct LfmGemm {
   int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain);
                        // 2: 128 x 128 tiles; 3: 64 x 64 tiles
   int tri_skip = 0;    // lower_only: skip the output tiles of the first `tri_skip` rows of C (the look-ahead chain owns them)
+  int c_mode = -1;     // set by the launcher from alpha / beta (the kernel must not compare doubles: DSETP shares the FP64 pipe
+                       // with the co-resident CTA's DMMAs): 0: beta == 0; 1: general beta; 2 / 3: beta == 1 and alpha == +1 / -1 (C starts in the accumulators, signs by integer XOR)
+  long long* stamps = nullptr;   // debug (lfm_debug_syrk_stamps, include/lfm_b200.h): 8 words per CTA -- SM id, clock64 at entry / first unit
+                                 // landed / last DMMA issued / stores issued, globaltimer at entry and exit, clock64 when the addresses are set up
   int smem_pad = 0;    // extra dynamic shared memory (bytes) the launch asks for and never touches: caps the CTAs of this launch per SM
   int64_t k_lo = 0, k_hi = ((int64_t)1 << 62);   // k-window: a tile's k-range (after kmode) is clipped to [k_lo, k_hi), multiples of 16;
                        // with beta == 1 a tile whose clipped range is empty is left untouched (K-chunked accumulation)

@@ -472,6 +472,17 @@ extern "C" int lfm_debug_syrk(lfm_stream_t stream, int64_t m, int64_t K, const d
   g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
   return lfm_dgemm((cudaStream_t)stream, g);
 }
+// the same launch with 8 debug words per CTA (LfmGemm::stamps): what a tile's life is made of
+extern "C" int lfm_debug_syrk_stamps(lfm_stream_t stream, int64_t m, int64_t K, const double* P, int64_t ldp, double* Cm,
+                                     int64_t ldc, long long* stamps) {
+  LfmGemm g;
+  g.transA = 0; g.transB = 1; g.M = m; g.N = m; g.K = K; g.A = P; g.lda = ldp; g.B = P; g.ldb = ldp;
+  g.C = Cm; g.ldc = ldc; g.alpha = -1.0; g.beta = 1.0; g.lower_only = 1; g.kmode = LFM_K_FULL;
+  g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
+  g.stamps = stamps;
+  if (getenv("LFM_DEBUG_SYRK_BETA0")) g.beta = 0.0;   // experiment: the same launch without the read of C
+  return lfm_dgemm((cudaStream_t)stream, g);
+}
 extern "C" int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv,
                                      int* info) {
   if (n <= 0 || n % LFM_NB || !A || !W || !info) return LFM_ERR_INVALID;
