@@ -481,6 +481,7 @@ extern "C" int lfm_debug_syrk_stamps(lfm_stream_t stream, int64_t m, int64_t K, 
   g.batch = 1; g.strideA = g.strideB = g.strideC = 0;
   g.stamps = stamps;
   if (getenv("LFM_DEBUG_SYRK_BETA0")) g.beta = 0.0;   // experiment: the same launch without the read of C
+  if (const char* e = getenv("LFM_DEBUG_SYRK_PAD")) g.smem_pad = atoi(e);   // experiment: 40960 = one CTA per SM
   return lfm_dgemm((cudaStream_t)stream, g);
 }
 extern "C" int lfm_debug_potrf_potri(lfm_stream_t stream, int64_t n, double* A, double* W, double* Sinv,
