@@ -777,8 +777,12 @@ static int early_lauum_mode() {
 // half-way through the sweep -- measured SLOWER (3.31 vs 3.25 ms): the 64 x 64-tile CTAs of the filler hold slots of the
 // partition for 40-170 us and the short kernels the chain-bound half waits for queue behind them (priority only
 // decides who gets a slot that frees).  0: off.
+// `chain_ready` (may be NULL): an event the caller recorded on `st` once the first TWO block columns of A were complete
+// while it went on filling the rest (nlml.cu builds Sigma that way): the chain -- leaf(0), chain step 0 -- starts behind
+// that event, everything else behind all of st's work as usual.
 static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                               int64_t pivot_base, bool with_trtri = false, double* ldiag = nullptr, int* early_done = nullptr) {
+                               int64_t pivot_base, bool with_trtri = false, double* ldiag = nullptr, int* early_done = nullptr,
+                               cudaEvent_t chain_ready = nullptr) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
   if (!lookahead_mode() || n < 4 * NB || dev < 0 || !g_la_dev[dev].init()) {
@@ -796,7 +800,7 @@ static int potrf_right_looking(cudaStream_t st, int64_t n, double* A, int64_t ld
   cudaStream_t tr = la.tri;
   cudaStream_t bk = la.bulk ? la.bulk : st;   // bulk work: the large SM partition, or the caller's stream
   LFM_CUDA_OK(cudaEventRecord(la.fork, st));
-  LFM_CUDA_OK(cudaStreamWaitEvent(ch, la.fork, 0));
+  LFM_CUDA_OK(cudaStreamWaitEvent(ch, chain_ready ? chain_ready : la.fork, 0));
   if (bk != st) LFM_CUDA_OK(cudaStreamWaitEvent(bk, la.fork, 0));
   if (with_trtri) LFM_CUDA_OK(cudaStreamWaitEvent(tr, la.fork, 0));
   const int64_t nb = n / NB;
@@ -1001,17 +1005,25 @@ static int potrf_rec(cudaStream_t st, int64_t n, double* A, int64_t lda, double*
 
 // Cholesky and W = L^-1 together: for a single right-looking sweep (n <= threshold, power-of-two block count)
 // the inverse is interleaved with the factorisation, otherwise the two run back to back.
-int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                         double* ldiag, int* early_done) {
-  if (n <= 0 || n % NB) return LFM_ERR_INVALID;
-  if (early_done) *early_done = 0;
+// Whether lfm_potrf_trtri_diag(n, lda == ldw) runs as ONE interleaved right-looking sweep (the path that can start its chain
+// behind a `chain_ready` event).
+bool lfm_potrf_trtri_is_one_sweep(int64_t n) {
   const int64_t nblk = n / NB;
   static int fuse = -1;
   if (fuse < 0) { const char* e = getenv("LFM_FUSE_TRTRI"); fuse = e ? atoi(e) : 1; }
-  if (fuse && nblk >= 4 && (nblk & (nblk - 1)) == 0 && lda == ldw && n <= rl_threshold()) {
-    LFM_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
-    return potrf_right_looking(st, n, A, lda, W, ldw, info, 0, true, ldiag, early_done);
+  return fuse && n > 0 && n % NB == 0 && nblk >= 4 && (nblk & (nblk - 1)) == 0 && n <= rl_threshold() && lookahead_mode();
+}
+// `chain_ready` (may be NULL, only with lfm_potrf_trtri_is_one_sweep(n)): see potrf_right_looking; the caller has then zeroed
+// *info itself BEFORE recording the event (the first leaf may report a failing pivot as soon as the event fires).
+int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
+                         double* ldiag, int* early_done, cudaEvent_t chain_ready) {
+  if (n <= 0 || n % NB) return LFM_ERR_INVALID;
+  if (early_done) *early_done = 0;
+  if (lfm_potrf_trtri_is_one_sweep(n) && lda == ldw) {
+    if (!chain_ready) LFM_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
+    return potrf_right_looking(st, n, A, lda, W, ldw, info, 0, true, ldiag, early_done, chain_ready);
   }
+  if (chain_ready) return LFM_ERR_INVALID;
   LFM_TRY(lfm_potrf(st, n, A, lda, W, ldw, info));
   LFM_TRY(lfm_trtri(st, n, A, lda, W, ldw));
   if (ldiag) {
@@ -1022,7 +1034,7 @@ int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, dou
   return LFM_OK;
 }
 int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {
-  return lfm_potrf_trtri_diag(st, n, A, lda, W, ldw, info, nullptr, nullptr);
+  return lfm_potrf_trtri_diag(st, n, A, lda, W, ldw, info, nullptr, nullptr, nullptr);
 }
 
 int lfm_potrf(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info) {

@@ -41,10 +41,10 @@ __global__ void __launch_bounds__(256) lfm_gram_tile_kernel(int64_t N, int64_t M
                                                           double* __restrict__ out, int64_t ld,
                                                           const double* __restrict__ diag_vec,
                                                           double diag_const, int add_sigma2, int64_t Npad,
-                                                          LfmGrid grid) {
+                                                          LfmGrid grid, int tc0) {
   __shared__ LfmPoint rowp[GT];
   __shared__ LfmPoint colp[GT];
-  const int64_t tr = blockIdx.y, tc = blockIdx.x;
+  const int64_t tr = blockIdx.y, tc = blockIdx.x + tc0;   // tc0: first column tile of this launch
   if (MODE == 1 && tc > tr) return;
   // time-grid tables (training matrix only): valid when the distinct times fit the caller's bound.  Both
   // instantiations are launched; the one that does not apply exits here.
@@ -112,7 +112,7 @@ int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X,
   if (grid.y > 65535) return LFM_ERR_UNSUPPORTED;
   LfmGrid none;
   memset(&none, 0, sizeof(none));
-  lfm_gram_tile_kernel<0, false><<<grid, dim3(32, 8), 0, st>>>(N, M, X, Y, G, theta, out, ld, nullptr, 0.0, 0, 0, none);
+  lfm_gram_tile_kernel<0, false><<<grid, dim3(32, 8), 0, st>>>(N, M, X, Y, G, theta, out, ld, nullptr, 0.0, 0, 0, none, 0);
   LFM_LAUNCHED(1);
   LFM_CUDA_OK(cudaGetLastError());
   return LFM_OK;
@@ -121,17 +121,22 @@ int lfm_launch_cross_cov(cudaStream_t st, int64_t N, int64_t M, const double* X,
 // Sigma (lower tiles, padded to Npad) = k_xx(X, X) + diag(diag_vec) + (diag_const [+ sigma^2]) I
 int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G,
                            const double* theta, const double* diag_vec, double diag_const, int add_sigma2,
-                           double* out, int64_t ld, const LfmGrid* tg) {
-  dim3 grid((unsigned)(Npad / GT), (unsigned)(Npad / GT));
+                           double* out, int64_t ld, const LfmGrid* tg, int64_t col_begin, int64_t col_end) {
+  // [col_begin, col_end): the block of columns this launch builds (multiples of 64; default: all of them)
+  if (col_end < 0 || col_end > Npad) col_end = Npad;
+  if (col_begin < 0) col_begin = 0;
+  if (col_begin >= col_end) return LFM_OK;
+  dim3 grid((unsigned)((col_end - col_begin) / GT), (unsigned)(Npad / GT));
+  const int tc0 = (int)(col_begin / GT);
   LfmGrid tgv;
   memset(&tgv, 0, sizeof(tgv));
   if (tg) tgv = *tg;
   lfm_gram_tile_kernel<1, false><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
-                                                              add_sigma2, Npad, tgv);
+                                                              add_sigma2, Npad, tgv, tc0);
   LFM_LAUNCHED(1);
   if (tgv.Tu > 0) {
     lfm_gram_tile_kernel<1, true><<<grid, dim3(32, 8), 0, st>>>(N, N, X, X, G, theta, out, ld, diag_vec, diag_const,
-                                                               add_sigma2, Npad, tgv);
+                                                               add_sigma2, Npad, tgv, tc0);
     LFM_LAUNCHED(1);
   }
   LFM_CUDA_OK(cudaGetLastError());

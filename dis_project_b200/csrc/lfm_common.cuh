@@ -114,8 +114,12 @@ int lfm_potrf_trtri(cudaStream_t st, int64_t n, double* A, int64_t lda, double* 
 int lfm_trtri(cudaStream_t st, int64_t n, const double* L, int64_t ldl, double* W, int64_t ldw);
 // lfm_potrf_trtri that also returns diag(L) in `ldiag` (n doubles) and may start S = W^T W early: *early_done = 1 means the
 // top-left half block of A (lower) holds W11^T W11 instead of L11 and the caller must finish with lfm_lauum_late(S = A).
+// `chain_ready` (may be NULL; only when lfm_potrf_trtri_is_one_sweep(n) and lda == ldw): an event recorded on `st` when the first two
+// block columns (256) of A were complete and *info zeroed, with the rest of A still being written by later work on `st`: the
+// dependent chain of the factorisation starts behind the event instead of behind all of it.
+bool lfm_potrf_trtri_is_one_sweep(int64_t n);
 int lfm_potrf_trtri_diag(cudaStream_t st, int64_t n, double* A, int64_t lda, double* W, int64_t ldw, int* info,
-                         double* ldiag, int* early_done);
+                         double* ldiag, int* early_done, cudaEvent_t chain_ready = nullptr);
 int lfm_lauum_late(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds);
 // S(lower) = W^T W, out of place.
 int lfm_lauum(cudaStream_t st, int64_t n, const double* W, int64_t ldw, double* S, int64_t lds);

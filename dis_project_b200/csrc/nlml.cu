@@ -294,11 +294,23 @@ static int check_common(int64_t N, int G, const void* X, const void* y, const vo
 // (src/gpytorch_alfi/model_alfi.py:294-299); it touches the diagonal tiles of the Sigma build only.
 static int nlml_factor(cudaStream_t st, int64_t N, int G, const double* X, const double* y, const double* variances,
                        const double* theta, double jitter, const NlmlWs& s, bool grad, LfmGrid* grid, int* info,
-                       double* ldiag = nullptr, int* early_done = nullptr) {
+                       double* ldiag = nullptr, int* early_done = nullptr, cudaEvent_t chain_ready = nullptr) {
   LFM_TRY(lfm_launch_residual(st, N, s.Np, X, y, G, theta, s.z, nullptr));
   LFM_TRY(lfm_grid_build(st, N, G, X, theta, s.Tu, grad, s.grid, grid));
+  // the gradient needs W = L^-1 as well: built together with the factorisation.  When that is one right-looking sweep,
+  // Sigma is built in two launches -- its first two block columns (all the first leaf and the first chain step read),
+  // then the rest -- and the dependent chain starts behind the first one: ~50 us of an N = 4000 evaluation in which the
+  // chain partition used to wait for 8 N^2 bytes of Sigma it does not touch.
+  static int split = -1;
+  if (split < 0) { const char* e = getenv("LFM_SIGMA_SPLIT"); split = e ? atoi(e) : 1; }
+  if (grad && split && chain_ready && lfm_potrf_trtri_is_one_sweep(s.Np) && s.Np >= 8 * LFM_NB) {
+    LFM_CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int), st));
+    LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, variances, jitter, 1, s.A, s.Np, grid, 0, 2 * LFM_NB));
+    LFM_CUDA_OK(cudaEventRecord(chain_ready, st));
+    LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, variances, jitter, 1, s.A, s.Np, grid, 2 * LFM_NB, s.Np));
+    return lfm_potrf_trtri_diag(st, s.Np, s.A, s.Np, s.W, s.Np, info, ldiag, early_done, chain_ready);
+  }
   LFM_TRY(lfm_launch_sigma_lower(st, N, s.Np, X, G, theta, variances, jitter, 1, s.A, s.Np, grid));
-  // the gradient needs W = L^-1 as well: built together with the factorisation
   return grad ? lfm_potrf_trtri_diag(st, s.Np, s.A, s.Np, s.W, s.Np, info, ldiag, early_done)
               : lfm_potrf(st, s.Np, s.A, s.Np, s.W, s.Np, info);
 }
@@ -331,11 +343,12 @@ extern "C" int lfm_nlml(lfm_stream_t stream, int64_t N, int G, const double* X, 
 // so they run beside Sigma^-1 = W^T W (the longest single launch of an evaluation) instead of in front of it.
 struct EvalSide {
   cudaStream_t side = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, cols = nullptr;   // cols: the first two block columns of Sigma are built
   bool ok = false;
   bool init() {
     if (ok) return true;
     if (cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) != cudaSuccess) return false;
+    if (cudaEventCreateWithFlags(&cols, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return false;
     if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) return false;
     ok = true;
@@ -352,10 +365,11 @@ static int nlml_grad_impl(cudaStream_t st, int64_t N, int G, const double* X, co
   // Sigma^-1 overwrites L -- its first half block possibly before the factorisation is over (early_done)
   double* ldiag = s.gscratch;
   int early_done = 0;
-  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, true, &grid, info, ldiag, &early_done));
-  auto lauum = [&]() { return early_done ? lfm_lauum_late(st, s.Np, s.W, s.Np, s.A, s.Np) : lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np); };
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) dev = -1;
+  cudaEvent_t chain_ready = (dev >= 0 && g_eval_side[dev].init()) ? g_eval_side[dev].cols : nullptr;
+  LFM_TRY(nlml_factor(st, N, G, X, y, variances, theta, jitter, s, true, &grid, info, ldiag, &early_done, chain_ready));
+  auto lauum = [&]() { return early_done ? lfm_lauum_late(st, s.Np, s.W, s.Np, s.A, s.Np) : lfm_lauum(st, s.Np, s.W, s.Np, s.A, s.Np); };
   if (dev >= 0 && g_eval_side[dev].init()) {
     EvalSide& es = g_eval_side[dev];
     LFM_CUDA_OK(cudaEventRecord(es.fork, st));

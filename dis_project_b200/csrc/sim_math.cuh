@@ -232,7 +232,7 @@ __device__ __forceinline__ double lfm_kff(double t, double tp, double l) {
 // Sigma (lower tiles, padded to Npad) = k_xx(X, X) + diag(diag_vec) + (diag_const [+ sigma^2]) I
 int lfm_launch_sigma_lower(cudaStream_t st, int64_t N, int64_t Npad, const double* X, int G, const double* theta,
                            const double* diag_vec, double diag_const, int add_sigma2, double* out, int64_t ld,
-                           const LfmGrid* tg = nullptr);
+                           const LfmGrid* tg = nullptr, int64_t col_begin = 0, int64_t col_end = -1);
 size_t lfm_grad_scratch_doubles(int64_t N);
 int lfm_launch_grad_contract(cudaStream_t st, int64_t N, const double* X, int G, const double* theta,
                              const double* Sinv, int64_t ld, const double* alpha, double* scratch, double* grad,
