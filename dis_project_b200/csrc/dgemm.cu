@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     const int64_t srows = g.tri_skip / BM;
     const int64_t skipped = srows * (srows + 1) / 2;
     const int64_t total = (int64_t)gridDim.x;
-    const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL);
+    const bool asc = (g.kmode == LFM_K_GE_ROW || g.kmode == LFM_K_GE_ROWCOL || g.kmode == LFM_K_LAUUM_LATE);
     const int64_t t = skipped + (asc ? (int64_t)blockIdx.x : total - 1 - (int64_t)blockIdx.x);
     // row of triangular index t: single-precision estimate, exact integer correction.  (A double-precision sqrt here is
     // ~14 dependent FP64 instructions that queue behind the DMMAs of the other CTA on the SM: `tools/tile_life.py` had a
@@ -109,12 +109,15 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
     case LFM_K_GE_COL: kb = col0; break;
     case LFM_K_GE_ROW: kb = row0; break;
     case LFM_K_GE_ROWCOL: kb = max(row0, col0); break;
+    case LFM_K_LAUUM_LATE: kb = row0 < g.k_split ? g.k_split : max(row0, col0); break;
     default: break;
   }
+  // (per-tile accumulate mode of LFM_K_LAUUM_LATE; every other launch: the launcher's mode word)
+  const int c_mode = g.kmode == LFM_K_LAUUM_LATE ? (row0 < g.k_split ? 2 : 0) : g.c_mode;
   kb = max(kb, g.k_lo);
   ke = min(ke, g.k_hi);
   const int nk = ke > kb ? (int)((ke - kb) / BK) : 0;
-  if (nk == 0 && g.c_mode >= 2) return;   // K-chunked accumulation: nothing of this chunk falls into the tile's k-range
+  if (nk == 0 && c_mode >= 2) return;   // K-chunked accumulation: nothing of this chunk falls into the tile's k-range
 
   double acc[WM][WN][2];
 #pragma unroll
@@ -179,9 +182,9 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   // read-modify-write of C at the end was a visible share of a tile's life): the C tile is loaded into the accumulators
   // NOW, behind the first unit's cp.async, so both latencies overlap and the epilogue only stores.  out = alpha * acc
   // with acc initialised to alpha * C gives C + alpha * A B exactly (alpha^2 = 1).
-  const bool c_in_acc = g.c_mode >= 2 && nk > 0;
+  const bool c_in_acc = c_mode >= 2 && nk > 0;
   // alpha = -1 as a flip of the sign bit (an integer instruction): the DMULs it replaces waited for the FP64 pipe too
-  const int sgn = g.c_mode == 3 ? (int)0x80000000 : 0;
+  const int sgn = c_mode == 3 ? (int)0x80000000 : 0;
   auto flip = [&](double x) { return __hiloint2double(__double2hiint(x) ^ sgn, __double2loint(x)); };
   if (c_in_acc) {
 #pragma unroll
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
         o.x = alpha * acc[i][j][0];
         o.y = alpha * acc[i][j][1];
       }
-      if (g.c_mode != 0 && !c_in_acc) {
+      if (c_mode != 0 && !c_in_acc) {
         const double2 old = *p;
         o.x += beta * old.x;
         o.y += beta * old.y;
@@ -318,6 +321,7 @@ static double gemm_exec_flops(const LfmGemm& g, int BM, int BN) {
         case LFM_K_GE_COL: kb = col0; break;
         case LFM_K_GE_ROW: kb = row0; break;
         case LFM_K_GE_ROWCOL: kb = row0 > col0 ? row0 : col0; break;
+        case LFM_K_LAUUM_LATE: kb = row0 < g.k_split ? g.k_split : (row0 > col0 ? row0 : col0); break;
         default: break;
       }
       if (kb < g.k_lo) kb = g.k_lo;

@@ -77,7 +77,9 @@ enum LfmKMode {
   LFM_K_LE_ROW = 1,   // k <  row_tile_end          (A lower-triangular, op(A) = A)
   LFM_K_GE_COL = 2,   // k >= col_tile_start        (B lower-triangular, op(B) = B, NN)
   LFM_K_GE_ROW = 3,   // k >= row_tile_start        (op(A) = A^T with A lower-triangular)
-  LFM_K_GE_ROWCOL = 4 // k >= max(row, col) start   (A^T A with A lower-triangular)
+  LFM_K_GE_ROWCOL = 4, // k >= max(row, col) start   (A^T A with A lower-triangular)
+  LFM_K_LAUUM_LATE = 5 // as 4 for the tiles of the rows >= k_split (beta = 0); tiles of the rows < k_split ACCUMULATE (beta = 1) over
+                       // k >= k_split only: the rest of S = W^T W when S11' = W11^T W11 is already in place (lfm_lauum_late), one launch
 };
 struct LfmGemm {
   int transA, transB;  // op(A) = A (M x K row-major) or A^T (A stored K x M row-major); same for B (op(B) is K x N;
@@ -94,6 +96,7 @@ struct LfmGemm {
   int tile = 0;        // 0: heuristic; 1: 16 x 128 tiles (latency-critical 128-row panels on the factorisation chain);
                        // 2: 128 x 128 tiles; 3: 64 x 64 tiles
   int tri_skip = 0;    // lower_only: skip the output tiles of the first `tri_skip` rows of C (the look-ahead chain owns them)
+  int64_t k_split = 0; // LFM_K_LAUUM_LATE
   int c_mode = -1;     // set by the launcher from alpha / beta (the kernel must not compare doubles: DSETP shares the FP64 pipe
                        // with the co-resident CTA's DMMAs): 0: beta == 0; 1: general beta; 2 / 3: beta == 1 and alpha == +1 / -1 (C starts in the accumulators, signs by integer XOR)
   long long* stamps = nullptr;   // debug (lfm_debug_syrk_stamps, include/lfm_b200.h): 8 words per CTA -- SM id, clock64 at entry / first unit
