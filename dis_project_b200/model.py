@@ -199,3 +199,39 @@ class ExactLFM:
         t = _to_host(test_inputs)
         mean, cov, var, info = ops.gene_posterior(x, y, variances, self.pack(), self.jitter, t, self.num_genes)
         return GaussianDistribution(mean, cov)
+
+    # ---- the GPyTorch twin's posteriors (reference src/gpytorch_alfi/model_alfi.py:68-150) ------------------
+    # Same two C-ABI entry points, the twin's conventions: no mean function (basal rates play no part), training
+    # covariance K_xx + 1e-4 I + diag(measurement variances) without the likelihood noise (model_alfi.py:282-299),
+    # K_ff + 1e-3 I (K_ff of the twin), and `jitter` added to the predictive variances at the end.
+    TWIN_KERNEL_JITTER = 1e-4
+
+    def _twin_theta(self, sigma: float) -> np.ndarray:
+        theta = self.pack()
+        G = self.num_genes
+        theta[2 * G:3 * G] = 0.0
+        theta[3 * G + 1] = sigma
+        return theta
+
+    def predict_f(self, pred_t, train_data: JaxP53Data, jitter: float = 1e-3):
+        """Twin's ``ExactLFM.predict_f(pred_t, jitter)`` (model_alfi.py:109-150): latent force at the times
+        ``pred_t``; returns (mean (T*,), variance (T*,)) -- the twin keeps the diagonal too (:141-143)."""
+        x, y, variances = dataset_3d(train_data)
+        t = _to_host(pred_t).reshape(-1)
+        xs = np.stack((t, -np.ones_like(t), np.zeros_like(t)), axis=-1)
+        kj = self.TWIN_KERNEL_JITTER
+        mean, var, info = ops.latent_posterior(x, y, variances, self._twin_theta(0.0), kj, xs, self.num_genes)
+        var = var.cpu().numpy() - 2.0 * kj + 1e-3 + float(jitter)
+        return mean.cpu().numpy(), var
+
+    def predict_m(self, pred_t, train_data: JaxP53Data, jitter: float = 1e-5):
+        """Twin's ``ExactLFM.predict_m(pred_t, jitter)`` (model_alfi.py:68-107): gene expressions at the times
+        ``pred_t``; returns (mean (T*, G), variance (T*, G)) as the twin's batch of diagonal normals (:100-107)."""
+        x, y, variances = dataset_3d(train_data)
+        t = _to_host(pred_t).reshape(-1)
+        G, T = self.num_genes, t.size
+        xg = np.stack((np.tile(t, G), np.repeat(np.arange(G), T).astype(np.float64), np.ones(G * T)), axis=-1)
+        kj = self.TWIN_KERNEL_JITTER
+        mean, _, var, info = ops.gene_posterior(x, y, variances, self._twin_theta(float(np.sqrt(kj))), kj, xg, G,
+                                                full_cov=False)
+        return mean.cpu().numpy().reshape(G, T).T, (var.cpu().numpy() + float(jitter)).reshape(G, T).T

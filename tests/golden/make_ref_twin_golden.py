@@ -6,6 +6,10 @@ of ``tests/golden/ref_csv``, exactly as ``src/gpytorch_alfi/main_alfi.py:24-35``
     model = ExactLFM(dataset, dataset.gene_variances.reshape(-1))
     loss = -ExactMarginalLogLikelihood(model.likelihood, model)(model(model.train_t), model.train_y.squeeze())
 
+Also recorded per parameter point: ``model.predict_f`` / ``model.predict_m`` (model_alfi.py:68-150) on the 80 prediction
+times of main_alfi.py:55-57 -- the twin's posteriors, with its own conventions (no mean function, Sigma = K_xx + 1e-4 I +
+diag(variances) without the likelihood noise, K_ff + 1e-3 I, float32 K_xf).
+
 This is the second, independent implementation of the same formulas inside the reference (block-structured Gram,
 model_alfi.py:266-300) and the source of the heteroscedastic training convention
 ``K_xx + 1e-4 I + diag(variances) (+ likelihood noise I)`` (model_alfi.py:294-299) that ``lfm_nlml_het_tg`` implements.
@@ -63,7 +67,36 @@ def main(out_dir=HERE):
             loss = -loss_fn(output, model.train_y.squeeze())                          # trainer_alfi.py:173
             loss.backward()
             K = model.covar_module(model.train_t).evaluate()
+            # the twin's posteriors exactly as main_alfi.py:55-57 calls them (80 times on [0, 13], jitter 1e-3).  K_xf()
+            # REPLACES the kernel's own k_xf method by its result (model_alfi.py: `self.k_xf = K_xf`), so predict_f works once
+            # per kernel object: the attribute is removed afterwards, which is what a fresh model would see.
+            with torch.no_grad():
+                t_predict = torch.linspace(0, 13, 80, dtype=torch.float64)
+                p_f = model.predict_f(t_predict, jitter=1e-3)
+                del model.covar_module.k_xf
+                p_m = model.predict_m(t_predict, jitter=1e-3)
+                post = {"t_predict": L(t_predict), "jitter": 1e-3,
+                        "f_mean": L(p_f.mean.reshape(-1)), "f_var": L(torch.diagonal(p_f.covariance_matrix, dim1=-2, dim2=-1).reshape(-1)),
+                        "m_mean": L(p_m.mean),                                                # (80, G)
+                        "m_var": L(torch.diagonal(p_m.covariance_matrix, dim1=-2, dim2=-1))}  # (80, G)
+                # the same unmodified methods after `model.double()` (torch.nn.Module API: the raw parameters become float64):
+                # what is left of float32 is K_xf's buffer (model_alfi.py: `torch.zeros(shape, dtype=torch.float32)`), so
+                # predict_m is float64 throughout and pins the conventions to ~1e-9 instead of float32 rounding
+                import copy
+                m64 = copy.deepcopy(model).double()
+                q_f = m64.predict_f(t_predict, jitter=1e-3)
+                del m64.covar_module.k_xf
+                q_m = m64.predict_m(t_predict, jitter=1e-3)
+                out64 = m64(m64.train_t)
+                post["f64"] = {"f_mean": L(q_f.mean.reshape(-1)),
+                               "f_var": L(torch.diagonal(q_f.covariance_matrix, dim1=-2, dim2=-1).reshape(-1)),
+                               "m_mean": L(q_m.mean), "m_var": L(torch.diagonal(q_m.covariance_matrix, dim1=-2, dim2=-1)),
+                               "loss": float(-ExactMarginalLogLikelihood(m64.likelihood, m64)(out64, m64.train_y.squeeze())),
+                               "decay": L(m64.covar_module.decay), "sensitivity": L(m64.covar_module.sensitivity),
+                               "basal": L(m64.mean_module.basal), "lengthscale": float(m64.covar_module.lengthscale),
+                               "noise": float(m64.likelihood.noise)}
             points.append({
+                "posterior": post,
                 "label": label,
                 "decay": L(model.covar_module.decay), "sensitivity": L(model.covar_module.sensitivity),
                 "basal": L(model.mean_module.basal), "lengthscale": float(model.covar_module.lengthscale),

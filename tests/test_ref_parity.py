@@ -339,3 +339,77 @@ def test_cuda_heteroscedastic_objective_matches_the_gpytorch_twin(cuda, name):
         assert np.max(np.abs(out[1:] - g_twin)) <= 1e-4 * np.max(np.abs(g_twin))
         K = ops.gram(X, theta, G).cpu().numpy() + np.diag(var) + c["kernel_jitter"] * np.eye(N)
         assert rel(K, pt["K_xx"]) < 1e-6
+
+# ---- the twin's posteriors (model_alfi.py:68-150: predict_f / predict_m as main_alfi.py:55-57 calls them) ---------------
+# Conventions the twin has and latent_predict / multi_gene_predict of src/model.py do not, expressed through the SAME entry
+# points: no mean function (basal = 0), Sigma = K_xx + 1e-4 I + diag(variances) WITHOUT the likelihood noise (latent: sigma
+# = 0 with jitter 1e-4; genes: sigma^2 = 1e-4), K_ff + 1e-3 I before and `jitter` after the Schur complement.  The fixture
+# holds the run with the twin's float32 parameters (float32 rounding, amplified by torch.inverse) and the same unmodified
+# methods after model.double(), where only K_xf's float32 buffer is left: predict_m then pins the conventions to 1e-9.
+def _twin_posterior_problem(c, pt, which):
+    G = c["G"]
+    po = pt["posterior"]
+    src = po["f64"] if which == "f64" else pt
+    ts = np.array(po["t_predict"])
+    T = ts.size
+    d, s_, l = np.array(src["decay"]), np.array(src["sensitivity"]), float(src["lengthscale"])
+    Xs = np.stack((ts, -np.ones(T), np.zeros(T)), axis=-1)                                         # utils.py:268-287 layout
+    Xg = np.stack((np.tile(ts, G), np.repeat(np.arange(G), T).astype(np.float64), np.ones(G * T)), axis=-1)
+    want = po["f64"] if which == "f64" else po
+    f_mean, f_var = np.array(want["f_mean"]), np.array(want["f_var"])
+    m_mean, m_var = np.array(want["m_mean"]).T.reshape(-1), np.array(want["m_var"]).T.reshape(-1)   # (80, G) -> gene-major
+    return d, s_, l, Xs, Xg, f_mean, f_var, m_mean, m_var, po["jitter"]
+
+
+TWIN_POST_TOL = {"f32": (5e-4, 2e-5, 5e-4, 2e-5), "f64": (5e-5, 5e-6, 1e-8, 1e-9)}   # f mean, f var, m mean, m var
+
+
+@pytest.mark.parametrize("which", ["f32", "f64"])
+@pytest.mark.parametrize("name", TWIN_CASES)
+def test_oracle_posteriors_match_the_gpytorch_twin(name, which):
+    c, G, N, X, y, var = _twin(name)
+    tol = TWIN_POST_TOL[which]
+    for pt in c["points"]:
+        d, s_, l, Xs, Xg, f_mean, f_var, m_mean, m_var, jit = _twin_posterior_problem(c, pt, which)
+        p = o.Params(d=d, s=s_, b=np.zeros(G), l=l, sigma=0.0, jitter=c["kernel_jitter"])
+        m, v = o.latent_predict(p, Xs, X, y, var)                    # var = 1 + 2 * 1e-4 - k^T Sigma^-1 k
+        v = v - 2 * c["kernel_jitter"] + 1e-3 + jit                  # twin: K_ff + 1e-3 I (model_alfi.py K_ff), + jitter (:143)
+        assert rel(m, f_mean) < tol[0] and rel(v, f_var) < tol[1]
+        p2 = o.Params(d=d, s=s_, b=np.zeros(G), l=l, sigma=np.sqrt(c["kernel_jitter"]), jitter=c["kernel_jitter"])
+        mm, cov = o.multi_gene_predict(p2, Xg, X, y, var)            # cov = K_tt - ... + 1e-4 I  (K_tt + 1e-4 I: model_alfi.py:294-296)
+        assert rel(mm, m_mean) < tol[2] and rel(np.diag(cov) + jit, m_var) < tol[3]                 # + jitter (:107)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["f32", "f64"])
+@pytest.mark.parametrize("name", TWIN_CASES)
+def test_cuda_posteriors_match_the_gpytorch_twin(cuda, name, which):
+    from dis_project_b200 import ops
+    c, G, N, X, y, var = _twin(name)
+    tol = TWIN_POST_TOL[which]
+    kj = c["kernel_jitter"]
+    for pt in c["points"]:
+        d, s_, l, Xs, Xg, f_mean, f_var, m_mean, m_var, jit = _twin_posterior_problem(c, pt, which)
+        theta = np.concatenate([d, s_, np.zeros(G), [l, 0.0]])
+        m, v, info = ops.latent_posterior(X, y, var, theta, kj, Xs, G)
+        assert int(info.item()) == 0
+        assert rel(m.cpu().numpy(), f_mean) < tol[0] and rel(v.cpu().numpy() - 2 * kj + 1e-3 + jit, f_var) < tol[1]
+        theta2 = np.concatenate([d, s_, np.zeros(G), [l, np.sqrt(kj)]])
+        mm, cov, vv, info2 = ops.gene_posterior(X, y, var, theta2, kj, Xg, G)
+        assert int(info2.item()) == 0
+        assert rel(mm.cpu().numpy(), m_mean) < tol[2] and rel(vv.cpu().numpy() + jit, m_var) < tol[3]
+        # the same through the model class (dis_project_b200.ExactLFM.predict_f / predict_m mirror the twin's methods)
+        from dis_project_b200.model import ExactLFM
+        T7 = N // G
+
+        class _Arrays:   # what dataset_3d reads of a JaxP53Data: one (times, expressions) entry per gene, the variances
+            num_genes, gene_variances = G, var.reshape(G, T7)
+            def __len__(self): return G
+            def __getitem__(self, i): return np.stack((np.array(c["train_t"])[:T7], y.reshape(G, T7)[i]))
+
+        data = _Arrays()
+        mdl = ExactLFM(jitter=kj, data=data, num_genes=G).with_leaves(np.concatenate([d, s_, np.full(G, 0.05), [l, 1.0]]))
+        fm, fv = mdl.predict_f(np.array(pt["posterior"]["t_predict"]), data, jitter=jit)
+        pm, pv = mdl.predict_m(np.array(pt["posterior"]["t_predict"]), data, jitter=jit)
+        assert rel(fm, f_mean) < tol[0] and rel(fv, f_var) < tol[1]
+        assert rel(pm.T.reshape(-1), m_mean) < tol[2] and rel(pv.T.reshape(-1), m_var) < tol[3]
