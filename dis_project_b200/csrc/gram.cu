@@ -15,6 +15,9 @@
 #include "sim_math.cuh"
 
 #define GT 64  // tile edge
+#ifndef LFM_GC_MINB
+#define LFM_GC_MINB 2
+#endif
 
 __device__ __forceinline__ void lfm_stage_points(LfmPoint* sp, const double* __restrict__ X, int64_t n,
                                                  int64_t base, int G, const double* __restrict__ theta,
@@ -162,7 +165,7 @@ static int lfm_gc_tiles(int64_t ntile) {
 }
 
 template <bool TAB>
-__global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
+__global__ void __launch_bounds__(256, TAB ? LFM_GC_MINB : 1) lfm_grad_contract_kernel(int64_t N, const double* __restrict__ X, int G,
                                                               const double* __restrict__ theta,
                                                               const double* __restrict__ Sinv, int64_t ld,
                                                               const double* __restrict__ alpha,
@@ -186,7 +189,12 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
   const bool tab = grid.Tu > 0 && *grid.count <= grid.Tu;
   if (tab != TAB) return;   // both instantiations are launched; the one that does not apply exits here
   const int* tix = TAB ? grid.tidx : nullptr;
-  if (tid < 64) lfm_stage_points(rowp, X, N, (int64_t)I * GT, G, theta, l, true, tid, tix);
+  __shared__ LfmPointGrad rowx[TAB ? GT : 1];   // per-point parts of the regrouped h-derivatives (table path only)
+  __shared__ LfmPointGrad colx[TAB ? GT : 1];
+  if (tid < 64) {
+    lfm_stage_points(rowp, X, N, (int64_t)I * GT, G, theta, l, true, tid, tix);
+    if (TAB) rowx[tid] = lfm_point_grad(rowp[tid], l, inv_l);
+  }
   double racc_d[8], racc_k[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) { racc_d[r] = 0.0; racc_k[r] = 0.0; }
@@ -194,11 +202,16 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
   const int c0 = lane * 2;
   for (int J = jt0; J <= jt1; ++J) {
     __syncthreads();
-    if (tid >= 64 && tid < 128) lfm_stage_points(colp, X, N, (int64_t)J * GT, G, theta, l, true, tid - 64, tix);
+    if (tid >= 64 && tid < 128) {
+      lfm_stage_points(colp, X, N, (int64_t)J * GT, G, theta, l, true, tid - 64, tix);
+      if (TAB) colx[tid - 64] = lfm_point_grad(colp[tid - 64], l, inv_l);
+    }
     __syncthreads();
     const int64_t j0 = (int64_t)J * GT + c0;
     const LfmPoint pc0 = colp[c0];
     const LfmPoint pc1 = colp[c0 + 1];
+    const LfmPointGrad xc0 = colx[TAB ? c0 : 0];
+    const LfmPointGrad xc1 = colx[TAB ? c0 + 1 : 0];
     const double a0 = (j0 < N) ? alpha[j0] : 0.0;
     const double a1 = (j0 + 1 < N) ? alpha[j0 + 1] : 0.0;
     double cd0 = 0.0, ck0 = 0.0, cd1 = 0.0, ck1 = 0.0;
@@ -208,12 +221,13 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
       const int64_t i = (int64_t)I * GT + r;
       if (i >= N) continue;
       const LfmPoint pr = rowp[r];
+      const LfmPointGrad xr = rowx[TAB ? r : 0];
       const double ai = alpha[i];
       const double2 sv = *reinterpret_cast<const double2*>(Sinv + i * ld + j0);
       if (j0 <= i && j0 < N) {
         const double w = (j0 == i ? 0.5 : 1.0) * (sv.x - ai * a0);
         double k, dr, dc, dl;
-        if (TAB) lfm_kxx_grad_tab(grid, pr, pc0, l, inv_l, k, dr, dc, dl);
+        if (TAB) lfm_kxx_grad_tab(grid, pr, xr, pc0, xc0, l, inv_l, k, dr, dc, dl);
         else lfm_kxx_grad(pr, pc0, l, inv_l, k, dr, dc, dl);
         racc_d[rr] += w * dr; racc_k[rr] += w * k;
         cd0 += w * dc; ck0 += w * k;
@@ -222,7 +236,7 @@ __global__ void __launch_bounds__(256, TAB ? 2 : 1) lfm_grad_contract_kernel(int
       if (j0 + 1 <= i && j0 + 1 < N) {
         const double w = (j0 + 1 == i ? 0.5 : 1.0) * (sv.y - ai * a1);
         double k, dr, dc, dl;
-        if (TAB) lfm_kxx_grad_tab(grid, pr, pc1, l, inv_l, k, dr, dc, dl);
+        if (TAB) lfm_kxx_grad_tab(grid, pr, xr, pc1, xc1, l, inv_l, k, dr, dc, dl);
         else lfm_kxx_grad(pr, pc1, l, inv_l, k, dr, dc, dl);
         racc_d[rr] += w * dr; racc_k[rr] += w * k;
         cd1 += w * dc; ck1 += w * k;

@@ -25,7 +25,7 @@ struct LfmGridWs {
   int* tidx;                  // [N]
   int* count;                 // [1]
   double* utime;              // [Tu]
-  double *A1R1, *A1R1t, *A1, *A1t, *g1, *g1t, *g2, *inv;
+  double *A1R1, *A1R1t, *Qd, *Qdt, *Rl, *Rlt, *inv;
   int64_t H;
   size_t total_doubles;
 };
@@ -50,9 +50,8 @@ static LfmGridWs grid_layout(int64_t N, int G, int64_t Tu, void* base) {
   s.utime = take((size_t)Tu);
   const size_t tab = (size_t)G * Tu * Tu;
   s.A1R1 = take(tab); s.A1R1t = take(tab);
-  s.A1 = take(tab); s.A1t = take(tab);
-  s.g1 = take(tab); s.g1t = take(tab);
-  s.g2 = take((size_t)G * Tu);
+  s.Qd = take(tab); s.Qdt = take(tab);
+  s.Rl = take(tab); s.Rlt = take(tab);
   s.inv = take((size_t)G * G);
   s.total_doubles = off;
   return s;
@@ -127,9 +126,13 @@ __global__ void __launch_bounds__(256) lfm_grid_tables_kernel(LfmGridWs w, int G
   const size_t ot = (size_t)b * per + (size_t)ib * Tu + ia;
   w.A1R1[o] = pt.A1R1; w.A1R1t[ot] = pt.A1R1;
   if (GRAD) {
-    w.A1[o] = pt.A1; w.A1t[ot] = pt.A1;
-    w.g1[o] = pt.g1; w.g1t[ot] = pt.g1;
-    if (ib == 0) w.g2[(size_t)b * Tu + ia] = pt.g2;
+    // the (gene b, u, v)-only parts of dH/dd_b and dH/dl (sim_math.cuh: LfmGrid, lfm_h_tab_grad)
+    const double u = w.utime[ia], delta = w.utime[ib] - u;
+    const double hl = 0.5 * l, hd = 0.5 * d_b, il2 = inv_l * inv_l;
+    const double Qd = (gam * l - delta) * pt.A1R1 + pt.A1 * hl * (pt.g2 - pt.g1);
+    const double Rl = gam * d_b * pt.A1R1 + pt.A1 * (pt.g1 * (-delta * il2 - hd) + pt.g2 * (-u * il2 + hd));
+    w.Qd[o] = Qd; w.Qdt[ot] = Qd;
+    w.Rl[o] = Rl; w.Rlt[ot] = Rl;
   }
 }
 
@@ -155,7 +158,7 @@ int lfm_grid_build(cudaStream_t st, int64_t N, int G, const double* X, const dou
   LFM_LAUNCHED(4);
   LFM_CUDA_OK(cudaGetLastError());
   g.tidx = w.tidx; g.count = w.count; g.Tu = (int)Tu;
-  g.A1R1 = w.A1R1; g.A1R1t = w.A1R1t; g.A1 = w.A1; g.A1t = w.A1t; g.g1 = w.g1; g.g1t = w.g1t; g.g2 = w.g2; g.inv = w.inv;
+  g.A1R1 = w.A1R1; g.A1R1t = w.A1R1t; g.Qd = w.Qd; g.Qdt = w.Qdt; g.Rl = w.Rl; g.Rlt = w.Rlt; g.inv = w.inv;
   *grid = g;
   return LFM_OK;
 }

@@ -148,43 +148,67 @@ struct LfmGrid {
   int Tu;              // leading dimension of the tables (host-side upper bound on *count); 0: no tables
   int G;
   const double* A1R1;  const double* A1R1t;
-  const double* A1;    const double* A1t;    // gradient only
-  const double* g1;    const double* g1t;    // gradient only
-  const double* g2;                          // [G][Tu]: term of (gene b, time index of a); gradient only
-  const double* inv;                         // [G][G] 1 / (d_a + d_b)
+  // gradient only: everything of dH/dd_b and dH/dl that depends on (gene b, u, v) alone, folded into ONE number each
+  // when the tables are built (grid.cu), so that the contraction kernel does a dozen flops per h-term instead of ~45:
+  //   Qd = (gam_b l - delta) A1R1 + A1 (l/2) (g2 - g1)
+  //   Rl = gam_b d_b A1R1 + A1 (g1 (-delta / l^2 - d_b/2) + g2 (-u / l^2 + d_b/2))
+  const double* Qd;    const double* Qdt;
+  const double* Rl;    const double* Rlt;
+  const double* inv;   // [G][G] 1 / (d_a + d_b)
 };
+// What a point contributes to the h-terms in which it is the "b" point (gradient only; staged beside LfmPoint):
+//   phi = e q,  rho = (t - gam l) phi - e (l/2) (g4 - g3),  sig = -gam d phi - e (g3 (-t/l^2 - d/2) + g4 d/2),  ue = t e
+struct LfmPointGrad { double phi, rho, sig, ue; };
+__device__ __forceinline__ LfmPointGrad lfm_point_grad(const LfmPoint& p, double l, double inv_l) {
+  LfmPointGrad x;
+  const double hl = 0.5 * l, hd = 0.5 * p.d, il2 = inv_l * inv_l;
+  x.phi = __dmul_rn(p.e, p.q);
+  x.rho = (p.t - p.gam * l) * x.phi - p.e * hl * (p.g4 - p.g3);
+  x.sig = -p.gam * p.d * x.phi - p.e * (p.g3 * (-p.t * il2 - hd) + p.g4 * hd);
+  x.ue = p.t * p.e;
+  return x;
+}
 // h(pa, pb) from the tables; `tr` selects the transposed copies (used for h(col, row), where the column
 // index runs along ia).
-template <bool GRAD>
-__device__ __forceinline__ void lfm_h_tab(const LfmGrid& g, const LfmPoint& pa, const LfmPoint& pb, bool tr, double l,
-                                          double inv_l, double& H, double& dH_da, double& dH_db, double& dH_dl) {
-  LfmPairTerms pt;
+__device__ __forceinline__ double lfm_h_tab(const LfmGrid& g, const LfmPoint& pa, const LfmPoint& pb, bool tr) {
   const size_t base = (size_t)pb.gene * g.Tu * g.Tu;
   const size_t off = tr ? base + (size_t)pb.ti * g.Tu + pa.ti : base + (size_t)pa.ti * g.Tu + pb.ti;
-  pt.A1R1 = (tr ? g.A1R1t : g.A1R1)[off];
-  if (GRAD) {
-    pt.A1 = (tr ? g.A1t : g.A1)[off];
-    pt.g1 = (tr ? g.g1t : g.g1)[off];
-    pt.g2 = g.g2[(size_t)pb.gene * g.Tu + pa.ti];
-  } else {
-    pt.A1 = 0.0; pt.g1 = 0.0; pt.g2 = 0.0;
-  }
-  pt.inv = g.inv[(size_t)pa.gene * g.G + pb.gene];
-  lfm_h_core<GRAD>(pa, pb, l, inv_l, pt, H, dH_da, dH_db, dH_dl);
+  const double A1R1 = (tr ? g.A1R1t : g.A1R1)[off];
+  const double E0 = pb.eg2 * g.inv[(size_t)pa.gene * g.G + pb.gene];
+  const double A2R2 = __dmul_rn(pa.e * pb.e, pb.q);
+  return E0 * (A1R1 - A2R2);
+}
+// H and its partials from the tables, regrouped (see LfmGrid): with E0 = exp(gam_b^2) / (d_a + d_b)
+//   H = E0 (A1R1 - e_a phi_b),  dH/dd_a = E0 ue_a phi_b - H inv,  dH/dd_b = E0 (Qd + e_a rho_b) - H inv,  dH/dl = E0 (Rl + e_a sig_b)
+// -- the same quantities as lfm_h_core<true> (the direct path), associated differently (agreement ~1e-15 relative).
+__device__ __forceinline__ void lfm_h_tab_grad(const LfmGrid& g, const LfmPoint& pa, const LfmPointGrad& xa, const LfmPoint& pb,
+                                               const LfmPointGrad& xb, bool tr, double& H, double& dH_da, double& dH_db,
+                                               double& dH_dl) {
+  const size_t base = (size_t)pb.gene * g.Tu * g.Tu;
+  const size_t off = tr ? base + (size_t)pb.ti * g.Tu + pa.ti : base + (size_t)pa.ti * g.Tu + pb.ti;
+  const double T1 = (tr ? g.A1R1t : g.A1R1)[off];
+  const double Q = (tr ? g.Qdt : g.Qd)[off];
+  const double R = (tr ? g.Rlt : g.Rl)[off];
+  const double inv = g.inv[(size_t)pa.gene * g.G + pb.gene];
+  const double E0 = pb.eg2 * inv;
+  H = E0 * (T1 - pa.e * xb.phi);
+  const double Hinv = H * inv;
+  dH_da = E0 * (xa.ue * xb.phi) - Hinv;
+  dH_db = E0 * (Q + pa.e * xb.rho) - Hinv;
+  dH_dl = E0 * (R + pa.e * xb.sig);
 }
 __device__ __forceinline__ double lfm_kxx_tab(const LfmGrid& g, const LfmPoint& pi, const LfmPoint& pj, double l,
                                               double inv_l) {
-  double H1, H2, u0, u1, u2;
-  lfm_h_tab<false>(g, pj, pi, true, l, inv_l, H1, u0, u1, u2);
-  lfm_h_tab<false>(g, pi, pj, false, l, inv_l, H2, u0, u1, u2);
+  const double H1 = lfm_h_tab(g, pj, pi, true);
+  const double H2 = lfm_h_tab(g, pi, pj, false);
   return pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l) * (H1 + H2);
 }
-__device__ __forceinline__ void lfm_kxx_grad_tab(const LfmGrid& g, const LfmPoint& pi, const LfmPoint& pj, double l,
-                                                 double inv_l, double& k, double& dk_drow, double& dk_dcol,
-                                                 double& dk_dl) {
+__device__ __forceinline__ void lfm_kxx_grad_tab(const LfmGrid& g, const LfmPoint& pi, const LfmPointGrad& xi, const LfmPoint& pj,
+                                                 const LfmPointGrad& xj, double l, double inv_l, double& k, double& dk_drow,
+                                                 double& dk_dcol, double& dk_dl) {
   double H1, dH1_da, dH1_db, dH1_dl, H2, dH2_da, dH2_db, dH2_dl;
-  lfm_h_tab<true>(g, pj, pi, true, l, inv_l, H1, dH1_da, dH1_db, dH1_dl);
-  lfm_h_tab<true>(g, pi, pj, false, l, inv_l, H2, dH2_da, dH2_db, dH2_dl);
+  lfm_h_tab_grad(g, pj, xj, pi, xi, true, H1, dH1_da, dH1_db, dH1_dl);
+  lfm_h_tab_grad(g, pi, xi, pj, xj, false, H2, dH2_da, dH2_db, dH2_dl);
   const double mult = pi.s * pj.s * (LFM_SQRT_PI * 0.5 * l);
   k = mult * (H1 + H2);
   dk_drow = mult * (dH1_db + dH2_da);
