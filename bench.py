@@ -323,6 +323,11 @@ def main():
                 "executed_flops_per_eval": fl.value / args.steps,
                 "launches_per_eval": nl.value / args.steps, "kernel_s_per_eval": gemm_s,
                 "kernel_share_of_step": gemm_s / prof_step_s,
+                "profiled_pass_ms_per_eval": prof_step_s * 1e3,
+                "profiled_pass_note": "the share is taken inside the PROFILED pass: stream launches with two event records per GEMM "
+                                      "launch, issued from Python -- that pass is host-launch-bound (its time per evaluation is "
+                                      "beside this note and varies with the box's host, 3.6-5.4 ms against the ~3.2 ms of a "
+                                      "graph replay), so the share moves between ~0.6 and ~0.9 while kernel_s_per_eval does not",
                 "kernel_s_per_eval_summed": lib.lfm_debug_profile_sum_ms() * 1e-3 / args.steps,
                 "note": "the factorisation launches on several streams and launches overlap: kernel_s_per_eval is the "
                         "length of the union of the launch intervals (CUDA-event timestamps), the plain sum is beside it",
