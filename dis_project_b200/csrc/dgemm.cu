@@ -285,13 +285,15 @@ __global__ void __launch_bounds__(128 * GM, (WM * WN * GM <= 16) ? 2 : 1) lfm_dg
   }
 }
 
-// ---- warp-specialised variant: cp.async.bulk (TMA unit, SASS UBLKCP) + per-stage mbarriers ----------------------------
+// ---- warp-specialised variant (opt-in, LFM_GEMM_WS = 1 / 2): cp.async.bulk (TMA unit, SASS UBLKCP) + per-stage mbarriers ------
 // The kernel above stops ALL its warps at one __syncthreads per 32-deep unit; `tools/tile_life.py` had a CTA alone on its SM
-// run its mainloop at 81-84 % of the DMMA pipe for that reason, and two co-resident CTAs of the same launch reach their
-// barriers together.  Here ONE producer warp stages the operands -- one bulk copy per operand row (256 B of a [row][k] operand,
+// run its mainloop at 81-84 % of the DMMA pipe, and two co-resident CTAs of the same launch reach their barriers together.
+// Here producer warps (two: one per operand) stage the operands -- one bulk copy per operand row (256 B of a [row][k] operand,
 // BM * 8 B of a [k][row] operand) into the same padded, conflict-free layouts, completion counted in bytes on the stage's FULL
-// mbarrier -- and the consumer warps never meet: each waits for FULL[s], runs its 8 k4-steps, and arrives on EMPTY[s]; the
-// producer refills a stage when all consumer warps have left it.  Three stages of 32 k: two units (64 k) in flight per CTA.
+// mbarrier; or, LDG = true, 16-byte cp.async with cp.async.mbarrier.arrive -- and the consumer warps never meet: each waits for
+// FULL[s], runs its 8 k4-steps, and arrives on EMPTY[s]; the producers refill a stage when all consumer warps have left it.
+// Three stages of 32 k: two units (64 k) in flight per CTA.  MEASURED SLOWER than the kernel above and therefore off by default
+// (profiles/gemm_ws_tma_r2c.md: a row-granular bulk copy costs its warp 70-80 cycles, and the barrier was not the bound).
 #define WS_BK 32
 #define WS_LDK (WS_BK + 4)   // 36 doubles = 72 banks == 8 (mod 32): the 4 rows of a half-warp's LDS.64 hit disjoint banks
 #define WS_STAGES 3
